@@ -1,0 +1,657 @@
+// gsa_api.cu -- the C ABI of libgsa_cuda.so (include/gsa_cuda.h): handle, model registry, launch logic.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+#include "gsa_internal.h"
+#include "gsa_common.cuh"
+#include "models.cuh"
+#include "sobol_design.cuh"
+#include "estimator_y.cuh"
+#include "fused_generic.cuh"
+#include "reduce_tiles.cuh"
+#include "dispatch.cuh"
+
+namespace gsa {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return GSA_ERR_CUDA;
+}
+
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return GSA_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        want = bytes;
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+        p = nullptr;
+        cudaGetLastError();
+        return fail(GSA_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    cap = want;
+    return GSA_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Joe-Kuo direction numbers (host): Bratley-Fox recurrence on the embedded table.
+// ------------------------------------------------------------------------------------------------
+extern "C" const unsigned char gsa_joe_kuo_blob[];
+extern "C" const unsigned char gsa_joe_kuo_blob_end[];
+
+const uint32_t* joe_kuo_table() { return reinterpret_cast<const uint32_t*>(gsa_joe_kuo_blob); }
+
+void direction_numbers(int dim_first, int ndim, uint32_t* V) {
+    const uint32_t* tab = joe_kuo_table();
+    for (int jj = 0; jj < ndim; ++jj) {
+        const int j = dim_first + jj;
+        uint64_t m[32];
+        if (j == 0) {
+            for (int i = 0; i < 32; ++i) m[i] = 1;
+        } else {
+            const uint32_t poly = tab[19 * j];
+            int deg = 0;
+            while ((poly >> (deg + 1)) != 0) ++deg;
+            for (int i = 0; i < deg; ++i) m[i] = tab[19 * j + 1 + i];
+            for (int i = deg; i < 32; ++i) {
+                uint64_t v = m[i - deg] ^ (m[i - deg] << deg);
+                for (int k = 1; k < deg; ++k)
+                    if ((poly >> (deg - k)) & 1u) v ^= m[i - k] << k;
+                m[i] = v;
+            }
+        }
+        for (int i = 0; i < 32; ++i) V[32 * jj + i] = (uint32_t)((m[i] << (31 - i)) & 0xFFFFFFFFull);
+    }
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+static bool is_device_or_pinned(const void* p, bool* is_device) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        *is_device = false;
+        return false;
+    }
+    *is_device = at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    return at.type != cudaMemoryTypeUnregistered;
+}
+
+// ------------------------------------------------------------------------------------------------
+// option / model validation
+// ------------------------------------------------------------------------------------------------
+static int check_opts(const gsa_sobol_opts* o) {
+    if (!o) return fail(GSA_ERR_INVALID, "opts is NULL");
+    if (o->nboot < 1) return fail(GSA_ERR_INVALID, "nboot must be >= 1 (got %d)", o->nboot);
+    if (o->ei_estimator < 0 || o->ei_estimator > 3)
+        return fail(GSA_ERR_INVALID, "unknown Ei_estimator %d (0 Homma1996, 1 Sobol2007, 2 Jansen1999, 3 Janon2014)", o->ei_estimator);
+    if (o->input_location != GSA_LOC_HOST && o->input_location != GSA_LOC_DEVICE)
+        return fail(GSA_ERR_INVALID, "input_location must be GSA_LOC_HOST or GSA_LOC_DEVICE");
+    if (o->nboot > 1 && !(o->conf_level > 0.0 && o->conf_level < 1.0))
+        return fail(GSA_ERR_INVALID, "conf_level must be in (0,1) (got %g)", o->conf_level);
+    return GSA_OK;
+}
+
+static int model_nout(int model, int np, int d, int* nout) {
+    switch (model) {
+        case GSA_MODEL_ISHIGAMI:
+            if (d < 3) return fail(GSA_ERR_INVALID, "ishigami needs d >= 3 (got %d)", d);
+            if (np != 2) return fail(GSA_ERR_INVALID, "ishigami takes 2 parameters {a, b} (got %d)", np);
+            *nout = 1;
+            return GSA_OK;
+        case GSA_MODEL_SOBOL_G:
+            if (np != d) return fail(GSA_ERR_INVALID, "sobol_g takes d parameters a[d] (got %d, d=%d)", np, d);
+            *nout = 1;
+            return GSA_OK;
+        case GSA_MODEL_LINEAR:
+            if (np < d || np % d) return fail(GSA_ERR_INVALID, "linear takes nout*d parameters W (got %d, d=%d)", np, d);
+            *nout = np / d;
+            return GSA_OK;
+        case GSA_MODEL_ISHI_LINEAR:
+            if (d < 3) return fail(GSA_ERR_INVALID, "ishi_linear needs d >= 3 (got %d)", d);
+            *nout = 2;
+            return GSA_OK;
+        default: return fail(GSA_ERR_INVALID, "unknown model id %d", model);
+    }
+}
+
+// Tiles: aim at ~2 tiles per resident CTA; a tile never straddles a replicate.
+static void choose_tiles(int64_t n, int nrep, int resident, int ts_min, int ts_max, int gran, int* ts, int* tpr) {
+    int64_t want_tpr = std::max<int64_t>(1, (2 * (int64_t)resident + nrep - 1) / std::max(nrep, 1));
+    int64_t t = (n + want_tpr - 1) / want_tpr;
+    t = (t + gran - 1) / gran * gran;
+    t = std::max<int64_t>(t, ts_min);
+    t = std::min<int64_t>(t, ts_max);
+    *ts = (int)t;
+    *tpr = (int)std::max<int64_t>(1, (n + t - 1) / t);
+}
+
+static int upload_params(gsa_handle* h, const double* params, int np) {
+    int rc = h->params.reserve(sizeof(double) * std::max(np, 1));
+    if (rc) return rc;
+    if (np > 0) {
+        bool dev;
+        is_device_or_pinned(params, &dev);
+        GSA_CUDA(cudaMemcpyAsync(h->params.p, params, sizeof(double) * np, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    }
+    return GSA_OK;
+}
+
+static int run_reduce(gsa_handle* h, int recsz, int nstat, int tpr, int rep_first, int nrep, double* partials) {
+    dim3 grid((recsz + RT_X - 1) / RT_X, nrep), block(RT_X, RT_Y);
+    reduce_tiles_kernel<<<grid, block, 0, h->stream>>>(h->tile_rec.as<double>(), partials, recsz, nstat, tpr, rep_first);
+    h->last_launches++;
+    GSA_CUDA(cudaGetLastError());
+    return GSA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2..K4 driver
+// ------------------------------------------------------------------------------------------------
+static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, const double* params, int np, const double* A,
+                         const double* B, int d, int64_t N, int64_t col0, int64_t ncols, double* partials) {
+    int rc = check_opts(o);
+    if (rc) return rc;
+    if (d < 1) return fail(GSA_ERR_INVALID, "d must be >= 1");
+    if (N < 0 || col0 < 0 || ncols < 0 || col0 + ncols > N) return fail(GSA_ERR_INVALID, "column range [%lld, %lld) outside the d x %lld design", (long long)col0, (long long)(col0 + ncols), (long long)N);
+    if (!partials) return fail(GSA_ERR_INVALID, "partials is NULL");
+    if (ncols > 0 && (!A || !B)) return fail(GSA_ERR_INVALID, "A or B is NULL");
+    int nout = 0;
+    if ((rc = model_nout(model, np, d, &nout))) return rc;
+    const bool second = o->second_order != 0;
+    const int est = o->ei_estimator;
+    const int nstat = stat_count(d, est, second), recsz = nstat * nout;
+    const int64_t n = N / o->nboot;
+
+    FusedPlan plan;
+    if ((rc = plan_fused(h, model, d, nout, np, second, est, &plan))) return rc;
+
+    h->last_launches = 0;
+    GSA_CUDA(cudaEventRecord(h->ev0, h->stream));
+    GSA_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (size_t)o->nboot * recsz, h->stream));
+    const int64_t valid_hi = std::min<int64_t>(col0 + ncols, (int64_t)o->nboot * n);
+    if (n > 0 && valid_hi > col0) {
+        if ((rc = upload_params(h, params, np))) return rc;
+        if ((rc = plan.prepare(h, params, np))) return rc;
+        TileGeom g;
+        g.n = n;
+        g.col_lo = col0;
+        g.col_hi = valid_hi;
+        g.buf_col0 = col0;
+        g.rep_first = (int)(col0 / n);
+        const int rep_last = (int)((valid_hi - 1) / n);
+        const int nrep = rep_last - g.rep_first + 1;
+        choose_tiles(n, nrep, plan.resident, plan.ts_min, plan.ts_max, plan.ts_gran, &g.ts, &g.tpr);
+        g.ntiles = nrep * g.tpr;
+        if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)g.ntiles * recsz))) return rc;
+
+        if (o->input_location == GSA_LOC_DEVICE) {
+            if ((rc = plan.launch(h, A, B, g, 0, g.ntiles))) return rc;
+        } else {
+            // Stream the host design through two device buffers: the H2D copy of chunk i+1 (copy stream)
+            // overlaps the kernel of chunk i.  Chunk boundaries are tile boundaries.
+            bool devp = false;
+            const bool pinned = is_device_or_pinned(A, &devp) && is_device_or_pinned(B, &devp);
+            const size_t col_bytes = sizeof(double) * (size_t)d;
+            const int64_t chunk_cols_target = std::max<int64_t>(g.ts, (int64_t)((96u << 20) / col_bytes));
+            int tiles_per_chunk = (int)std::max<int64_t>(1, chunk_cols_target / g.ts);
+            const size_t buf_bytes = 2 * col_bytes * (size_t)tiles_per_chunk * g.ts;
+            for (int b = 0; b < 2; ++b)
+                if ((rc = h->dev_in[b].reserve(buf_bytes))) return rc;
+            if (!pinned && h->pinned_cap < buf_bytes) {
+                for (int b = 0; b < 2; ++b) {
+                    if (h->pinned[b]) cudaFreeHost(h->pinned[b]);
+                    h->pinned[b] = nullptr;
+                }
+                h->pinned_cap = 0;
+                for (int b = 0; b < 2; ++b) GSA_CUDA(cudaMallocHost(&h->pinned[b], buf_bytes));
+                h->pinned_cap = buf_bytes;
+            }
+            int ci = 0;
+            for (int t0 = 0; t0 < g.ntiles; t0 += tiles_per_chunk, ++ci) {
+                const int t1 = std::min(g.ntiles, t0 + tiles_per_chunk), b = ci & 1;
+                int64_t c0, c1, tmp;
+                tile_range(g, t0, c0, tmp);
+                tile_range(g, t1 - 1, tmp, c1);
+                // tiles in between may be clipped to empty; take the hull of non-empty ones
+                for (int t = t0; t < t1; ++t) {
+                    int64_t a0, a1;
+                    tile_range(g, t, a0, a1);
+                    if (a1 > a0) { c0 = std::min(c0, a0); c1 = std::max(c1, a1); }
+                }
+                if (c1 <= c0) continue;
+                const size_t bytes = col_bytes * (size_t)(c1 - c0);
+                double* dA = h->dev_in[b].as<double>();
+                double* dB = dA + (size_t)d * (size_t)tiles_per_chunk * g.ts;
+                const double* hA = A + (size_t)d * (size_t)(c0 - col0);
+                const double* hB = B + (size_t)d * (size_t)(c0 - col0);
+                if (ci >= 2) {
+                    GSA_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));   // buffer free again?
+                    if (!pinned) GSA_CUDA(cudaEventSynchronize(h->ev_copy[b]));        // staging buffer drained?
+                }
+                if (pinned) {
+                    GSA_CUDA(cudaMemcpyAsync(dA, hA, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+                    GSA_CUDA(cudaMemcpyAsync(dB, hB, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+                } else {
+                    char* st = static_cast<char*>(h->pinned[b]);
+                    memcpy(st, hA, bytes);
+                    memcpy(st + bytes, hB, bytes);
+                    GSA_CUDA(cudaMemcpyAsync(dA, st, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+                    GSA_CUDA(cudaMemcpyAsync(dB, st + bytes, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+                }
+                GSA_CUDA(cudaEventRecord(h->ev_copy[b], h->copy_stream));
+                GSA_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy[b], 0));
+                TileGeom gc = g;
+                gc.buf_col0 = c0;
+                if ((rc = plan.launch(h, dA, dB, gc, t0, t1))) return rc;
+                GSA_CUDA(cudaEventRecord(h->ev_done[b], h->stream));
+            }
+        }
+        if ((rc = run_reduce(h, recsz, nstat, g.tpr, g.rep_first, nrep, partials))) return rc;
+    }
+    GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
+    return GSA_OK;
+}
+
+static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double* Y, int nout, int d, int64_t n, double* partials) {
+    int rc = check_opts(o);
+    if (rc) return rc;
+    if (d < 1 || nout < 1 || n < 0) return fail(GSA_ERR_INVALID, "bad shape: nout=%d d=%d n=%lld", nout, d, (long long)n);
+    if (!partials || (!Y && n > 0)) return fail(GSA_ERR_INVALID, "Y or partials is NULL");
+    const bool second = o->second_order != 0;
+    const int est = o->ei_estimator, step = second ? 2 * d + 2 : d + 2;
+    const int nstat = stat_count(d, est, second), recsz = nstat * nout;
+    h->last_launches = 0;
+    const double* Yd = Y;
+    const size_t ybytes = sizeof(double) * (size_t)nout * (size_t)n * step * o->nboot;
+    if (o->input_location == GSA_LOC_HOST && ybytes) {
+        if ((rc = h->ybuf.reserve(ybytes))) return rc;
+        GSA_CUDA(cudaMemcpyAsync(h->ybuf.p, Y, ybytes, cudaMemcpyHostToDevice, h->stream));
+        Yd = h->ybuf.as<double>();
+    }
+    GSA_CUDA(cudaEventRecord(h->ev0, h->stream));
+    GSA_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (size_t)o->nboot * recsz, h->stream));
+    if (n > 0) {
+        EstYArgs a;
+        a.Y = Yd;
+        a.n = n;
+        a.nout = nout; a.d = d; a.nstat = nstat; a.est = est; a.step = step;
+        a.ts = (int)std::min<int64_t>(KY_TS_MAX, (n + 31) / 32 * 32);
+        a.tpr = (int)((n + a.ts - 1) / a.ts);
+        a.ntiles = a.tpr * o->nboot;
+        if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)a.ntiles * recsz))) return rc;
+        a.tile_rec = h->tile_rec.as<double>();
+        dim3 grid(std::min(a.ntiles, h->sm_count * 8), nout);
+        if (second) estimator_y_kernel<true><<<grid, 256, 0, h->stream>>>(a);
+        else estimator_y_kernel<false><<<grid, 256, 0, h->stream>>>(a);
+        h->last_launches++;
+        GSA_CUDA(cudaGetLastError());
+        if ((rc = run_reduce(h, recsz, nstat, a.tpr, 0, o->nboot, partials))) return rc;
+    }
+    GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
+    return GSA_OK;
+}
+
+// all_points writer (fuse_designs, reference :94-108 + :116-134)
+__global__ void __launch_bounds__(256) all_points_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ P,
+                                                         int d, int64_t n, int step, int64_t total /* d * cols */) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t col = e / d;
+        const int i = (int)(e - col * d);
+        const int64_t blk = col / n, s = col - blk * n;
+        const int r = (int)(blk / step), b = (int)(blk - (int64_t)r * step);
+        const int64_t src = (int64_t)d * ((int64_t)r * n + s) + i;
+        bool fromA;
+        if (b == 0) fromA = true;
+        else if (b == 1) fromA = false;
+        else if (b < 2 + d) fromA = (i != b - 2);       // AB_k: A with row k from B
+        else fromA = (i == b - 2 - d);                  // BA_k: B with row k from A
+        P[e] = fromA ? A[src] : B[src];
+    }
+}
+
+}  // namespace gsa
+
+using namespace gsa;
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+extern "C" {
+
+int gsa_version(void) { return GSA_VERSION; }
+
+int gsa_last_error(char* buf, size_t n) {
+    if (!buf || n == 0) return GSA_ERR_INVALID;
+    snprintf(buf, n, "%s", g_err);
+    return GSA_OK;
+}
+
+int gsa_create(int device, gsa_handle** out) {
+    if (!out) return fail(GSA_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    GSA_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0) GSA_CUDA(cudaGetDevice(&device));
+    if (device >= ndev) return fail(GSA_ERR_INVALID, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    GSA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(GSA_ERR_UNSUPPORTED, "libgsa_cuda is built for sm_100a only; device %d is sm_%d%d (%s)", device, prop.major, prop.minor, prop.name);
+    DeviceGuard guard(device);
+    gsa_handle* h = new (std::nothrow) gsa_handle();
+    if (!h) return fail(GSA_ERR_NOMEM, "out of host memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+        e = cudaEventCreateWithFlags(&h->ev_copy[b], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        gsa_destroy(h);
+        return cuda_fail(e, "gsa_create");
+    }
+    h->stream = h->own_stream;
+    *out = h;
+    return GSA_OK;
+}
+
+int gsa_destroy(gsa_handle* h) {
+    if (!h) return GSA_OK;
+    {
+        DeviceGuard guard(h->device);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+        DevBuf* bufs[] = {&h->tile_rec, &h->partials, &h->params, &h->vtab, &h->lbub, &h->stage[0], &h->stage[1], &h->dev_in[0], &h->dev_in[1], &h->ybuf, &h->aux};
+        for (DevBuf* b : bufs) b->release();
+        for (int b = 0; b < 2; ++b) {
+            if (h->pinned[b]) cudaFreeHost(h->pinned[b]);
+            if (h->ev_copy[b]) cudaEventDestroy(h->ev_copy[b]);
+            if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
+        }
+        if (h->ev0) cudaEventDestroy(h->ev0);
+        if (h->ev1) cudaEventDestroy(h->ev1);
+        if (h->own_stream) cudaStreamDestroy(h->own_stream);
+        if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    }
+    delete h;
+    return GSA_OK;
+}
+
+int gsa_set_stream(gsa_handle* h, void* s) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->stream = s ? static_cast<cudaStream_t>(s) : h->own_stream;
+    return GSA_OK;
+}
+
+int gsa_synchronize(gsa_handle* h) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    DeviceGuard guard(h->device);
+    GSA_CUDA(cudaStreamSynchronize(h->stream));
+    return GSA_OK;
+}
+
+int gsa_model_lookup(const char* name, int* id) {
+    if (!name || !id) return fail(GSA_ERR_INVALID, "name or id is NULL");
+    static const struct { const char* n; int id; } tab[] = {
+        {"ishigami", GSA_MODEL_ISHIGAMI}, {"sobol_g", GSA_MODEL_SOBOL_G}, {"linear", GSA_MODEL_LINEAR},
+        {"linear_gaussian", GSA_MODEL_LINEAR}, {"ishi_linear", GSA_MODEL_ISHI_LINEAR}};
+    for (auto& t : tab)
+        if (!strcmp(t.n, name)) {
+            *id = t.id;
+            return GSA_OK;
+        }
+    return fail(GSA_ERR_INVALID, "unknown model '%s'", name);
+}
+
+int gsa_model_nout(gsa_handle*, int model_id, int nparams, int d, int* nout) {
+    if (!nout) return fail(GSA_ERR_INVALID, "nout is NULL");
+    return model_nout(model_id, nparams, d, nout);
+}
+
+int gsa_model_register_fatbin(gsa_handle*, const void*, size_t, const char*, int, int*) {
+    return fail(GSA_ERR_UNSUPPORTED, "user device models are not implemented in this build yet");
+}
+
+int gsa_sobol_nstat(const gsa_sobol_opts* o, int d, int* nstat) {
+    int rc = check_opts(o);
+    if (rc) return rc;
+    if (!nstat || d < 1) return fail(GSA_ERR_INVALID, "bad arguments");
+    *nstat = stat_count(d, o->ei_estimator, o->second_order != 0);
+    return GSA_OK;
+}
+
+int gsa_sobol_design(gsa_handle* h, int64_t n, int d, int num_mats, const double* lb, const double* ub, int64_t col0,
+                     int64_t ncols, double* const* out, int out_location) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    if (n < 1 || d < 1 || num_mats < 1 || !lb || !ub || !out) return fail(GSA_ERR_INVALID, "bad arguments to gsa_sobol_design");
+    if (col0 < 0 || ncols < 0 || col0 + ncols > n) return fail(GSA_ERR_INVALID, "column range outside [0, n)");
+    if ((int64_t)d * num_mats > 21201) return fail(GSA_ERR_INVALID, "num_mats*d = %lld exceeds the 21201 dimensions of the Joe-Kuo table", (long long)d * num_mats);
+    if (n >= ((int64_t)1 << 31)) return fail(GSA_ERR_UNSUPPORTED, "n must be < 2^31");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    const int dT = d * num_mats;
+    int rc;
+    if (h->vdims < dT) {
+        h->vhost.resize((size_t)dT * 32);
+        direction_numbers(0, dT, h->vhost.data());
+        if ((rc = h->vtab.reserve(sizeof(uint32_t) * 32 * (size_t)dT))) return rc;
+        GSA_CUDA(cudaMemcpyAsync(h->vtab.p, h->vhost.data(), sizeof(uint32_t) * 32 * (size_t)dT, cudaMemcpyHostToDevice, h->stream));
+        h->vdims = dT;
+    }
+    if ((rc = h->lbub.reserve(sizeof(double) * 2 * (size_t)d))) return rc;
+    std::vector<double> sc(2 * (size_t)d);
+    for (int i = 0; i < d; ++i) {
+        sc[i] = ub[i] - lb[i];
+        sc[d + i] = lb[i];
+    }
+    GSA_CUDA(cudaMemcpyAsync(h->lbub.p, sc.data(), sizeof(double) * 2 * d, cudaMemcpyHostToDevice, h->stream));
+    GSA_CUDA(cudaStreamSynchronize(h->stream));  // sc is a stack-lifetime staging vector
+    h->last_launches = 0;
+    uint64_t first = 1;
+    while ((first << 1) <= (uint64_t)n) first <<= 1;   // 2^floor(log2 n)
+    first += (uint64_t)col0;
+
+    // host output: generate column chunks into device scratch and copy back
+    const bool to_host = out_location == GSA_LOC_HOST;
+    int64_t chunk = ncols;
+    if (to_host) chunk = std::max<int64_t>(1, std::min<int64_t>(ncols, (int64_t)(256u << 20) / (sizeof(double) * dT)));
+    if (to_host && ncols > 0)
+        if ((rc = h->stage[0].reserve(sizeof(double) * (size_t)dT * chunk))) return rc;
+    GSA_CUDA(cudaEventRecord(h->ev0, h->stream));
+    for (int64_t cc = 0; cc < ncols; cc += chunk) {
+        const int64_t nc = std::min(chunk, ncols - cc);
+        for (int m0 = 0; m0 < num_mats; m0 += 8) {
+            const int nm = std::min(8, num_mats - m0);
+            DesignArgs a;
+            a.V = h->vtab.as<uint32_t>() + (size_t)32 * d * m0;
+            a.scale = h->lbub.as<double>();
+            a.lb = h->lbub.as<double>() + d;
+            for (int m = 0; m < 8; ++m) a.out[m] = nullptr;
+            for (int m = 0; m < nm; ++m)
+                a.out[m] = to_host ? h->stage[0].as<double>() + (size_t)(m0 + m) * d * nc : out[m0 + m] + (size_t)d * cc;
+            a.first = first + (uint64_t)cc;
+            a.ncols = nc;
+            a.d = d;
+            a.dT = d * nm;
+            // P*dT threads ~ 2 full waves of 2048 threads per SM
+            const int64_t want = (int64_t)h->sm_count * 2048 * 2;
+            int lp = 0;
+            while (((int64_t)1 << lp) * a.dT < want && ((int64_t)1 << lp) < nc) ++lp;
+            a.lp = lp;
+            const int64_t threads = ((int64_t)1 << lp) * a.dT;
+            sobol_design_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, h->stream>>>(a);
+            h->last_launches++;
+            GSA_CUDA(cudaGetLastError());
+        }
+        if (to_host) {
+            for (int m = 0; m < num_mats; ++m)
+                GSA_CUDA(cudaMemcpyAsync(out[m] + (size_t)d * cc, h->stage[0].as<double>() + (size_t)m * d * nc, sizeof(double) * (size_t)d * nc,
+                                         cudaMemcpyDeviceToHost, h->stream));
+            GSA_CUDA(cudaStreamSynchronize(h->stream));
+        }
+    }
+    GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
+    return GSA_OK;
+}
+
+int gsa_sobol_partials(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams, const double* A,
+                       const double* B, int d, int64_t N, int64_t col0, int64_t ncols, double* partials_dev) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    return partials_impl(h, opts, model_id, params, nparams, A, B, d, N, col0, ncols, partials_dev);
+}
+
+int gsa_sobol_partials_y(gsa_handle* h, const gsa_sobol_opts* opts, const double* Y, int nout, int d, int64_t n, double* partials_dev) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    return partials_y_impl(h, opts, Y, nout, d, n, partials_dev);
+}
+
+int gsa_sobol_finalize(const gsa_sobol_opts* opts, const double* partials_host, int nout, int d, int64_t n, gsa_sobol_result* out) {
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    if (!partials_host || !out || nout < 1 || d < 1) return fail(GSA_ERR_INVALID, "bad arguments to gsa_sobol_finalize");
+    return finalize_host(*opts, partials_host, nout, d, n, out);
+}
+
+static int fetch_and_finalize(gsa_handle* h, const gsa_sobol_opts* opts, int nout, int d, int64_t n, gsa_sobol_result* out) {
+    const int nstat = stat_count(d, opts->ei_estimator, opts->second_order != 0);
+    std::vector<double> host((size_t)opts->nboot * nout * nstat);
+    GSA_CUDA(cudaMemcpyAsync(host.data(), h->partials.p, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, h->stream));
+    GSA_CUDA(cudaStreamSynchronize(h->stream));
+    return finalize_host(*opts, host.data(), nout, d, n, out);
+}
+
+int gsa_sobol_run(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams, const double* A,
+                  const double* B, int d, int64_t N, gsa_sobol_result* out) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    if (!out) return fail(GSA_ERR_INVALID, "result is NULL");
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    int nout = 0;
+    if (d < 1) return fail(GSA_ERR_INVALID, "d must be >= 1");
+    if ((rc = model_nout(model_id, nparams, d, &nout))) return rc;
+    const int nstat = stat_count(d, opts->ei_estimator, opts->second_order != 0);
+    if ((rc = h->partials.reserve(sizeof(double) * (size_t)opts->nboot * nout * nstat))) return rc;
+    if ((rc = partials_impl(h, opts, model_id, params, nparams, A, B, d, N, 0, N, h->partials.as<double>()))) return rc;
+    return fetch_and_finalize(h, opts, nout, d, N / opts->nboot, out);
+}
+
+int gsa_sobol_analyze_y(gsa_handle* h, const gsa_sobol_opts* opts, const double* Y, int nout, int d, int64_t n, gsa_sobol_result* out) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    if (!out) return fail(GSA_ERR_INVALID, "result is NULL");
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    if (d < 1 || nout < 1) return fail(GSA_ERR_INVALID, "bad shape");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    const int nstat = stat_count(d, opts->ei_estimator, opts->second_order != 0);
+    if ((rc = h->partials.reserve(sizeof(double) * (size_t)opts->nboot * nout * nstat))) return rc;
+    if ((rc = partials_y_impl(h, opts, Y, nout, d, n, h->partials.as<double>()))) return rc;
+    return fetch_and_finalize(h, opts, nout, d, n, out);
+}
+
+int gsa_sobol_all_points(gsa_handle* h, const gsa_sobol_opts* opts, const double* A, const double* B, int d, int64_t N, double* P,
+                         int p_location) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    if (d < 1 || N < 0 || !A || !B || !P) return fail(GSA_ERR_INVALID, "bad arguments to gsa_sobol_all_points");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    const int64_t n = N / opts->nboot;
+    const int step = opts->second_order ? 2 * d + 2 : d + 2;
+    const int64_t total = (int64_t)d * n * step * opts->nboot;
+    if (total == 0) return GSA_OK;
+    const double *dA = A, *dB = B;
+    const size_t in_bytes = sizeof(double) * (size_t)d * (size_t)(n * opts->nboot);
+    if (opts->input_location == GSA_LOC_HOST) {
+        for (int b = 0; b < 2; ++b)
+            if ((rc = h->dev_in[b].reserve(in_bytes))) return rc;
+        GSA_CUDA(cudaMemcpyAsync(h->dev_in[0].p, A, in_bytes, cudaMemcpyHostToDevice, h->stream));
+        GSA_CUDA(cudaMemcpyAsync(h->dev_in[1].p, B, in_bytes, cudaMemcpyHostToDevice, h->stream));
+        dA = h->dev_in[0].as<double>();
+        dB = h->dev_in[1].as<double>();
+    }
+    double* dP = P;
+    if (p_location == GSA_LOC_HOST) {
+        if ((rc = h->ybuf.reserve(sizeof(double) * (size_t)total))) return rc;
+        dP = h->ybuf.as<double>();
+    }
+    h->last_launches = 0;
+    GSA_CUDA(cudaEventRecord(h->ev0, h->stream));
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
+    all_points_kernel<<<grid, 256, 0, h->stream>>>(dA, dB, dP, d, n, step, total);
+    h->last_launches++;
+    GSA_CUDA(cudaGetLastError());
+    GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
+    if (p_location == GSA_LOC_HOST) {
+        GSA_CUDA(cudaMemcpyAsync(P, dP, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+        GSA_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return GSA_OK;
+}
+
+int gsa_last_timing(gsa_handle* h, float* ms, int* launches) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    DeviceGuard guard(h->device);
+    GSA_CUDA(cudaEventSynchronize(h->ev1));
+    float t = 0.f;
+    GSA_CUDA(cudaEventElapsedTime(&t, h->ev0, h->ev1));
+    if (ms) *ms = t;
+    if (launches) *launches = h->last_launches;
+    return GSA_OK;
+}
+
+}  // extern "C"

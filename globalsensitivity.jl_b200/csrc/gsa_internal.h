@@ -1,0 +1,55 @@
+// gsa_internal.h -- host-side internals of libgsa_cuda (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gsa_cuda.h"
+
+namespace gsa {
+
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define GSA_CUDA(call)                                                \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return ::gsa::cuda_fail(e__, #call);  \
+    } while (0)
+
+// growable device scratch
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+int finalize_host(const gsa_sobol_opts& o, const double* partials, int nout, int d, int64_t n, gsa_sobol_result* out);
+double host_norm_quantile(double p);
+
+// Joe-Kuo table embedded in the library (directions_blob.S)
+const uint32_t* joe_kuo_table();
+void direction_numbers(int dim_first, int ndim, uint32_t* V /* ndim x 32 */);
+
+}  // namespace gsa
+
+struct gsa_handle {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    std::mutex mu;
+    gsa::DevBuf tile_rec, partials, params, vtab, lbub, stage[2], dev_in[2], ybuf, aux;
+    void* pinned[2] = {nullptr, nullptr};
+    size_t pinned_cap = 0;
+    std::vector<uint32_t> vhost;  // cached direction numbers [vdims][32]
+    int vdims = 0;
+    float last_ms = 0.f;
+    int last_launches = 0;
+};

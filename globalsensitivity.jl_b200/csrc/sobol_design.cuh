@@ -1,0 +1,54 @@
+// sobol_design.cuh -- K1: unrandomised Sobol design matrices, bit-exact with the reference's generator
+// (QuasiMonteCarlo.generate_design_matrices -> Sobol.jl; call sites src/sobol_sensitivity.jl:408-413,
+// README.md:55-56, test/sobol_method.jl:29-30).
+//
+// Integer work + an HBM write stream (8 B per coordinate).  Layout = Julia's d x n column-major, i.e.
+// the d coordinates of a sample are contiguous, so consecutive THREADS take consecutive coordinates of
+// the flattened (point, dim) index and every warp store is one contiguous 256-byte run.  A thread owns
+// one dimension j and walks points p, p+P, p+2P, ... (P a power of two): in Gray-code order the Sobol
+// integer of index q+P differs from that of q by exactly two direction numbers,
+//     x(q+P) = x(q) ^ V[j][lp-1] ^ V[j][lp + ctz(~(q >> lp))]      (lp = log2 P; first term absent if lp=0)
+// so after one random-access start (popcount(gray(q)) XORs) each further point costs 2 XORs.
+#pragma once
+#include "gsa_common.cuh"
+
+namespace gsa {
+
+struct DesignArgs {
+    const uint32_t* V;      // [dT][32] direction numbers, MSB aligned
+    const double* scale;    // [d]  ub - lb   (rounded once, as Julia's `ub .- lb`)
+    const double* lb;       // [d]
+    double* out[8];         // up to 8 matrices per launch, each d x ncols (local columns)
+    uint64_t first;         // 0-based sequence index of local column 0
+    int64_t ncols;
+    int d, dT, lp;          // dT = dims handled by this launch (<= 8*d), P = 1 << lp
+};
+
+__global__ void __launch_bounds__(256) sobol_design_kernel(DesignArgs a) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t P = (int64_t)1 << a.lp;
+    if (f >= P * a.dT) return;
+    const int64_t p0 = f / a.dT;
+    const int j = (int)(f - p0 * a.dT);
+    if (p0 >= a.ncols) return;
+    const int m = j / a.d, i = j - m * a.d;
+    const uint32_t* Vj = a.V + 32 * j;
+    const double sc = __ldg(a.scale + i), lo = __ldg(a.lb + i);
+    double* out = a.out[m] + i;
+
+    uint64_t q = a.first + (uint64_t)p0;
+    uint32_t x = 0;
+    for (uint64_t g = q ^ (q >> 1); g; g &= g - 1) x ^= __ldg(Vj + (__ffsll((long long)g) - 1));
+    const uint32_t vlow = a.lp > 0 ? __ldg(Vj + a.lp - 1) : 0u;
+
+    for (int64_t p = p0; p < a.ncols; p += P) {
+        const double u = (double)x * 0x1p-32;                       // exact
+        out[(size_t)a.d * p] = __dadd_rn(__dmul_rn(sc, u), lo);     // (ub-lb)*u + lb, mul and add rounded separately
+        const uint64_t h = q >> a.lp;
+        const int c = __ffsll((long long)~h) - 1;                   // trailing ones of h
+        x ^= vlow ^ __ldg(Vj + min(a.lp + c, 31));               // (clamp only matters for the unused last update)
+        q += (uint64_t)P;
+    }
+}
+
+}  // namespace gsa

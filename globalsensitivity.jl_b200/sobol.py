@@ -1,0 +1,379 @@
+"""Host-side mirror of the reference's Sobol interface (src/sobol_sensitivity.jl) over libgsa_cuda.so.
+
+Reference API                                            here
+---------------------------------------------------------------------------------------------------
+Sobol(; order=[0,1], nboot=1, conf_level=0.95)  :77-83   Sobol(order=(0, 1), nboot=1, conf_level=0.95)
+SobolResult (S1, S1_Conf_Int, S2, S2_Conf_Int,  :85-92   SobolResult (same field names and order)
+             ST, ST_Conf_Int)
+gsa(f, ::Sobol, A, B; batch, Ei_estimator)      :110     gsa(f, Sobol(...), A, B, batch=True, Ei_estimator=...)
+gsa(f, ::Sobol, p_range; samples, ...)          :407     gsa(f, Sobol(...), p_range, samples=...)
+gsa_sobol_all_y_analysis(method, all_y, d, n,   :169     gsa_sobol_all_y_analysis(method, all_y, d, n, Ei_estimator)
+                         Ei_estimator, ...)
+QuasiMonteCarlo.generate_design_matrices(n, lb, ub,      generate_design_matrices(n, lb, ub, num_mats=2)
+                         SobolSample(), num_mats)
+
+`f` is a DeviceModel (a model evaluated inside the fused CUDA kernel: "ishigami", "sobol_g", "linear", ...) or,
+as in the reference, any Python callable: with batch=True it receives the d x cols matrix of all design
+points (built on the GPU) and returns a vector / nout x cols matrix; the estimator kernels then run on it.
+
+Shapes follow Julia: designs are (d, N) with one sample per column; results are S1/ST (d,) or (nout, d),
+S2 (d, d) or (d, d, nout); the *_Conf_Int fields are None when nboot == 1.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any, Callable, Optional, Sequence, Union
+
+import numpy as np
+
+from . import _lib
+from ._lib import EI_ESTIMATORS, LOC_DEVICE, LOC_HOST, SobolOpts, SobolResultC, check, lib
+
+
+@dataclass
+class Sobol:
+    """`struct Sobol <: GSAMethod` (reference :77-83).  Only `2 in order` matters: S1 and ST are always computed."""
+    order: Sequence[int] = (0, 1)
+    nboot: int = 1
+    conf_level: float = 0.95
+
+
+@dataclass
+class SobolResult:
+    """`mutable struct SobolResult` (reference :85-92) -- same fields, same order."""
+    S1: Any
+    S1_Conf_Int: Any
+    S2: Any
+    S2_Conf_Int: Any
+    ST: Any
+    ST_Conf_Int: Any
+
+
+@dataclass
+class DeviceModel:
+    """A model evaluated on the GPU inside the fused kernel; replaces the Julia closure `f`.
+
+    name    "ishigami" {a, b} | "sobol_g" a[d] | "linear"/"linear_gaussian" W (nout x d) | "ishi_linear"
+    params  array of parameters (a 2-D W is flattened column-major, as Julia would store it)
+    """
+    name: str
+    params: Any = field(default_factory=lambda: np.zeros(0))
+
+    def __post_init__(self):
+        self.params = np.ascontiguousarray(np.asarray(self.params, dtype=np.float64).ravel(order="F"))
+        mid = C.c_int()
+        check(lib().gsa_model_lookup(self.name.encode(), C.byref(mid)))
+        self.model_id = mid.value
+
+    def nout(self, d: int) -> int:
+        n = C.c_int()
+        check(lib().gsa_model_nout(None, self.model_id, self.params.size, d, C.byref(n)))
+        return n.value
+
+
+class GsaHandle:
+    """Owns a gsa_handle (one CUDA device, its stream and scratch buffers)."""
+
+    def __init__(self, device: int = -1):
+        self._h = C.c_void_p()
+        check(lib().gsa_create(device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().gsa_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def ptr(self):
+        return self._h
+
+    def set_stream(self, cuda_stream: int = 0):
+        check(lib().gsa_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        check(lib().gsa_synchronize(self._h))
+
+    def last_timing(self):
+        ms, n = C.c_float(), C.c_int()
+        check(lib().gsa_last_timing(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+_default = {}
+
+
+def default_handle(device: int = -1) -> GsaHandle:
+    if device < 0:
+        try:
+            import torch
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        except ImportError:
+            device = 0
+    if device not in _default:
+        _default[device] = GsaHandle(device)
+    return _default[device]
+
+
+# ---------------------------------------------------------------------------------------------------
+# array plumbing
+# ---------------------------------------------------------------------------------------------------
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class _Mat:
+    """A d x N design in Julia layout (the d values of a sample contiguous): pointer + location."""
+
+    def __init__(self, x):
+        if _is_torch(x):
+            import torch
+            if x.dim() != 2:
+                raise ValueError("design matrices must be 2-D (d, N)")
+            t = x.detach()
+            if t.dtype != torch.float64:
+                t = t.to(torch.float64)
+            tt = t.t()                         # (N, d) view
+            if not tt.is_contiguous():
+                tt = tt.contiguous()
+            self.keep = tt
+            self.d, self.N = int(x.shape[0]), int(x.shape[1])
+            self.ptr = tt.data_ptr()
+            self.loc = LOC_DEVICE if tt.is_cuda else LOC_HOST
+            self.device = tt.device.index if tt.is_cuda else None
+        else:
+            a = np.asarray(x)
+            if a.ndim != 2:
+                raise ValueError("design matrices must be 2-D (d, N)")
+            a = np.asfortranarray(a, dtype=np.float64)
+            self.keep = a
+            self.d, self.N = a.shape
+            self.ptr = a.ctypes.data
+            self.loc = LOC_HOST
+            self.device = None
+
+
+def _opts(method: Sobol, Ei_estimator, loc: int) -> SobolOpts:
+    est = Ei_estimator.lstrip(":") if isinstance(Ei_estimator, str) else Ei_estimator
+    if est not in EI_ESTIMATORS:
+        # the reference fails late with a BoundsError on an unknown symbol (:202-236); we fail early
+        raise ValueError(f"unknown Ei_estimator {Ei_estimator!r}; expected one of {sorted(EI_ESTIMATORS)}")
+    return SobolOpts(int(2 in method.order), int(method.nboot), float(method.conf_level), EI_ESTIMATORS[est], loc)
+
+
+def _alloc_result(nout: int, d: int, nboot: int, second: bool, multi: bool):
+    z = lambda *s: np.zeros(s, dtype=np.float64, order="F")
+    s1, st = z(nout, d), z(nout, d)
+    s1c, stc = (z(nout, d), z(nout, d)) if nboot > 1 else (None, None)
+    s2 = z(d, d, nout) if second else None
+    s2c = z(d, d, nout) if second and nboot > 1 else None
+    p = lambda a: None if a is None else a.ctypes.data_as(_lib._dp)
+    rc = SobolResultC(p(s1), p(s1c), p(s2), p(s2c), p(st), p(stc))
+
+    def finish() -> SobolResult:
+        v = (lambda a: None if a is None else (a if multi else a[0].copy()))
+        m = (lambda a: None if a is None else (a if multi else a[:, :, 0].copy()))
+        return SobolResult(v(s1), v(s1c), m(s2), m(s2c), v(st), v(stc))
+
+    return rc, finish, (s1, s1c, s2, s2c, st, stc)
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1
+# ---------------------------------------------------------------------------------------------------
+def generate_design_matrices(n: int, lb, ub, num_mats: int = 2, *, device: bool = False, col0: int = 0,
+                             ncols: Optional[int] = None, handle: Optional[GsaHandle] = None):
+    """QuasiMonteCarlo.generate_design_matrices(n, lb, ub, SobolSample(), num_mats) on the GPU, bit-exact.
+
+    Returns `num_mats` matrices of shape (d, ncols): NumPy (Fortran order) by default, or, with device=True,
+    CUDA torch tensors that view the Julia layout (strides (1, d)).  `col0`/`ncols` select a column range
+    (used to generate one rank's shard in place)."""
+    h = handle or default_handle()
+    lb = np.ascontiguousarray(lb, dtype=np.float64)
+    ub = np.ascontiguousarray(ub, dtype=np.float64)
+    if lb.shape != ub.shape or lb.ndim != 1:
+        raise ValueError("lb and ub must be vectors of equal length")
+    d = lb.size
+    ncols = n - col0 if ncols is None else ncols
+    ptrs = (C.c_void_p * num_mats)()
+    if device:
+        import torch
+        mats = [torch.empty((ncols, d), dtype=torch.float64, device="cuda") for _ in range(num_mats)]
+        for m in range(num_mats):
+            ptrs[m] = mats[m].data_ptr()
+        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        try:
+            check(lib().gsa_sobol_design(h.ptr, n, d, num_mats, lb.ctypes.data, ub.ctypes.data, col0, ncols, ptrs, LOC_DEVICE))
+        finally:
+            h.set_stream(0)
+        return [m.t() for m in mats]
+    mats = [np.empty((d, ncols), dtype=np.float64, order="F") for _ in range(num_mats)]
+    for m in range(num_mats):
+        ptrs[m] = mats[m].ctypes.data
+    check(lib().gsa_sobol_design(h.ptr, n, d, num_mats, lb.ctypes.data, ub.ctypes.data, col0, ncols, ptrs, LOC_HOST))
+    return mats
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2..K4
+# ---------------------------------------------------------------------------------------------------
+def gsa_sobol_all_y_analysis(method: Sobol, all_y, d: int, n: int, Ei_estimator="Jansen1999", *,
+                             handle: Optional[GsaHandle] = None) -> SobolResult:
+    """gsa_sobol_all_y_analysis (reference :169-405) on the GPU.  `all_y`: vector (scalar model) or nout x cols matrix
+    (NumPy or torch, host or device), blocks per replicate [A | B | AB_1..AB_d (| BA_1..BA_d)]."""
+    h = handle or default_handle()
+    second = 2 in method.order
+    step = 2 * d + 2 if second else d + 2
+    if _is_torch(all_y):
+        import torch
+        t = all_y.detach().to(torch.float64)
+        multi = t.dim() == 2
+        tt = (t.t().contiguous() if multi else t.contiguous())      # (cols, nout): Julia layout
+        nout = int(t.shape[0]) if multi else 1
+        cols = int(t.shape[-1])
+        ptr, loc, keep = tt.data_ptr(), (LOC_DEVICE if tt.is_cuda else LOC_HOST), tt
+    else:
+        a = np.asarray(all_y, dtype=np.float64)
+        multi = a.ndim == 2
+        a = np.asfortranarray(a) if multi else np.ascontiguousarray(a)
+        nout = a.shape[0] if multi else 1
+        cols = a.shape[-1]
+        ptr, loc, keep = a.ctypes.data, LOC_HOST, a
+    if cols != method.nboot * n * step:
+        raise ValueError(f"all_y has {cols} columns, expected nboot*n*step = {method.nboot * n * step}")
+    o = _opts(method, Ei_estimator, loc)
+    rc, finish, _ = _alloc_result(nout, d, method.nboot, second, multi)
+    check(lib().gsa_sobol_analyze_y(h.ptr, C.byref(o), ptr, nout, d, n, C.byref(rc)))
+    del keep
+    return finish()
+
+
+def _all_points(h: GsaHandle, method: Sobol, A: _Mat, B: _Mat, want_torch: bool):
+    second = 2 in method.order
+    n = A.N // method.nboot
+    cols = method.nboot * n * (2 * A.d + 2 if second else A.d + 2)
+    o = _opts(method, "Jansen1999", A.loc)
+    if want_torch:
+        import torch
+        P = torch.empty((cols, A.d), dtype=torch.float64, device="cuda")
+        check(lib().gsa_sobol_all_points(h.ptr, C.byref(o), A.ptr, B.ptr, A.d, A.N, P.data_ptr(), LOC_DEVICE))
+        h.synchronize()
+        return P.t()
+    P = np.empty((A.d, cols), dtype=np.float64, order="F")
+    check(lib().gsa_sobol_all_points(h.ptr, C.byref(o), A.ptr, B.ptr, A.d, A.N, P.ctypes.data, LOC_HOST))
+    return P
+
+
+def gsa(f, method: Sobol, A, B=None, *, batch: bool = False, Ei_estimator="Jansen1999", samples: Optional[int] = None,
+        handle: Optional[GsaHandle] = None) -> SobolResult:
+    """gsa(f, method::Sobol, A, B; batch, Ei_estimator) (reference :110-168), or, when `B is None` and `samples` is
+    given, gsa(f, method::Sobol, p_range; samples) (:407-417) with the design generated on the GPU."""
+    if not isinstance(method, Sobol):
+        raise TypeError("only the Sobol method is implemented by this package")
+    h = handle or default_handle()
+    if B is None:
+        if samples is None:
+            raise TypeError("gsa(f, Sobol(), p_range; samples) needs `samples`")
+        p_range = A
+        lb = [float(p[0]) for p in p_range]
+        ub = [float(p[1]) for p in p_range]
+        dev = isinstance(f, DeviceModel)
+        AB = generate_design_matrices(samples, lb, ub, 2 * method.nboot, device=dev, handle=h)     # :408-413
+        if dev:
+            import torch
+            A = torch.cat([m.t() for m in AB[:method.nboot]], dim=0).t()                           # :414-415
+            B = torch.cat([m.t() for m in AB[method.nboot:]], dim=0).t()
+        else:
+            A = np.concatenate(AB[:method.nboot], axis=1)
+            B = np.concatenate(AB[method.nboot:], axis=1)
+        return gsa(f, method, A, B, batch=batch, Ei_estimator=Ei_estimator, handle=h)
+
+    Am, Bm = _Mat(A), _Mat(B)
+    if (Am.d, Am.N) != (Bm.d, Bm.N):
+        raise ValueError("A and B must have the same shape")
+    if Am.loc != Bm.loc:
+        raise ValueError("A and B must both be on the host or both on the device")
+    d, N = Am.d, Am.N
+    second = 2 in method.order
+
+    if isinstance(f, DeviceModel):
+        nout = f.nout(d)
+        o = _opts(method, Ei_estimator, Am.loc)
+        rc, finish, _ = _alloc_result(nout, d, method.nboot, second, nout > 1)
+        check(lib().gsa_sobol_run(h.ptr, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size,
+                                  Am.ptr, Bm.ptr, d, N, C.byref(rc)))
+        return finish()
+
+    if not callable(f):
+        raise TypeError("f must be a DeviceModel or a callable")
+    # closure path: fused design on the GPU (fuse_designs :94-108), user code evaluates it, estimator kernels reduce it
+    n = N // method.nboot
+    on_dev = Am.loc == LOC_DEVICE
+    P = _all_points(h, method, Am, Bm, on_dev)
+    if batch:
+        all_y = f(P)                                                                               # :143
+    else:
+        cols = P.shape[1]
+        ys = [np.asarray(f(P[:, i].cpu().numpy() if on_dev else P[:, i]), dtype=np.float64) for i in range(cols)]   # :151
+        all_y = np.stack(ys, axis=-1) if ys and ys[0].ndim else np.asarray(ys, dtype=np.float64)
+        if all_y.ndim > 2:
+            all_y = all_y.reshape(-1, cols)
+    return gsa_sobol_all_y_analysis(method, all_y, d, n, Ei_estimator, handle=h)
+
+
+# ---------------------------------------------------------------------------------------------------
+# sharded form (one process per GPU): local partial sums -> all-reduce -> finalize
+# ---------------------------------------------------------------------------------------------------
+def shard_columns(N: int, rank: int, world: int):
+    """Contiguous column range [col0, col0+ncols) of rank `rank`."""
+    base, rem = divmod(N, world)
+    col0 = rank * base + min(rank, rem)
+    return col0, base + (1 if rank < rem else 0)
+
+
+def nstat(method: Sobol, d: int, Ei_estimator="Jansen1999") -> int:
+    o = _opts(method, Ei_estimator, LOC_HOST)
+    k = C.c_int()
+    check(lib().gsa_sobol_nstat(C.byref(o), d, C.byref(k)))
+    return k.value
+
+
+def sobol_partials(f: DeviceModel, method: Sobol, A_local, B_local, N: int, col0: int, *, Ei_estimator="Jansen1999",
+                   handle: Optional[GsaHandle] = None, out=None):
+    """Per-replicate partial sums of this rank's column shard, as a CUDA torch tensor (nboot, nout, nstat).
+    The sums are additive: `torch.distributed.all_reduce(partials)` then `sobol_finalize`.  Runs on torch's
+    current CUDA stream; asynchronous."""
+    import torch
+    h = handle or default_handle()
+    Am, Bm = _Mat(A_local), _Mat(B_local)
+    d = Am.d
+    nout = f.nout(d)
+    o = _opts(method, Ei_estimator, Am.loc)
+    ns = nstat(method, d, Ei_estimator)
+    if out is None:
+        out = torch.empty((method.nboot, nout, ns), dtype=torch.float64, device="cuda")
+    h.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        check(lib().gsa_sobol_partials(h.ptr, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size, Am.ptr, Bm.ptr,
+                                       d, N, col0, Am.N, out.data_ptr()))
+    finally:
+        h.set_stream(0)
+    return out
+
+
+def sobol_finalize(method: Sobol, partials, d: int, N: int, *, Ei_estimator="Jansen1999") -> SobolResult:
+    """(:318-404) summed partials (nboot, nout, nstat) -> SobolResult.  Pure host code."""
+    if _is_torch(partials):
+        partials = partials.detach().cpu().numpy()
+    p = np.ascontiguousarray(partials, dtype=np.float64)
+    nboot, nout, _ = p.shape
+    o = _opts(method, Ei_estimator, LOC_HOST)
+    rc, finish, _ = _alloc_result(nout, d, nboot, 2 in method.order, nout > 1)
+    check(lib().gsa_sobol_finalize(C.byref(o), p.ctypes.data, nout, d, N // nboot, C.byref(rc)))
+    return finish()

@@ -1,0 +1,161 @@
+/*
+ * gsa_cuda.h -- C ABI of libgsa_cuda.so: the B200 (sm_100a) implementation of the Sobol path of
+ * SciML/GlobalSensitivity.jl,   gsa(f, Sobol(order, nboot, conf_level), A, B; batch=true).
+ *
+ * The reference has no FFI for this path (it is pure Julia); the seam this library replaces is the
+ * Julia method   gsa(f, method::Sobol, A::AbstractMatrix, B::AbstractMatrix; batch, Ei_estimator)
+ * (reference src/sobol_sensitivity.jl:110-168) and its internal analysis function
+ * gsa_sobol_all_y_analysis (:169-405).  INTEGRATION.md shows the `ccall` shim a maintainer adds.
+ *
+ * Conventions
+ *   - every entry point returns an int status (GSA_OK == 0); gsa_last_error() gives the message of
+ *     the last failure on the calling thread.  No C++ exception crosses this boundary.
+ *   - all matrices use Julia's column-major layout verbatim:
+ *         A[i + d*c]            parameter i of sample (column) c, d values of a sample contiguous
+ *         Y[o + nout*c]         output o of column c
+ *         S1/ST[o + nout*k]     (a length-d vector when nout == 1)
+ *         S2[k + d*j + d*d*o]   only k<j is non-zero (reference :194-200, :256-264)
+ *   - counts that scale with the number of samples are int64_t.
+ *   - the caller owns every buffer it passes; the library keeps no caller pointer after a call returns.
+ *   - a handle is bound to one CUDA device and serialises its own calls (one in flight per handle).
+ */
+#ifndef GSA_CUDA_H
+#define GSA_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSA_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define GSA_API __attribute__((visibility("default")))
+#else
+#define GSA_API
+#endif
+
+/* status codes */
+enum {
+    GSA_OK = 0,
+    GSA_ERR_INVALID = 1,     /* bad argument (message says which) */
+    GSA_ERR_CUDA = 2,        /* a CUDA runtime/driver call failed */
+    GSA_ERR_UNSUPPORTED = 3, /* valid request outside what this build implements */
+    GSA_ERR_NOMEM = 4,
+    GSA_ERR_NCCL = 5
+};
+
+/* Ei_estimator of the reference (src/sobol_sensitivity.jl:112, :202-236) */
+enum { GSA_EI_HOMMA1996 = 0, GSA_EI_SOBOL2007 = 1, GSA_EI_JANSEN1999 = 2, GSA_EI_JANON2014 = 3 };
+
+/* where a data pointer lives */
+enum { GSA_LOC_HOST = 0, GSA_LOC_DEVICE = 1 };
+
+/* built-in device models (gsa_model_lookup names) */
+enum {
+    GSA_MODEL_ISHIGAMI = 0,    /* params {a, b};  y = sin x1 + a sin^2 x2 + b x3^4 sin x1          */
+    GSA_MODEL_SOBOL_G = 1,     /* params a[d];    y = prod_i (|4 x_i - 2| + a_i) / (1 + a_i)       */
+    GSA_MODEL_LINEAR = 2,      /* params W[nout x d] column-major; y = W x  (multi-output)         */
+    GSA_MODEL_ISHI_LINEAR = 3, /* the 2-output model of reference test/sobol_method.jl:146-158     */
+    GSA_MODEL_USER_BASE = 1000 /* ids returned by gsa_model_register_fatbin                        */
+};
+
+typedef struct gsa_handle gsa_handle; /* opaque */
+
+/* mirrors `struct Sobol` (reference :77-83) + the call's keyword arguments (:112) */
+typedef struct gsa_sobol_opts {
+    int second_order;   /* 2 in method.order                                   */
+    int nboot;          /* replicates; n = N / nboot columns each (:116-127)   */
+    double conf_level;  /* used when nboot > 1 (:359)                          */
+    int ei_estimator;   /* GSA_EI_*; the reference default is Jansen1999       */
+    int input_location; /* GSA_LOC_* of A, B (or Y)                            */
+} gsa_sobol_opts;
+
+/* mirrors `SobolResult` (reference :85-92); caller-allocated, a NULL member is skipped.
+ * The *_conf_int members are written only when nboot > 1, S2* only when second_order. */
+typedef struct gsa_sobol_result {
+    double* S1;          /* nout*d   */
+    double* S1_conf_int; /* nout*d   */
+    double* S2;          /* d*d*nout */
+    double* S2_conf_int; /* d*d*nout */
+    double* ST;          /* nout*d   */
+    double* ST_conf_int; /* nout*d   */
+} gsa_sobol_result;
+
+/* ---- library / handle ------------------------------------------------------------------------ */
+GSA_API int gsa_version(void);
+/* copies the calling thread's last error message (NUL-terminated, truncated to n) */
+GSA_API int gsa_last_error(char* buf, size_t n);
+/* device < 0: use the calling thread's current CUDA device */
+GSA_API int gsa_create(int device, gsa_handle** out);
+GSA_API int gsa_destroy(gsa_handle* h);
+/* all work of the handle is issued on this CUDA stream (a cudaStream_t); NULL = handle-owned stream */
+GSA_API int gsa_set_stream(gsa_handle* h, void* cuda_stream);
+/* block until the handle's stream is idle */
+GSA_API int gsa_synchronize(gsa_handle* h);
+
+/* ---- device-model registry (replaces the Julia closure `f`) ------------------------------------ */
+GSA_API int gsa_model_lookup(const char* name, int* model_id);
+/* number of outputs of a model for given (nparams, d); replaces `all_y isa AbstractMatrix` (:144) */
+GSA_API int gsa_model_nout(gsa_handle* h, int model_id, int nparams, int d, int* nout);
+/* Link a user model into the fused kernel.  `image` is a fatbin/cubin/PTX/LTO-IR image built with
+ * `nvcc -rdc=true` for sm_100a that defines
+ *     extern "C" __device__ void <symbol>(const double* x, int d, const double* p, int np, double* y, int nout);
+ * The linked module is cached in the handle.  Returns an id >= GSA_MODEL_USER_BASE. */
+GSA_API int gsa_model_register_fatbin(gsa_handle* h, const void* image, size_t len, const char* symbol, int nout,
+                              int* model_id);
+
+/* ---- K1: unrandomised Sobol A/B design --------------------------------------------------------- */
+/* Replaces QuasiMonteCarlo.generate_design_matrices(n, lb, ub, SobolSample(), num_mats) (reference
+ * call sites src/sobol_sensitivity.jl:408-413, README.md:55-56, test/sobol_method.jl:29-30): one
+ * (num_mats*d)-dimensional Gray-code Sobol sequence (Joe-Kuo 21201 table), first emitted 0-based index
+ * 2^floor(log2 n), split by rows into num_mats matrices of d x n, scaled (ub-lb)*u + lb.
+ * Writes columns [col0, col0+ncols) of every matrix: out[m] has d*ncols doubles (m < num_mats);
+ * `out` is an array of num_mats pointers, all in `out_location`.  Bit-exact. */
+GSA_API int gsa_sobol_design(gsa_handle* h, int64_t n, int d, int num_mats, const double* lb, const double* ub,
+                     int64_t col0, int64_t ncols, double* const* out, int out_location);
+
+/* ---- K2..K4: the path ---------------------------------------------------------------------------- */
+/* Doubles per (replicate, output) sufficient-statistics record for these options. */
+GSA_API int gsa_sobol_nstat(const gsa_sobol_opts* opts, int d, int* nstat);
+
+/* gsa(model, Sobol(...), A, B; batch=true)  (:110-149 + :169-405) on one GPU.  A, B are d x N. */
+GSA_API int gsa_sobol_run(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams,
+                  const double* A, const double* B, int d, int64_t N, gsa_sobol_result* out);
+
+/* Sharded form (one process per GPU).  This rank holds columns [col0, col0+ncols) of the d x N design
+ * (A, B point at its first local column).  Fills `partials` -- nboot*nout*nstat doubles in DEVICE memory,
+ * zero where this shard has no samples -- with per-replicate sums that are ADDITIVE across shards:
+ * all-reduce (sum) them over ranks, then call gsa_sobol_finalize.  Asynchronous on the handle's stream. */
+GSA_API int gsa_sobol_partials(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params,
+                       int nparams, const double* A, const double* B, int d, int64_t N, int64_t col0,
+                       int64_t ncols, double* partials_dev);
+
+/* Same sums from a precomputed model output `Y` = f(all_points), nout x (nboot*n*step), block order
+ * [A | B | AB_1..AB_d (| BA_1..BA_d)] per replicate (:105-107, :181-190): the estimator-only kernel. */
+GSA_API int gsa_sobol_partials_y(gsa_handle* h, const gsa_sobol_opts* opts, const double* Y, int nout, int d,
+                         int64_t n, double* partials_dev);
+
+/* (:318-404) partial sums (HOST memory, nboot*nout*nstat) -> SobolResult.  n = N / nboot. Pure host code. */
+GSA_API int gsa_sobol_finalize(const gsa_sobol_opts* opts, const double* partials_host, int nout, int d, int64_t n,
+                       gsa_sobol_result* out);
+
+/* gsa_sobol_all_y_analysis (:169-405) on a host or device `Y`: partials_y + finalize. */
+GSA_API int gsa_sobol_analyze_y(gsa_handle* h, const gsa_sobol_opts* opts, const double* Y, int nout, int d, int64_t n,
+                        gsa_sobol_result* out);
+
+/* fuse_designs (:94-108) + replicate concatenation (:116-134) written to DEVICE/HOST memory, for callers
+ * that still evaluate their own closure: P is d x (nboot*n*step). */
+GSA_API int gsa_sobol_all_points(gsa_handle* h, const gsa_sobol_opts* opts, const double* A, const double* B, int d,
+                         int64_t N, double* P, int p_location);
+
+/* device time (ms, CUDA events on the handle's stream) of the last partials / design call, and the
+ * number of kernels it launched; for bench.py's roofline line. */
+GSA_API int gsa_last_timing(gsa_handle* h, float* kernel_ms, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSA_CUDA_H */

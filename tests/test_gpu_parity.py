@@ -1,0 +1,250 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical inputs.
+
+Tolerance (SURVEY 8 / BASELINE.md): indices |delta| <= 1e-12 * max(1, |ref|); Sobol points bit-exact."""
+import numpy as np
+import pytest
+
+import gsa_loader
+import gsa_ref
+import sobol_oracle as so
+from conftest import parity_err
+
+pytestmark = pytest.mark.gpu
+g = gsa_loader.load()
+
+TOL = 1e-12
+FIELDS = ("S1", "ST", "S2", "S1_Conf_Int", "ST_Conf_Int", "S2_Conf_Int")
+
+
+def assert_parity(res, ref, tol=TOL, what=""):
+    for f in FIELDS:
+        a, b = getattr(res, f), getattr(ref, f)
+        assert (a is None) == (b is None), (f, what)
+        if a is not None:
+            assert np.shape(a) == np.shape(b), (f, what, np.shape(a), np.shape(b))
+            e = parity_err(a, b)
+            assert e <= tol, (f, what, e)
+
+
+# ------------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("n,d,num_mats", [(4, 4, 1), (8, 2, 1), (5, 3, 2), (1000, 3, 2), (600000, 4, 2), (4097, 100, 2),
+                                           (300, 7, 40), (1, 2, 2), (65536, 1, 2)])
+def test_design_bit_exact(n, d, num_mats):
+    rng = np.random.default_rng(n + d)
+    lb = -rng.random(d) * 3
+    ub = lb + rng.random(d) * 5 + 0.1
+    got = g.generate_design_matrices(n, lb, ub, num_mats)
+    want = gsa_ref.sobol_design(n, lb, ub, num_mats)
+    for m in range(num_mats):
+        assert got[m].shape == (d, n)
+        assert np.array_equal(got[m], want[m]), (m, np.abs(got[m] - want[m]).max())
+
+
+def test_design_golden_points(golden):
+    k = golden["sobol_points_kat"]
+    assert np.array_equal(g.generate_design_matrices(4, np.zeros(4), np.ones(4), 1)[0], np.array(k["n4_dim4"]))
+    assert np.array_equal(g.generate_design_matrices(8, np.zeros(2), np.ones(2), 1)[0], np.array(k["n8_dim2"]))
+    A, B = g.generate_design_matrices(600000, -np.pi * np.ones(4), np.pi * np.ones(4))
+    assert np.array_equal(A[:, 0], np.array(k["n600000_A_col1"])) and np.array_equal(B[:, 0], np.array(k["n600000_B_col1"]))
+
+
+def test_design_device_shard_and_far_indices():
+    import torch
+    n, d = (1 << 26), 100          # BASELINE config 5 geometry; only a window of columns is generated
+    lb, ub = np.zeros(d), np.ones(d)
+    col0, ncols = (1 << 26) - 5000, 5000
+    A, B = g.generate_design_matrices(n, lb, ub, 2, device=True, col0=col0, ncols=ncols)
+    assert A.shape == (d, ncols) and A.is_cuda
+    wA, wB = gsa_ref.sobol_design(n, lb, ub, 2, col0=col0, ncols=ncols)
+    assert np.array_equal(A.cpu().numpy(), wA) and np.array_equal(B.cpu().numpy(), wB)
+    # against SciPy's independent generator at index 2^26 + col0
+    from scipy.stats import qmc
+    sp = qmc.Sobol(2 * d, scramble=False, bits=32)
+    sp.fast_forward((1 << 26) + col0)
+    pts = sp.random(16).T
+    assert np.array_equal(A.cpu().numpy()[:, :16], pts[:d]) and np.array_equal(B.cpu().numpy()[:, :16], pts[d:])
+
+
+# ------------------------------------------------------------------------------------------------ K2..K4
+def test_reference_goldens_on_gpu(golden, ishigami_design):
+    """The reference's own literal vectors (test/sobol_method.jl:41-45, :55-71) through the CUDA path."""
+    A, B = ishigami_design
+    ishi = g.DeviceModel("ishigami", [7.0, 0.1])
+    r = g.gsa(ishi, g.Sobol(order=[0, 1, 2]), A, B, batch=True)
+    assert np.abs(r.S2 - np.array(golden["ishigami_S2_order012"]["value"])).max() < 1e-13
+    assert np.abs(r.S1 - np.array(golden["ishigami_S1_atol1e-4"]["value"])).max() < 1e-4
+    assert np.abs(r.ST - np.array(golden["ishigami_ST_atol1e-4"]["value"])).max() < 1e-4
+    assert r.S1_Conf_Int is None and r.S2_Conf_Int is None
+    r = g.gsa(ishi, g.Sobol(order=[0, 1, 2], nboot=20), A, B, batch=True)
+    assert np.abs(r.S1_Conf_Int - np.array(golden["ishigami_nboot20_S1_Conf_Int"]["value"])).max() < 1e-13
+    assert np.abs(r.ST_Conf_Int - np.array(golden["ishigami_nboot20_ST_Conf_Int"]["value"])).max() < 1e-13
+    assert np.abs(r.S2_Conf_Int - np.array(golden["ishigami_nboot20_S2_Conf_Int"]["value"])).max() < 1e-13
+    lin = g.DeviceModel("linear", np.array([[7.0, 0.1, 0.0, 0.0]]))
+    r = g.gsa(lin, g.Sobol(), A, B, batch=True)
+    want = np.array(golden["linear_S1_ST_atol1e-4"]["value"])
+    assert np.abs(r.S1[0] - want).max() < 1e-4 and np.abs(r.ST[0] - want).max() < 1e-4
+
+
+@pytest.mark.parametrize("est", so.EI_ESTIMATORS)
+@pytest.mark.parametrize("nboot", [1, 20])
+def test_ishigami_all_estimators(ishigami_design, est, nboot):
+    A, B = ishigami_design
+    ref = gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=(0, 1, 2), nboot=nboot, Ei_estimator=est)
+    res = g.gsa(g.DeviceModel("ishigami", [7.0, 0.1]), g.Sobol(order=[0, 1, 2], nboot=nboot), A, B, batch=True, Ei_estimator=est)
+    assert_parity(res, ref, what=(est, nboot))
+
+
+def test_ci_properties_issue_181(ishigami_design):
+    """test/sobol_method.jl:74-105."""
+    A, B = ishigami_design
+    ishi = g.DeviceModel("ishigami", [7.0, 0.1])
+    res = {c: g.gsa(ishi, g.Sobol(order=[0, 1, 2], nboot=20, conf_level=c), A, B, batch=True) for c in (0.8, 0.95, 0.99)}
+    for f in ("S1", "ST", "S2"):
+        assert np.array_equal(getattr(res[0.8], f), getattr(res[0.95], f)) and np.array_equal(getattr(res[0.95], f), getattr(res[0.99], f))
+    z = {c: so.norm_quantile((1 + c) / 2) for c in res}
+    for f in ("S1_Conf_Int", "ST_Conf_Int", "S2_Conf_Int"):
+        a, b, c = (getattr(res[k], f) for k in (0.8, 0.95, 0.99))
+        assert np.all(a <= b) and np.all(b <= c) and not np.array_equal(a, b)
+        assert np.allclose(a / z[0.8], b / z[0.95], rtol=1e-13, atol=0) and np.allclose(a / z[0.8], c / z[0.99], rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("d,N,nboot,second", [(8, 1 << 16, 1, True), (8, 50000, 7, True), (3, 1000, 1, False), (13, 4099, 3, False),
+                                               (40, 3001, 2, True), (100, 2000, 1, False), (128, 700, 1, False), (1, 999, 1, True)])
+def test_sobol_g(d, N, nboot, second):
+    a = np.array(([0.0, 1.0, 4.5, 9.0] + [99.0] * d)[:d])
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    order = (0, 1, 2) if second else (0, 1)
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, order=order, nboot=nboot)
+    res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(order=order, nboot=nboot), A, B, batch=True)
+    assert_parity(res, ref, what=(d, N, nboot, second))
+
+
+@pytest.mark.parametrize("est", so.EI_ESTIMATORS)
+def test_multi_output(ishigami_design, est):
+    """res.S1[out, :] layout (test/sobol_method.jl:160-175); S2 is d x d x nout."""
+    A, B = ishigami_design
+    A, B = A[:, :100001], B[:, :100001]
+    ref = gsa_ref.gsa_sobol("ishi_linear", [0.0], A, B, order=(0, 1, 2), nboot=3, Ei_estimator=est)
+    res = g.gsa(g.DeviceModel("ishi_linear"), g.Sobol(order=[0, 1, 2], nboot=3), A, B, batch=True, Ei_estimator=est)
+    assert res.S1.shape == (2, 4) and res.S2.shape == (4, 4, 2) and res.S2_Conf_Int.shape == (4, 4, 2)
+    assert_parity(res, ref, what=est)
+    W = np.arange(1, 16, dtype=np.float64).reshape(3, 5) / 7.0
+    A, B = gsa_ref.sobol_design(20000, -np.ones(5), np.ones(5) * 2)
+    ref = gsa_ref.gsa_sobol("linear", W, A, B, order=(0, 1, 2), Ei_estimator=est)
+    res = g.gsa(g.DeviceModel("linear", W), g.Sobol(order=[0, 1, 2]), A, B, batch=True, Ei_estimator=est)
+    assert_parity(res, ref, what=("linear", est))
+
+
+def test_device_inputs_and_torch(ishigami_design):
+    import torch
+    A, B = ishigami_design
+    ref = gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=(0, 1, 2), nboot=4)
+    At, Bt = torch.from_numpy(np.ascontiguousarray(A)).cuda(), torch.from_numpy(np.ascontiguousarray(B)).cuda()   # plain (d, N) row-major tensors
+    res = g.gsa(g.DeviceModel("ishigami", [7.0, 0.1]), g.Sobol(order=[0, 1, 2], nboot=4), At, Bt, batch=True)
+    assert_parity(res, ref)
+    # pinned host tensors go through the streamed (chunked H2D) path
+    Ap, Bp = torch.from_numpy(np.ascontiguousarray(A.T)).pin_memory().t(), torch.from_numpy(np.ascontiguousarray(B.T)).pin_memory().t()
+    res = g.gsa(g.DeviceModel("ishigami", [7.0, 0.1]), g.Sobol(order=[0, 1, 2], nboot=4), Ap, Bp, batch=True)
+    assert_parity(res, ref)
+
+
+def test_edge_cases():
+    ishi = g.DeviceModel("ishigami", [7.0, 0.1])
+    lb, ub = -np.pi * np.ones(3), np.pi * np.ones(3)
+    # N not a multiple of nboot: trailing columns silently dropped (:118)
+    A, B = gsa_ref.sobol_design(1048583, lb, ub)
+    ref = gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=(0, 1, 2), nboot=1000)
+    res = g.gsa(ishi, g.Sobol(order=[0, 1, 2], nboot=1000), A, B, batch=True)
+    assert_parity(res, ref)
+    # tiny designs
+    for N, nboot in ((2, 1), (5, 2), (33, 1)):
+        A, B = gsa_ref.sobol_design(N, lb, ub)
+        ref = gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=(0, 1, 2), nboot=nboot)
+        res = g.gsa(ishi, g.Sobol(order=[0, 1, 2], nboot=nboot), A, B, batch=True)
+        assert_parity(res, ref, tol=1e-11, what=(N, nboot))
+    # nboot > N  =>  n = 0  =>  NaNs, as in the reference (SURVEY 8(b) "Errors")
+    A, B = gsa_ref.sobol_design(3, lb, ub)
+    res = g.gsa(ishi, g.Sobol(nboot=5), A, B, batch=True)
+    assert np.all(np.isnan(res.S1)) and np.all(np.isnan(res.ST))
+    with pytest.raises(ValueError):
+        g.gsa(ishi, g.Sobol(), A, B[:, :2], batch=True)
+    with pytest.raises(g.GsaError, match="ishigami needs d >= 3"):
+        g.gsa(ishi, g.Sobol(), A[:2], B[:2], batch=True)
+
+
+# ------------------------------------------------------------------------------------------------ K3 (estimator on Y)
+@pytest.mark.parametrize("est", so.EI_ESTIMATORS)
+@pytest.mark.parametrize("nboot,second", [(1, False), (1, True), (6, True)])
+def test_analyze_y_scalar(est, nboot, second):
+    d, N = 6, 30011
+    a = np.array([0.0, 0.5, 3.0, 9.0, 99.0, 99.0])
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    order = (0, 1, 2) if second else (0, 1)
+    P = gsa_ref.all_points(A, B, nboot, second)
+    Y = gsa_ref.model_batch("sobol_g", a, P)
+    ref = gsa_ref.analyze_y(Y, d, N // nboot, order=order, nboot=nboot, Ei_estimator=est)
+    res = g.gsa_sobol_all_y_analysis(g.Sobol(order=order, nboot=nboot), Y, d, N // nboot, est)
+    assert_parity(res, ref, what=(est, nboot, second))
+
+
+def test_analyze_y_multi_output_and_device():
+    import torch
+    d, N, nboot = 4, 20001, 3
+    A, B = gsa_ref.sobol_design(N, -np.pi * np.ones(d), np.pi * np.ones(d))
+    P = gsa_ref.all_points(A, B, nboot, True)
+    Y = gsa_ref.model_batch("ishi_linear", [0.0], P)           # (2, cols)
+    ref = gsa_ref.analyze_y(Y, d, N // nboot, order=(0, 1, 2), nboot=nboot)
+    res = g.gsa_sobol_all_y_analysis(g.Sobol(order=[0, 1, 2], nboot=nboot), Y, d, N // nboot)
+    assert res.S1.shape == (2, d) and res.S2.shape == (d, d, 2)
+    assert_parity(res, ref)
+    res = g.gsa_sobol_all_y_analysis(g.Sobol(order=[0, 1, 2], nboot=nboot), torch.from_numpy(Y).cuda(), d, N // nboot)
+    assert_parity(res, ref)
+
+
+def test_closure_path_and_all_points():
+    """An arbitrary (Python) closure with batch=true: fuse_designs on the GPU + estimator kernels."""
+    d, N, nboot = 4, 5003, 2
+    A, B = gsa_ref.sobol_design(N, -np.pi * np.ones(d), np.pi * np.ones(d))
+    seen = {}
+
+    def f(X):
+        seen["X"] = np.array(X)
+        return so.ishigami_batch(X)
+
+    res = g.gsa(f, g.Sobol(order=[0, 1, 2], nboot=nboot), A, B, batch=True)
+    assert np.array_equal(seen["X"], so.all_points(A, B, nboot, True))          # bit-exact copy semantics
+    ref = so.gsa_sobol(so.ishigami_batch, A, B, order=(0, 1, 2), nboot=nboot)
+    assert_parity(res, ref)
+    res = g.gsa(lambda x: so.ishigami_batch(x[:, None])[0], g.Sobol(), A[:, :200], B[:, :200])     # batch=false (:151)
+    ref = so.gsa_sobol(so.ishigami_batch, A[:, :200], B[:, :200])
+    assert_parity(res, ref)
+
+
+def test_p_range_entry():
+    """gsa(f, Sobol(nboot), p_range; samples) (:407-417): a 2*nboot*d-dimensional design."""
+    p_range = [[-np.pi, np.pi]] * 3
+    ref = so.gsa_sobol_p_range(so.ishigami_batch, p_range, 4000, order=(0, 1, 2), nboot=5)
+    res = g.gsa(g.DeviceModel("ishigami", [7.0, 0.1]), g.Sobol(order=[0, 1, 2], nboot=5), p_range, samples=4000, batch=True)
+    assert_parity(res, ref)
+    res = g.gsa(so.ishigami_batch, g.Sobol(order=[0, 1, 2], nboot=5), p_range, samples=4000, batch=True)
+    assert_parity(res, ref)
+
+
+# ------------------------------------------------------------------------------------------------ K5 (sharding)
+def test_sharded_partials_are_additive():
+    import torch
+    d, N, nboot = 8, 100003, 3
+    a = np.array([0.0, 1.0, 4.5, 9.0, 99.0, 99.0, 99.0, 99.0])
+    model, method = g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2], nboot=nboot)
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, order=(0, 1, 2), nboot=nboot)
+    total = None
+    for rank in range(4):
+        c0, nc = g.shard_columns(N, rank, 4)
+        # each "rank" generates its own shard on the device (K1 is random-access)
+        Al, Bl = g.generate_design_matrices(N, np.zeros(d), np.ones(d), 2, device=True, col0=c0, ncols=nc)
+        p = g.sobol_partials(model, method, Al, Bl, N, c0)
+        total = p.clone() if total is None else total + p
+    torch.cuda.synchronize()
+    res = g.sobol_finalize(method, total, d, N)
+    assert_parity(res, ref)
