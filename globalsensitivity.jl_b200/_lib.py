@@ -57,7 +57,7 @@ SIGNATURES = {
     "gsa_sobol_finalize": [_op, _vp, _i, _i, _i64, _rp],
     "gsa_sobol_analyze_y": [_vp, _op, _vp, _i, _i, _i64, _rp],
     "gsa_sobol_all_points": [_vp, _op, _vp, _vp, _i, _i64, _vp, _i],
-    "gsa_last_timing": [_vp, C.POINTER(C.c_float), _ip],
+    "gsa_last_timing": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _ip],
 }
 
 _lib = None

@@ -1,13 +1,16 @@
 // dispatch.cuh -- picks the fused K2+K3 kernel for (model, d, nout, options) and launches it.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 #include "gsa_internal.h"
 #include "fused_generic.cuh"
+#include "fused_product.cuh"
 
 namespace gsa {
 
-enum { PLAN_GENERIC = 0 };
+enum { PLAN_GENERIC = 0, PLAN_PRODUCT = 1 };
 
 struct FusedPlan {
     int kind = PLAN_GENERIC;
@@ -18,7 +21,9 @@ struct FusedPlan {
     int resident = 148, ts_min = 256, ts_max = 1 << 20, ts_gran = 32;
     const void* kernel = nullptr;
 
-    int prepare(gsa_handle*, const double*, int) { return GSA_OK; }
+    int prod_T = 0, prod_CPL = 0;
+
+    int prepare(gsa_handle* h, const double* params, int np);
     int launch(gsa_handle* h, const double* A, const double* B, const TileGeom& g, int t0, int t1);
 };
 
@@ -60,23 +65,117 @@ static int plan_generic(gsa_handle* h, FusedPlan* p) {
     return GSA_OK;
 }
 
+// ---- product-form (Sobol G) fast path -------------------------------------------------------------
+using ProductKernel = void (*)(ProductArgs);
+static const int kProdCpl[] = {1, 2, 3, 4, 6, 8, 10, 13};
+
+template <int T>
+static ProductKernel product_kernel_T(int cpl) {
+    switch (cpl) {
+        case 8: return fused_product_kernel<T, 8>;
+        case 10: return fused_product_kernel<T, 10>;
+        case 13: return fused_product_kernel<T, 13>;
+        default: return nullptr;
+    }
+}
+static ProductKernel product_kernel_for(int T, int cpl) {
+    switch (T) {
+        case 1:
+            switch (cpl) {
+                case 1: return fused_product_kernel<1, 1>;
+                case 2: return fused_product_kernel<1, 2>;
+                case 3: return fused_product_kernel<1, 3>;
+                case 4: return fused_product_kernel<1, 4>;
+                case 6: return fused_product_kernel<1, 6>;
+                default: return product_kernel_T<1>(cpl);
+            }
+        case 2: return product_kernel_T<2>(cpl);
+        case 4: return product_kernel_T<4>(cpl);
+        case 8: return product_kernel_T<8>(cpl);
+        case 16: return product_kernel_T<16>(cpl);
+        case 32: return product_kernel_T<32>(cpl);
+        default: return nullptr;
+    }
+}
+
+static bool product_shape(int d, int* T, int* cpl) {
+    int t = 1;
+    const char* env = getenv("GSA_PRODUCT_T");   // tuning knob: force the lanes-per-sample
+    if (env && atoi(env) > 0) t = atoi(env);
+    for (; t <= 32; t <<= 1) {
+        const int need = (d + t - 1) / t;
+        if (need > 13) continue;
+        for (int c : kProdCpl)
+            if (c >= need && product_kernel_for(t, c)) {
+                *T = t;
+                *cpl = c;
+                return true;
+            }
+    }
+    return false;
+}
+
+static int plan_product(gsa_handle* h, FusedPlan* p) {
+    p->kind = PLAN_PRODUCT;
+    p->kernel = (const void*)product_kernel_for(p->prod_T, p->prod_CPL);
+    p->threads = PROD_THREADS;
+    const int slots = p->prod_T * p->prod_CPL;
+    p->smem = sizeof(double) * (2 * slots + (PROD_THREADS / 32) * (2 * slots + 8));
+    if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    int nb = 0;
+    GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));
+    p->resident = std::max(1, nb) * h->sm_count;
+    p->ts_min = p->ts_gran = PROD_THREADS / p->prod_T;
+    return GSA_OK;
+}
+
 static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool second, int est, FusedPlan* p) {
     p->model = model; p->d = d; p->nout = nout; p->np = np; p->second = second; p->est = est;
     p->nstat = stat_count(d, est, second);
+    const char* force = getenv("GSA_FORCE_GENERIC");   // testing knob: always take the generic kernel
+    const bool generic_only = force && atoi(force) != 0;
+    if (!generic_only && model == GSA_MODEL_SOBOL_G && !second && est == GSA_EI_JANSEN1999 && product_shape(d, &p->prod_T, &p->prod_CPL))
+        return plan_product(h, p);
     return plan_generic(h, p);
 }
 
 inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, const TileGeom& g, int t0, int t1) {
     if (t1 <= t0) return GSA_OK;
     const int grid = std::min(t1 - t0, resident);
+    GSA_CUDA(cudaEventRecord(h->evk0, h->stream));
     if (kind == PLAN_GENERIC) {
         GenericArgs a;
         a.A = A; a.B = B; a.params = h->params.as<double>(); a.tile_rec = h->tile_rec.as<double>();
         a.g = g; a.d = d; a.np = np; a.nout = nout; a.nstat = nstat; a.est = est; a.t_begin = t0; a.t_end = t1;
         ((GenericKernel)kernel)<<<grid, threads, smem, h->stream>>>(a);
     }
+    else if (kind == PLAN_PRODUCT) {
+        ProductArgs a;
+        a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = h->tile_rec.as<double>();
+        a.g = g; a.d = d; a.nstat = nstat; a.t_begin = t0; a.t_end = t1;
+        ((ProductKernel)kernel)<<<grid, threads, smem, h->stream>>>(a);
+    }
+    GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
+    h->kernel_timed = true;
     h->last_launches++;
     GSA_CUDA(cudaGetLastError());
+    return GSA_OK;
+}
+
+inline int FusedPlan::prepare(gsa_handle* h, const double* params, int np_) {
+    if (kind == PLAN_PRODUCT) {
+        // g_k(x) = (|4x-2| + a_k)/(1 + a_k) = |x - 0.5| * 4/(1+a_k) + a_k/(1+a_k)
+        std::vector<double> c(2 * (size_t)d);
+        for (int k = 0; k < d; ++k) {
+            c[2 * k] = 4.0 / (1.0 + params[k]);
+            c[2 * k + 1] = params[k] / (1.0 + params[k]);
+        }
+        int rc = h->aux.reserve(sizeof(double) * c.size());
+        if (rc) return rc;
+        GSA_CUDA(cudaMemcpyAsync(h->aux.p, c.data(), sizeof(double) * c.size(), cudaMemcpyHostToDevice, h->stream));
+        GSA_CUDA(cudaStreamSynchronize(h->stream));   // c is a stack-lifetime staging vector
+    }
+    (void)np_;
     return GSA_OK;
 }
 

@@ -1,0 +1,177 @@
+// fused_product.cuh -- K2+K3 for PRODUCT-FORM models  f(x) = prod_k g_k(x_k)  (Sobol G-function), S1/ST.
+//
+// For such models  f(AB_k) = g_k(B_k) * prod_{j != k} g_j(A_j), so all d+2 model values of a sample cost
+// O(d) instead of O(d^2): one pass of prefix products, one of suffix products (no division -- g may be 0).
+// This is what makes BASELINE config 5 (d = 100, N = 2^26) HBM-bound (16*d bytes per sample, A and B read once)
+// instead of FP64-bound (SURVEY 7 "hard parts").
+//
+// Mapping: T lanes (a power of two) cooperate on one sample; lane t owns coordinates k = t + T*i, i < CPL, so
+// the T lanes of a group read T consecutive doubles of the sample's row (full 32-byte sectors, no staging
+// needed) and everything else lives in registers:
+//     gA[i], gB[i]           factor values of the lane's coordinates
+//     others = prod of the OTHER lanes' A-products   (xor butterfly, log2 T shuffles; also yields yA, yB)
+//     yAB_k  = (others * prod_{i'<i} gA[i']) * gB[i] * prod_{i'>i} gA[i']
+//     V[i] += yB (yAB_k - yA)        (reference src/sobol_sensitivity.jl:192)
+//     E[i] += (yA - yAB_k)^2         (:213, Jansen1999)
+// Accumulators stay in registers for the whole tile; one butterfly + shared-memory combine per tile, in a fixed
+// order (bitwise reproducible).  The AB_k matrices of fuse_designs (:94-108) never exist.
+#pragma once
+#include "gsa_common.cuh"
+
+namespace gsa {
+
+struct ProductArgs {
+    const double* A;
+    const double* B;
+    const double2* coef;  // [d] (c1_k, c0_k): g_k(x) = |x - 0.5| * c1_k + c0_k,  c1 = 4/(1+a_k), c0 = a_k/(1+a_k)
+    double* tile_rec;     // [ntiles][nstat]
+    TileGeom g;
+    int d, nstat, t_begin, t_end;
+};
+
+constexpr int PROD_THREADS = 128;  // ~160 registers/thread at CPL = 13: three CTAs (12 warps) per SM
+
+template <int T, int CPL>
+__global__ void __launch_bounds__(PROD_THREADS) fused_product_kernel(ProductArgs a) {
+    constexpr int NW = PROD_THREADS / 32;
+    constexpr int SLOTS = T * CPL;       // padded coordinate count
+    constexpr int RED = 2 * SLOTS + 8;   // per-warp reduction record: V[SLOTS], E[SLOTS], 4 dd pairs
+    extern __shared__ double smem_p[];
+    double2* scoef = reinterpret_cast<double2*>(smem_p);  // [SLOTS]
+    double* sred = smem_p + 2 * SLOTS;                     // [NW][RED]
+    const int d = a.d;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & (T - 1);
+    const int grp = threadIdx.x / T;  // sample group within the CTA
+    for (int i = threadIdx.x; i < SLOTS; i += PROD_THREADS) scoef[i] = i < d ? a.coef[i] : make_double2(0.0, 1.0);
+    __syncthreads();
+
+    for (int tile = a.t_begin + blockIdx.x; tile < a.t_end; tile += gridDim.x) {
+        int64_t c0, c1;
+        tile_range(a.g, tile, c0, c1);
+        double V[CPL], E[CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) V[i] = E[i] = 0.0;
+        // double-double sums of y, y^2.  T >= 2: lane t==0 carries yA in (sA1, sA2), lane t==1 carries yB there.
+        // T == 1: the single lane carries yA in (sA1, sA2) and yB in (sB1, sB2).
+        dd sA1{0.0, 0.0}, sA2{0.0, 0.0}, sB1{0.0, 0.0}, sB2{0.0, 0.0};
+
+        for (int64_t s = c0 + grp; s < c1; s += PROD_THREADS / T) {
+            const double* as = a.A + (size_t)(s - a.g.buf_col0) * d + t;
+            const double* bs = a.B + (size_t)(s - a.g.buf_col0) * d + t;
+            double gA[CPL], gB[CPL], P[CPL];
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                // padded coordinates (k >= d) re-read coordinate 0 of the row and get coef (0, 1), i.e. g = 1
+                const int off = (t + T * i) < d ? T * i : -t;
+                gA[i] = ldg_stream(as + off);
+                gB[i] = ldg_stream(bs + off);
+            }
+            double LA = 1.0, LB = 1.0;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                const double2 c = scoef[t + T * i];
+                gA[i] = fma(fabs(gA[i] - 0.5), c.x, c.y);
+                gB[i] = fma(fabs(gB[i] - 0.5), c.x, c.y);
+                LA *= gA[i];
+                LB *= gB[i];
+            }
+            // butterfly over the T lanes of the group: product of the others (A) and the totals (A, B)
+            double others = 1.0, yA = LA, yB = LB;
+#pragma unroll
+            for (int o = 1; o < T; o <<= 1) {
+                const double pa = __shfl_xor_sync(0xffffffffu, yA, o);
+                const double pb = __shfl_xor_sync(0xffffffffu, yB, o);
+                others *= pa;
+                yA *= pa;
+                yB *= pb;
+            }
+            // prefix products seeded with the other lanes' product, then the suffix sweep
+            double run = others;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                P[i] = run;
+                run *= gA[i];
+            }
+            double suf = 1.0;
+#pragma unroll
+            for (int i = CPL - 1; i >= 0; --i) {
+                const double yAB = P[i] * (gB[i] * suf);
+                suf *= gA[i];
+                const double df = yAB - yA;
+                V[i] = fma(yB, df, V[i]);  // :192
+                E[i] = fma(df, df, E[i]);  // :213
+            }
+            if (T == 1) {
+                dd_add(sA1, yA); dd_add_sq(sA2, yA);
+                dd_add(sB1, yB); dd_add_sq(sB2, yB);
+            } else {
+                const double y = t == 0 ? yA : yB;  // lanes >= 2 accumulate a copy that is never used
+                dd_add(sA1, y); dd_add_sq(sA2, y);
+            }
+        }
+
+        // ---- tile flush: butterfly over the groups of the warp (lanes with equal t), then across warps ----
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+#pragma unroll
+            for (int o = T; o < 32; o <<= 1) {
+                V[i] += __shfl_xor_sync(0xffffffffu, V[i], o);
+                E[i] += __shfl_xor_sync(0xffffffffu, E[i], o);
+            }
+        }
+        // dd pairs: reduce over groups (xor offsets >= T keep t fixed)
+#pragma unroll
+        for (int o = (T > 1 ? T : 1); o < 32; o <<= 1) {
+            dd w;
+            w.hi = __shfl_xor_sync(0xffffffffu, sA1.hi, o); w.lo = __shfl_xor_sync(0xffffffffu, sA1.lo, o); dd_add_dd(sA1, w);
+            w.hi = __shfl_xor_sync(0xffffffffu, sA2.hi, o); w.lo = __shfl_xor_sync(0xffffffffu, sA2.lo, o); dd_add_dd(sA2, w);
+            if (T == 1) {
+                w.hi = __shfl_xor_sync(0xffffffffu, sB1.hi, o); w.lo = __shfl_xor_sync(0xffffffffu, sB1.lo, o); dd_add_dd(sB1, w);
+                w.hi = __shfl_xor_sync(0xffffffffu, sB2.hi, o); w.lo = __shfl_xor_sync(0xffffffffu, sB2.lo, o); dd_add_dd(sB2, w);
+            }
+        }
+        if (T > 1) {  // bring lane 1's (yB) sums next to lane 0's
+            sB1.hi = __shfl_sync(0xffffffffu, sA1.hi, 1); sB1.lo = __shfl_sync(0xffffffffu, sA1.lo, 1);
+            sB2.hi = __shfl_sync(0xffffffffu, sA2.hi, 1); sB2.lo = __shfl_sync(0xffffffffu, sA2.lo, 1);
+        }
+        double* wr = sred + warp * RED;
+        if (lane < T) {
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                wr[t + T * i] = V[i];
+                wr[SLOTS + t + T * i] = E[i];
+            }
+        }
+        if (lane == 0) {
+            wr[2 * SLOTS + 0] = sA1.hi; wr[2 * SLOTS + 1] = sA1.lo; wr[2 * SLOTS + 2] = sA2.hi; wr[2 * SLOTS + 3] = sA2.lo;
+            wr[2 * SLOTS + 4] = sB1.hi; wr[2 * SLOTS + 5] = sB1.lo; wr[2 * SLOTS + 6] = sB2.hi; wr[2 * SLOTS + 7] = sB2.lo;
+        }
+        __syncthreads();
+        double* rec = a.tile_rec + (size_t)tile * a.nstat;
+        for (int k = threadIdx.x; k < d; k += PROD_THREADS) {
+            double v = 0.0, e = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                v += sred[w * RED + k];
+                e += sred[w * RED + SLOTS + k];
+            }
+            rec[stat_v(k)] = v;
+            rec[stat_e(d, 0, k)] = e;
+        }
+        if (threadIdx.x == 0) {
+            dd a1{0, 0}, a2{0, 0}, b1{0, 0}, b2{0, 0};
+            for (int w = 0; w < NW; ++w) {
+                const double* q = sred + w * RED + 2 * SLOTS;
+                dd_add_dd(a1, dd{q[0], q[1]}); dd_add_dd(a2, dd{q[2], q[3]});
+                dd_add_dd(b1, dd{q[4], q[5]}); dd_add_dd(b2, dd{q[6], q[7]});
+            }
+            rec[4] = a1.hi; rec[5] = a1.lo; rec[6] = a2.hi; rec[7] = a2.lo;   // sum yA, sum yA^2
+            dd_add_dd(a1, b1); dd_add_dd(a2, b2);
+            rec[0] = a1.hi; rec[1] = a1.lo; rec[2] = a2.hi; rec[3] = a2.lo;   // over [yA; yB]
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace gsa

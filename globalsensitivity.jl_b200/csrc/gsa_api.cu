@@ -208,6 +208,7 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
     if ((rc = plan_fused(h, model, d, nout, np, second, est, &plan))) return rc;
 
     h->last_launches = 0;
+    h->kernel_timed = false;
     GSA_CUDA(cudaEventRecord(h->ev0, h->stream));
     GSA_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (size_t)o->nboot * recsz, h->stream));
     const int64_t valid_hi = std::min<int64_t>(col0 + ncols, (int64_t)o->nboot * n);
@@ -323,8 +324,11 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
         if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)a.ntiles * recsz))) return rc;
         a.tile_rec = h->tile_rec.as<double>();
         dim3 grid(std::min(a.ntiles, h->sm_count * 8), nout);
+        GSA_CUDA(cudaEventRecord(h->evk0, h->stream));
         if (second) estimator_y_kernel<true><<<grid, 256, 0, h->stream>>>(a);
         else estimator_y_kernel<false><<<grid, 256, 0, h->stream>>>(a);
+        GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
+        h->kernel_timed = true;
         h->last_launches++;
         GSA_CUDA(cudaGetLastError());
         if ((rc = run_reduce(h, recsz, nstat, a.tpr, 0, o->nboot, partials))) return rc;
@@ -388,6 +392,8 @@ int gsa_create(int device, gsa_handle** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->evk0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->evk1);
     for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
         e = cudaEventCreateWithFlags(&h->ev_copy[b], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming);
@@ -416,6 +422,8 @@ int gsa_destroy(gsa_handle* h) {
         }
         if (h->ev0) cudaEventDestroy(h->ev0);
         if (h->ev1) cudaEventDestroy(h->ev1);
+        if (h->evk0) cudaEventDestroy(h->evk0);
+        if (h->evk1) cudaEventDestroy(h->evk1);
         if (h->own_stream) cudaStreamDestroy(h->own_stream);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     }
@@ -643,13 +651,15 @@ int gsa_sobol_all_points(gsa_handle* h, const gsa_sobol_opts* opts, const double
     return GSA_OK;
 }
 
-int gsa_last_timing(gsa_handle* h, float* ms, int* launches) {
+int gsa_last_timing(gsa_handle* h, float* ms, float* kernel_ms, int* launches) {
     if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
     DeviceGuard guard(h->device);
     GSA_CUDA(cudaEventSynchronize(h->ev1));
-    float t = 0.f;
+    float t = 0.f, tk = 0.f;
     GSA_CUDA(cudaEventElapsedTime(&t, h->ev0, h->ev1));
+    if (h->kernel_timed) GSA_CUDA(cudaEventElapsedTime(&tk, h->evk0, h->evk1));
     if (ms) *ms = t;
+    if (kernel_ms) *kernel_ms = tk;
     if (launches) *launches = h->last_launches;
     return GSA_OK;
 }

@@ -43,7 +43,7 @@ struct gsa_handle {
     int device = 0;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     std::mutex mu;
     gsa::DevBuf tile_rec, partials, params, vtab, lbub, stage[2], dev_in[2], ybuf, aux;
     void* pinned[2] = {nullptr, nullptr};
@@ -51,5 +51,6 @@ struct gsa_handle {
     std::vector<uint32_t> vhost;  // cached direction numbers [vdims][32]
     int vdims = 0;
     float last_ms = 0.f;
+    bool kernel_timed = false;   // evk0/evk1 bracket the dominant kernel of the last call
     int last_launches = 0;
 };

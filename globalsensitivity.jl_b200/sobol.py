@@ -101,9 +101,9 @@ class GsaHandle:
         check(lib().gsa_synchronize(self._h))
 
     def last_timing(self):
-        ms, n = C.c_float(), C.c_int()
-        check(lib().gsa_last_timing(self._h, C.byref(ms), C.byref(n)))
-        return ms.value, n.value
+        ms, kms, n = C.c_float(), C.c_float(), C.c_int()
+        check(lib().gsa_last_timing(self._h, C.byref(ms), C.byref(kms), C.byref(n)))
+        return ms.value, kms.value, n.value
 
 
 _default = {}

@@ -151,9 +151,10 @@ GSA_API int gsa_sobol_analyze_y(gsa_handle* h, const gsa_sobol_opts* opts, const
 GSA_API int gsa_sobol_all_points(gsa_handle* h, const gsa_sobol_opts* opts, const double* A, const double* B, int d,
                          int64_t N, double* P, int p_location);
 
-/* device time (ms, CUDA events on the handle's stream) of the last partials / design call, and the
- * number of kernels it launched; for bench.py's roofline line. */
-GSA_API int gsa_last_timing(gsa_handle* h, float* kernel_ms, int* launches);
+/* Device times (ms, CUDA events on the handle's stream) of the last partials / design call: the whole call,
+ * and its dominant kernel alone (the last fused / estimator launch; 0 if none); plus the number of kernels
+ * the call launched.  Used by bench.py's roofline line. */
+GSA_API int gsa_last_timing(gsa_handle* h, float* total_ms, float* kernel_ms, int* launches);
 
 #ifdef __cplusplus
 }

@@ -82,7 +82,7 @@ def test_reference_goldens_on_gpu(golden, ishigami_design):
     lin = g.DeviceModel("linear", np.array([[7.0, 0.1, 0.0, 0.0]]))
     r = g.gsa(lin, g.Sobol(), A, B, batch=True)
     want = np.array(golden["linear_S1_ST_atol1e-4"]["value"])
-    assert np.abs(r.S1[0] - want).max() < 1e-4 and np.abs(r.ST[0] - want).max() < 1e-4
+    assert np.abs(r.S1 - want).max() < 1e-4 and np.abs(r.ST - want).max() < 1e-4
 
 
 @pytest.mark.parametrize("est", so.EI_ESTIMATORS)
@@ -248,3 +248,22 @@ def test_sharded_partials_are_additive():
     torch.cuda.synchronize()
     res = g.sobol_finalize(method, total, d, N)
     assert_parity(res, ref)
+
+
+def test_product_path_matches_generic_path(monkeypatch):
+    """The product-form fast kernel (prefix/suffix products, reciprocal coefficients) against the generic kernel
+    (full model evaluation per swapped coordinate) and the oracle, at BASELINE config 5's dimension."""
+    d, N = 100, 30000
+    a = np.array(([0.0, 1.0, 4.5, 9.0] + [99.0] * d)[:d])
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, nboot=3)
+    fast = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(nboot=3), A, B, batch=True)
+    monkeypatch.setenv("GSA_FORCE_GENERIC", "1")
+    slow = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(nboot=3), A, B, batch=True)
+    monkeypatch.delenv("GSA_FORCE_GENERIC")
+    assert_parity(fast, ref)
+    assert_parity(slow, ref)
+    for T in ("16", "32"):
+        monkeypatch.setenv("GSA_PRODUCT_T", T)
+        alt = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(nboot=3), A, B, batch=True)
+        assert_parity(alt, ref, what=T)
