@@ -106,14 +106,14 @@ def reference_arm(args):
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index: int):
         self.idx, self.rows, self.proc = gpu_index, [], None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -121,15 +121,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, t0, t1):
+        """terminate nvidia-smi and summarise the samples taken inside the timed region [t0, t1] (perf_counter clock)"""
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
+        rows = list(self.rows)
+        inside = [r[1:] for r in rows if t0 <= r[0] <= t1]
+        self.rows = inside if inside else [r[1:] for r in rows[-3:]]
         sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = []
@@ -193,24 +197,28 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                     # nvidia-smi needs ~1 s to start: launch it before the warm-up
     for _ in range(args.warmup):
         res = step()
     launches_per_step = h.last_timing()[2]
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
     barrier()
+    tw0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         res = step()
         kernel_ms.append(h.last_timing()[1])               # events already complete: the step synchronised
     ev1.record()
     barrier()
+    tw1 = time.perf_counter()
     ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        clocks = sampler.stop(tw0, tw1)
     t = torch.tensor([ms_total, float(np.mean(kernel_ms))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -44,7 +44,7 @@ SIGNATURES = {
     "gsa_last_error": [C.c_char_p, _sz],
     "gsa_create": [_i, C.POINTER(_vp)],
     "gsa_destroy": [_vp],
-    "gsa_set_stream": [_vp, _vp],
+    "gsa_set_stream": [_vp, _vp, _i],
     "gsa_synchronize": [_vp],
     "gsa_model_lookup": [C.c_char_p, _ip],
     "gsa_model_nout": [_vp, _i, _i, _i, _ip],

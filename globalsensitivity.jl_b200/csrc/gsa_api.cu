@@ -431,10 +431,10 @@ int gsa_destroy(gsa_handle* h) {
     return GSA_OK;
 }
 
-int gsa_set_stream(gsa_handle* h, void* s) {
+int gsa_set_stream(gsa_handle* h, void* s, int external) {
     if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
     std::lock_guard<std::mutex> lk(h->mu);
-    h->stream = s ? static_cast<cudaStream_t>(s) : h->own_stream;
+    h->stream = external ? static_cast<cudaStream_t>(s) : h->own_stream;
     return GSA_OK;
 }
 

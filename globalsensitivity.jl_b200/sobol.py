@@ -94,8 +94,13 @@ class GsaHandle:
     def ptr(self):
         return self._h
 
-    def set_stream(self, cuda_stream: int = 0):
-        check(lib().gsa_set_stream(self._h, C.c_void_p(cuda_stream)))
+    def set_stream(self, cuda_stream: Optional[int] = None):
+        """Issue the handle's work on an external CUDA stream (an integer cudaStream_t, 0 = legacy default stream);
+        None = back to the handle-owned stream."""
+        if cuda_stream is None:
+            check(lib().gsa_set_stream(self._h, None, 0))
+        else:
+            check(lib().gsa_set_stream(self._h, C.c_void_p(cuda_stream), 1))
 
     def synchronize(self):
         check(lib().gsa_synchronize(self._h))
@@ -211,7 +216,7 @@ def generate_design_matrices(n: int, lb, ub, num_mats: int = 2, *, device: bool 
         try:
             check(lib().gsa_sobol_design(h.ptr, n, d, num_mats, lb.ctypes.data, ub.ctypes.data, col0, ncols, ptrs, LOC_DEVICE))
         finally:
-            h.set_stream(0)
+            h.set_stream(None)
         return [m.t() for m in mats]
     mats = [np.empty((d, ncols), dtype=np.float64, order="F") for _ in range(num_mats)]
     for m in range(num_mats):
@@ -363,7 +368,7 @@ def sobol_partials(f: DeviceModel, method: Sobol, A_local, B_local, N: int, col0
         check(lib().gsa_sobol_partials(h.ptr, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size, Am.ptr, Bm.ptr,
                                        d, N, col0, Am.N, out.data_ptr()))
     finally:
-        h.set_stream(0)
+        h.set_stream(None)
     return out
 
 

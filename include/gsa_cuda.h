@@ -91,8 +91,9 @@ GSA_API int gsa_last_error(char* buf, size_t n);
 /* device < 0: use the calling thread's current CUDA device */
 GSA_API int gsa_create(int device, gsa_handle** out);
 GSA_API int gsa_destroy(gsa_handle* h);
-/* all work of the handle is issued on this CUDA stream (a cudaStream_t); NULL = handle-owned stream */
-GSA_API int gsa_set_stream(gsa_handle* h, void* cuda_stream);
+/* external != 0: all work of the handle is issued on `cuda_stream` (a cudaStream_t; NULL is the legacy default
+ * stream), e.g. the caller framework's current stream.  external == 0: back to the handle-owned stream. */
+GSA_API int gsa_set_stream(gsa_handle* h, void* cuda_stream, int external);
 /* block until the handle's stream is idle */
 GSA_API int gsa_synchronize(gsa_handle* h);
 
