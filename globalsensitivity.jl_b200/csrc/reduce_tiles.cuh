@@ -6,7 +6,7 @@
 
 namespace gsa {
 
-constexpr int RT_X = 32, RT_Y = 8;
+constexpr int RT_X = 32, RT_Y = 32;
 
 __global__ void __launch_bounds__(RT_X* RT_Y) reduce_tiles_kernel(const double* __restrict__ tile_rec, double* __restrict__ partials,
                                                                   int recsz, int nstat, int tpr, int rep_first) {

@@ -24,29 +24,43 @@ struct DesignArgs {
     int d, dT, lp;          // dT = dims handled by this launch (<= 8*d), P = 1 << lp
 };
 
-__global__ void __launch_bounds__(256) sobol_design_kernel(DesignArgs a) {
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int DESIGN_THREADS = 256;
+
+__global__ void __launch_bounds__(DESIGN_THREADS) sobol_design_kernel(DesignArgs a) {
+    // Direction numbers of the CTA's 256 (point, dim) slots, transposed to [bit][slot] (+1 padding) so that the
+    // per-iteration lookup Vs[b][slot] is bank-conflict free (b is almost always warp-uniform).  Reading them from
+    // global memory instead costs 32 L1 wavefronts per warp (each lane owns a different 128-byte table row) and
+    // capped the kernel at ~2 TB/s (profiles/r1_k1_design_before.txt).
+    __shared__ uint32_t Vs[32][DESIGN_THREADS + 1];
     const int64_t P = (int64_t)1 << a.lp;
-    if (f >= P * a.dT) return;
+    const int64_t total = P * a.dT;
+    const int64_t f0 = (int64_t)blockIdx.x * DESIGN_THREADS;
+    for (int idx = threadIdx.x; idx < 32 * DESIGN_THREADS; idx += DESIGN_THREADS) {
+        const int slot = idx >> 5, b = idx & 31;
+        const int64_t fs = f0 + slot;
+        if (fs < total) Vs[b][slot] = __ldg(a.V + 32 * (int)(fs % a.dT) + b);
+    }
+    __syncthreads();
+    const int64_t f = f0 + threadIdx.x;
+    if (f >= total) return;
     const int64_t p0 = f / a.dT;
     const int j = (int)(f - p0 * a.dT);
     if (p0 >= a.ncols) return;
     const int m = j / a.d, i = j - m * a.d;
-    const uint32_t* Vj = a.V + 32 * j;
     const double sc = __ldg(a.scale + i), lo = __ldg(a.lb + i);
     double* out = a.out[m] + i;
 
     uint64_t q = a.first + (uint64_t)p0;
     uint32_t x = 0;
-    for (uint64_t g = q ^ (q >> 1); g; g &= g - 1) x ^= __ldg(Vj + (__ffsll((long long)g) - 1));
-    const uint32_t vlow = a.lp > 0 ? __ldg(Vj + a.lp - 1) : 0u;
+    for (uint64_t g = q ^ (q >> 1); g; g &= g - 1) x ^= Vs[__ffsll((long long)g) - 1][threadIdx.x];
+    const uint32_t vlow = a.lp > 0 ? Vs[a.lp - 1][threadIdx.x] : 0u;
 
     for (int64_t p = p0; p < a.ncols; p += P) {
         const double u = (double)x * 0x1p-32;                       // exact
         out[(size_t)a.d * p] = __dadd_rn(__dmul_rn(sc, u), lo);     // (ub-lb)*u + lb, mul and add rounded separately
         const uint64_t h = q >> a.lp;
         const int c = __ffsll((long long)~h) - 1;                   // trailing ones of h
-        x ^= vlow ^ __ldg(Vj + min(a.lp + c, 31));               // (clamp only matters for the unused last update)
+        x ^= vlow ^ Vs[min(a.lp + c, 31)][threadIdx.x];             // (clamp only matters for the unused last update)
         q += (uint64_t)P;
     }
 }
