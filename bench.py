@@ -55,6 +55,7 @@ def workload(log2n: int):
 def cpu_sample(log2n_cpu: int, reps: int):
     import gsa_ref
     gsa_ref.build()
+    gsa_ref.use_all_cores()
     n = 1 << log2n_cpu
     lb, ub = np.zeros(D), np.ones(D)
     A, B = gsa_ref.sobol_design(n, lb, ub)
@@ -79,6 +80,7 @@ def reference_arm(args):
     times, rows = [], 0
     import gsa_ref
     gsa_ref.build()
+    gsa_ref.use_all_cores()
     n = 1 << args.cpu_log2n
     A, B = gsa_ref.sobol_design(n, np.zeros(D), np.ones(D))
     a = np.array(SOBOL_G_A)

@@ -7,10 +7,11 @@
 #include "gsa_internal.h"
 #include "fused_generic.cuh"
 #include "fused_product.cuh"
+#include "small_launch.cuh"
 
 namespace gsa {
 
-enum { PLAN_GENERIC = 0, PLAN_PRODUCT = 1 };
+enum { PLAN_GENERIC = 0, PLAN_PRODUCT = 1, PLAN_SMALL_ISHIGAMI = 2, PLAN_SMALL_SOBOLG = 3 };
 
 struct FusedPlan {
     int kind = PLAN_GENERIC;
@@ -22,6 +23,7 @@ struct FusedPlan {
     const void* kernel = nullptr;
 
     int prod_T = 0, prod_CPL = 0;
+    double pa = 0.0, pb = 0.0;   // Ishigami parameters (small kernel)
 
     int prepare(gsa_handle* h, const double* params, int np);
     int launch(gsa_handle* h, const double* A, const double* B, const TileGeom& g, int t0, int t1);
@@ -136,6 +138,16 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
     const bool generic_only = force && atoi(force) != 0;
     if (!generic_only && model == GSA_MODEL_SOBOL_G && !second && est == GSA_EI_JANSEN1999 && product_shape(d, &p->prod_T, &p->prod_CPL))
         return plan_product(h, p);
+    const bool small_ishi = model == GSA_MODEL_ISHIGAMI && (d == 3 || d == 4);
+    const bool small_g = model == GSA_MODEL_SOBOL_G && d <= (second ? SMALL_DMAX2 : SMALL_DMAX);
+    if (!generic_only && (small_ishi || small_g)) {
+        // thread-per-sample register kernels: few, large tiles (the per-tile flush costs ~300 instructions per thread)
+        p->kind = small_ishi ? PLAN_SMALL_ISHIGAMI : PLAN_SMALL_SOBOLG;
+        p->threads = SMALL_THREADS;
+        p->resident = h->sm_count;
+        p->ts_min = p->ts_gran = SMALL_THREADS;
+        return GSA_OK;
+    }
     return plan_generic(h, p);
 }
 
@@ -149,6 +161,10 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         a.g = g; a.d = d; a.np = np; a.nout = nout; a.nstat = nstat; a.est = est; a.t_begin = t0; a.t_end = t1;
         ((GenericKernel)kernel)<<<grid, threads, smem, h->stream>>>(a);
     }
+    else if (kind == PLAN_SMALL_ISHIGAMI)
+        return launch_small_ishigami(h, d, second, est, A, B, pa, pb, g, t0, t1, nstat, h->tile_rec.as<double>());
+    else if (kind == PLAN_SMALL_SOBOLG)
+        return launch_small_sobolg(h, d, second, est, A, B, h->aux.as<double2>(), g, t0, t1, nstat, h->tile_rec.as<double>());
     else if (kind == PLAN_PRODUCT) {
         ProductArgs a;
         a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = h->tile_rec.as<double>();
@@ -163,7 +179,11 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
 }
 
 inline int FusedPlan::prepare(gsa_handle* h, const double* params, int np_) {
-    if (kind == PLAN_PRODUCT) {
+    if (kind == PLAN_SMALL_ISHIGAMI) {
+        pa = params[0];
+        pb = params[1];
+    }
+    if (kind == PLAN_PRODUCT || kind == PLAN_SMALL_SOBOLG) {
         // g_k(x) = (|4x-2| + a_k)/(1 + a_k) = |x - 0.5| * 4/(1+a_k) + a_k/(1+a_k)
         std::vector<double> c(2 * (size_t)d);
         for (int k = 0; k < d; ++k) {

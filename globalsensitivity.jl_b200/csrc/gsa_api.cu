@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 #include "gsa_internal.h"
@@ -304,6 +305,7 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
     const int est = o->ei_estimator, step = second ? 2 * d + 2 : d + 2;
     const int nstat = stat_count(d, est, second), recsz = nstat * nout;
     h->last_launches = 0;
+    h->kernel_timed = false;
     const double* Yd = Y;
     const size_t ybytes = sizeof(double) * (size_t)nout * (size_t)n * step * o->nboot;
     if (o->input_location == GSA_LOC_HOST && ybytes) {
@@ -314,24 +316,39 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
     GSA_CUDA(cudaEventRecord(h->ev0, h->stream));
     GSA_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (size_t)o->nboot * recsz, h->stream));
     if (n > 0) {
-        EstYArgs a;
-        a.Y = Yd;
-        a.n = n;
-        a.nout = nout; a.d = d; a.nstat = nstat; a.est = est; a.step = step;
-        a.ts = (int)std::min<int64_t>(KY_TS_MAX, (n + 31) / 32 * 32);
-        a.tpr = (int)((n + a.ts - 1) / a.ts);
-        a.ntiles = a.tpr * o->nboot;
-        if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)a.ntiles * recsz))) return rc;
-        a.tile_rec = h->tile_rec.as<double>();
-        dim3 grid(std::min(a.ntiles, h->sm_count * 8), nout);
-        GSA_CUDA(cudaEventRecord(h->evk0, h->stream));
-        if (second) estimator_y_kernel<true><<<grid, 256, 0, h->stream>>>(a);
-        else estimator_y_kernel<false><<<grid, 256, 0, h->stream>>>(a);
-        GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
-        h->kernel_timed = true;
-        h->last_launches++;
-        GSA_CUDA(cudaGetLastError());
-        if ((rc = run_reduce(h, recsz, nstat, a.tpr, 0, o->nboot, partials))) return rc;
+        const char* force = getenv("GSA_FORCE_GENERIC");
+        const bool small = d <= (second ? SMALL_DMAX2 : SMALL_DMAX) && !(force && atoi(force) != 0);
+        int tpr = 1;
+        if (small) {
+            // thread-per-sample register kernel: every Y value is read exactly once, straight into registers
+            TileGeom g;
+            g.n = n; g.col_lo = 0; g.col_hi = (int64_t)o->nboot * n; g.buf_col0 = 0; g.rep_first = 0;
+            choose_tiles(n, o->nboot, std::max(1, h->sm_count / nout), SMALL_THREADS, 1 << 30, SMALL_THREADS, &g.ts, &g.tpr);
+            g.ntiles = g.tpr * o->nboot;
+            tpr = g.tpr;
+            if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)g.ntiles * recsz))) return rc;
+            if ((rc = launch_small_y(h, d, second, est, Yd, n, nout, step, g, nstat, h->tile_rec.as<double>()))) return rc;
+        } else {
+            EstYArgs a;
+            a.Y = Yd;
+            a.n = n;
+            a.nout = nout; a.d = d; a.nstat = nstat; a.est = est; a.step = step;
+            a.ts = (int)std::min<int64_t>(KY_TS_MAX, (n + 31) / 32 * 32);
+            a.tpr = (int)((n + a.ts - 1) / a.ts);
+            a.ntiles = a.tpr * o->nboot;
+            tpr = a.tpr;
+            if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)a.ntiles * recsz))) return rc;
+            a.tile_rec = h->tile_rec.as<double>();
+            dim3 grid(std::min(a.ntiles, h->sm_count * 8), nout);
+            GSA_CUDA(cudaEventRecord(h->evk0, h->stream));
+            if (second) estimator_y_kernel<true><<<grid, 256, 0, h->stream>>>(a);
+            else estimator_y_kernel<false><<<grid, 256, 0, h->stream>>>(a);
+            GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
+            h->kernel_timed = true;
+            h->last_launches++;
+            GSA_CUDA(cudaGetLastError());
+        }
+        if ((rc = run_reduce(h, recsz, nstat, tpr, 0, o->nboot, partials))) return rc;
     }
     GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
     return GSA_OK;

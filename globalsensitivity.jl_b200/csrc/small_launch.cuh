@@ -1,0 +1,41 @@
+// small_launch.cuh -- host launcher shared by the small_*.cu translation units.
+#pragma once
+#include <algorithm>
+
+#include "fused_small.cuh"
+#include "gsa_internal.h"
+
+namespace gsa {
+
+constexpr int SMALL_DMAX = 12;   // first order only
+constexpr int SMALL_DMAX2 = 8;   // with second order (2D+2 values + 2D + D(D-1)/2 accumulators must fit in registers)
+
+template <class Src, int D, bool SECOND, bool JANSEN>
+int launch_small(gsa_handle* h, SmallArgs<Src>& a) {
+    auto kern = small_kernel<Src, D, SECOND, JANSEN>;
+    int nb = 0;
+    GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SMALL_THREADS, 0));
+    const int units = (a.t_end - a.t_begin) * a.nout;
+    if (units <= 0) return GSA_OK;
+    const int grid = std::min(units, std::max(1, nb) * h->sm_count);
+    GSA_CUDA(cudaEventRecord(h->evk0, h->stream));
+    kern<<<grid, SMALL_THREADS, 0, h->stream>>>(a);
+    GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
+    h->kernel_timed = true;
+    h->last_launches++;
+    GSA_CUDA(cudaGetLastError());
+    return GSA_OK;
+}
+
+// expands CASE(D) for D = 1..12
+#define GSA_SMALL_D_CASES(CASE) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+
+// declared here, defined in small_y.cu / small_ishigami.cu / small_sobolg.cu
+int launch_small_y(gsa_handle* h, int d, bool second, int est, const double* Y, int64_t n, int nout, int step, const TileGeom& g,
+                   int nstat, double* tile_rec);
+int launch_small_ishigami(gsa_handle* h, int d, bool second, int est, const double* A, const double* B, double pa, double pb,
+                          const TileGeom& g, int t0, int t1, int nstat, double* tile_rec);
+int launch_small_sobolg(gsa_handle* h, int d, bool second, int est, const double* A, const double* B, const double2* coef,
+                        const TileGeom& g, int t0, int t1, int nstat, double* tile_rec);
+
+}  // namespace gsa

@@ -382,3 +382,21 @@ def sobol_finalize(method: Sobol, partials, d: int, N: int, *, Ei_estimator="Jan
     rc, finish, _ = _alloc_result(nout, d, nboot, 2 in method.order, nout > 1)
     check(lib().gsa_sobol_finalize(C.byref(o), p.ctypes.data, nout, d, N // nboot, C.byref(rc)))
     return finish()
+
+
+def reduce_and_finalize(method: Sobol, partials, d: int, N: int, *, Ei_estimator="Jansen1999", group=None) -> SobolResult:
+    """K5: the single collective of the path.  Sums the per-rank partial sums (nboot, nout, nstat) over the ranks of
+    `group` with one `torch.distributed.all_reduce` (NCCL on GPUs; gloo in the CPU tests) -- a few KB -- and runs the
+    host epilogue.  Every rank returns the same SobolResult."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+    return sobol_finalize(method, partials, d, N, Ei_estimator=Ei_estimator)
+
+
+def gsa_sharded(f: DeviceModel, method: Sobol, A_local, B_local, N: int, col0: int, *, Ei_estimator="Jansen1999",
+                group=None, handle: Optional[GsaHandle] = None) -> SobolResult:
+    """gsa(f, Sobol(...), A, B; batch=true) with the d x N design sharded by contiguous column ranges over the ranks of a
+    torch.distributed group (one process per GPU): local fused kernel -> one all-reduce -> epilogue."""
+    p = sobol_partials(f, method, A_local, B_local, N, col0, Ei_estimator=Ei_estimator, handle=handle)
+    return reduce_and_finalize(method, p, _Mat(A_local).d, N, Ei_estimator=Ei_estimator, group=group)

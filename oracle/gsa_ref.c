@@ -32,6 +32,15 @@
 enum { REF_HOMMA1996 = 0, REF_SOBOL2007 = 1, REF_JANSEN1999 = 2, REF_JANON2014 = 3 };
 enum { REF_MODEL_ISHIGAMI = 0, REF_MODEL_SOBOL_G = 1, REF_MODEL_LINEAR = 2, REF_MODEL_ISHI_LINEAR = 3 };
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline should use every core it may run on */
+REF_API void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 REF_API int ref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

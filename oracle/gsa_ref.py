@@ -33,6 +33,8 @@ def lib():
     if _lib is None:
         L = C.CDLL(build())
         L.ref_num_threads.restype = C.c_int
+        L.ref_set_num_threads.restype = None
+        L.ref_set_num_threads.argtypes = [C.c_int]
         L.ref_norm_quantile.restype = C.c_double
         L.ref_norm_quantile.argtypes = [C.c_double]
         L.ref_all_points_cols.restype = C.c_int64
@@ -64,6 +66,13 @@ def _f(a):
 
 
 def num_threads() -> int:
+    return lib().ref_num_threads()
+
+
+def use_all_cores() -> int:
+    """OpenMP threads = the cores this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().ref_set_num_threads(n)
     return lib().ref_num_threads()
 
 

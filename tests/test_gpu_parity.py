@@ -267,3 +267,43 @@ def test_product_path_matches_generic_path(monkeypatch):
         monkeypatch.setenv("GSA_PRODUCT_T", T)
         alt = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(nboot=3), A, B, batch=True)
         assert_parity(alt, ref, what=T)
+
+
+@pytest.mark.parametrize("est", so.EI_ESTIMATORS)
+@pytest.mark.parametrize("d,second,nboot", [(3, False, 1), (3, True, 1000), (4, False, 7)])
+def test_ishigami_small_kernels(est, d, second, nboot):
+    """BASELINE configs 1 and 2 shapes (d = 3; README.md:46-56) through the thread-per-sample register kernel."""
+    N = 600000 if nboot == 1 else (1 << 20)
+    A, B = gsa_ref.sobol_design(N, -np.pi * np.ones(d), np.pi * np.ones(d))
+    order = (0, 1, 2) if second else (0, 1)
+    ref = gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=order, nboot=nboot, Ei_estimator=est)
+    res = g.gsa(g.DeviceModel("ishigami", [7.0, 0.1]), g.Sobol(order=order, nboot=nboot), A, B, batch=True, Ei_estimator=est)
+    assert_parity(res, ref, what=(est, d, second, nboot))
+
+
+@pytest.mark.parametrize("second", [False, True])
+def test_analyze_y_large_d(second):
+    """d > 12 takes the shared-memory estimator kernel (estimator_y.cuh) instead of the register kernel."""
+    d, N, nboot = 14, 9001, 2
+    a = np.linspace(0.0, 20.0, d)
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    order = (0, 1, 2) if second else (0, 1)
+    Y = gsa_ref.model_batch("sobol_g", a, gsa_ref.all_points(A, B, nboot, second))
+    for est in so.EI_ESTIMATORS:
+        ref = gsa_ref.analyze_y(Y, d, N // nboot, order=order, nboot=nboot, Ei_estimator=est)
+        res = g.gsa_sobol_all_y_analysis(g.Sobol(order=order, nboot=nboot), Y, d, N // nboot, est)
+        assert_parity(res, ref, what=(est, second))
+
+
+def test_small_kernels_match_generic(monkeypatch):
+    d, N = 8, 1 << 17
+    a = np.array([0.0, 1.0, 4.5, 9.0, 99.0, 99.0, 99.0, 99.0])
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, order=(0, 1, 2), nboot=2)
+    Y = gsa_ref.model_batch("sobol_g", a, gsa_ref.all_points(A, B, 2, True))
+    for force in ("0", "1"):
+        monkeypatch.setenv("GSA_FORCE_GENERIC", force)
+        res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2], nboot=2), A, B, batch=True)
+        assert_parity(res, ref, what=("fused", force))
+        res = g.gsa_sobol_all_y_analysis(g.Sobol(order=[0, 1, 2], nboot=2), Y, d, N // 2)
+        assert_parity(res, ref, what=("y", force))
