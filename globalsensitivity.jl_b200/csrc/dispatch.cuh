@@ -8,10 +8,11 @@
 #include "fused_generic.cuh"
 #include "fused_product.cuh"
 #include "small_launch.cuh"
+#include "fused_linear.cuh"
 
 namespace gsa {
 
-enum { PLAN_GENERIC = 0, PLAN_PRODUCT = 1, PLAN_SMALL_ISHIGAMI = 2, PLAN_SMALL_SOBOLG = 3 };
+enum { PLAN_GENERIC = 0, PLAN_PRODUCT = 1, PLAN_SMALL_ISHIGAMI = 2, PLAN_SMALL_SOBOLG = 3, PLAN_LINEAR = 4 };
 
 struct FusedPlan {
     int kind = PLAN_GENERIC;
@@ -24,6 +25,7 @@ struct FusedPlan {
 
     int prod_T = 0, prod_CPL = 0;
     double pa = 0.0, pb = 0.0;   // Ishigami parameters (small kernel)
+    int lin_DP = 0;              // padded d+1 of the linear (Gram) kernel
 
     int prepare(gsa_handle* h, const double* params, int np);
     int launch(gsa_handle* h, const double* A, const double* B, const TileGeom& g, int t0, int t1);
@@ -138,6 +140,14 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
     const bool generic_only = force && atoi(force) != 0;
     if (!generic_only && model == GSA_MODEL_SOBOL_G && !second && est == GSA_EI_JANSEN1999 && product_shape(d, &p->prod_T, &p->prod_CPL))
         return plan_product(h, p);
+    if (!generic_only && model == GSA_MODEL_LINEAR && !second && est == GSA_EI_JANSEN1999 && d + 1 <= LIN_DPMAX) {
+        p->kind = PLAN_LINEAR;
+        p->lin_DP = (d + 1 + 3) / 4 * 4;
+        p->threads = LIN_THREADS;
+        p->resident = h->sm_count;          // few, large tiles: every tile costs one moments->records conversion per output
+        p->ts_min = p->ts_gran = LIN_S;
+        return GSA_OK;
+    }
     const bool small_ishi = model == GSA_MODEL_ISHIGAMI && (d == 3 || d == 4);
     const bool small_g = model == GSA_MODEL_SOBOL_G && d <= (second ? SMALL_DMAX2 : SMALL_DMAX);
     if (!generic_only && (small_ishi || small_g)) {
@@ -165,6 +175,31 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         return launch_small_ishigami(h, d, second, est, A, B, pa, pb, g, t0, t1, nstat, h->tile_rec.as<double>());
     else if (kind == PLAN_SMALL_SOBOLG)
         return launch_small_sobolg(h, d, second, est, A, B, h->aux.as<double2>(), g, t0, t1, nstat, h->tile_rec.as<double>());
+    else if (kind == PLAN_LINEAR) {
+        const int gs = lin_gram_size(lin_DP);
+        int rc = h->gram.reserve(sizeof(double) * (size_t)g.ntiles * gs);
+        if (rc) return rc;
+        LinearArgs a;
+        a.A = A; a.B = B; a.gram = h->gram.as<double>(); a.g = g; a.d = d; a.t_begin = t0; a.t_end = t1;
+        const int grid_l = std::min(t1 - t0, h->sm_count * 3);
+        switch (lin_DP) {
+#define GSA_LIN_CASE(DPV) case DPV: linear_gram_kernel<DPV><<<grid_l, LIN_THREADS, 0, h->stream>>>(a); break;
+            GSA_LIN_CASE(4) GSA_LIN_CASE(8) GSA_LIN_CASE(12) GSA_LIN_CASE(16) GSA_LIN_CASE(20) GSA_LIN_CASE(24) GSA_LIN_CASE(28) GSA_LIN_CASE(32)
+#undef GSA_LIN_CASE
+            default: return fail(GSA_ERR_UNSUPPORTED, "linear kernel: unsupported padded dimension %d", lin_DP);
+        }
+        GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
+        h->kernel_timed = true;
+        h->last_launches++;
+        GSA_CUDA(cudaGetLastError());
+        LinearRecArgs r;
+        r.gram = h->gram.as<double>(); r.W = h->params.as<double>(); r.tile_rec = h->tile_rec.as<double>();
+        r.d = d; r.DP = lin_DP; r.nout = nout; r.nstat = nstat; r.t_begin = t0; r.t_end = t1;
+        linear_records_kernel<<<t1 - t0, 256, sizeof(double) * gs, h->stream>>>(r);
+        h->last_launches++;
+        GSA_CUDA(cudaGetLastError());
+        return GSA_OK;
+    }
     else if (kind == PLAN_PRODUCT) {
         ProductArgs a;
         a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = h->tile_rec.as<double>();

@@ -12,7 +12,9 @@
 
 namespace gsa {
 
-constexpr int KY_TS_MAX = 2048;  // samples per tile (2 * 16 KB of shared memory)
+constexpr int KY_TS_DEFAULT = 2048;  // samples per tile (16 bytes of dynamic shared memory each)
+constexpr int KY_TS_LIMIT = 12288;   // 192 KB
+constexpr int KY_U = 8;               // loads in flight per lane in the streaming loops
 
 struct EstYArgs {
     const double* Y;
@@ -22,8 +24,10 @@ struct EstYArgs {
 };
 
 template <bool SECOND>
-__global__ void __launch_bounds__(256) estimator_y_kernel(EstYArgs a) {
-    __shared__ double sA[KY_TS_MAX], sB[KY_TS_MAX];
+__global__ void __launch_bounds__(1024) estimator_y_kernel(EstYArgs a) {
+    extern __shared__ double sm_y[];
+    double* sA = sm_y;
+    double* sB = sm_y + a.ts;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int o = blockIdx.y, d = a.d, est = a.est;
     const int64_t n = a.n, nout = a.nout;
@@ -47,7 +51,7 @@ __global__ void __launch_bounds__(256) estimator_y_kernel(EstYArgs a) {
         }
         __syncthreads();
         // dd sums: warp butterfly, then warp 0 combines the warps through shared memory (reuse after sync below)
-        __shared__ double sdd[8][8];
+        __shared__ double sdd[32][8];
         {
             dd r0 = warp_sum_dd(sy), r1 = warp_sum_dd(syy), r2 = warp_sum_dd(sa), r3 = warp_sum_dd(saa);
             if (lane == 0) {
@@ -58,13 +62,25 @@ __global__ void __launch_bounds__(256) estimator_y_kernel(EstYArgs a) {
         for (int k = warp; k < d; k += nwarps) {
             const double* pk = blk(2 + k);
             double v = 0.0, e0 = 0.0, e1 = 0.0, e2 = 0.0;
-#pragma unroll 4
-            for (int s = lane; s < len; s += 32) {
-                const double fab = ldg_stream(pk + nout * s), fa = sA[s], fb = sB[s];
-                v += fb * (fab - fa);                                             // :192
-                if (est == GSA_EI_JANSEN1999) { double df = fa - fab; e0 += df * df; }   // :213
-                else if (est == GSA_EI_SOBOL2007) e0 += fa * (fa - fab);          // :211
-                else { e0 += fa * fab; e1 += fa * fa + fab * fab; e2 += fa + fab; }      // :207, :219-224
+            // batches of KY_U loads issued back to back (KY_U * 256 bytes in flight per warp), then consumed
+            for (int s0 = lane; s0 < len; s0 += 32 * KY_U) {
+                double f[KY_U];
+#pragma unroll
+                for (int u = 0; u < KY_U; ++u) {
+                    const int s = s0 + 32 * u;
+                    f[u] = s < len ? ldg_stream(pk + nout * s) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < KY_U; ++u) {
+                    const int s = s0 + 32 * u;
+                    if (s < len) {
+                        const double fab = f[u], fa = sA[s], fb = sB[s];
+                        v += fb * (fab - fa);                                             // :192
+                        if (est == GSA_EI_JANSEN1999) { double df = fa - fab; e0 += df * df; }   // :213
+                        else if (est == GSA_EI_SOBOL2007) e0 += fa * (fa - fab);          // :211
+                        else { e0 += fa * fab; e1 += fa * fa + fab * fab; e2 += fa + fab; }      // :207, :219-224
+                    }
+                }
             }
             v = warp_sum(v); e0 = warp_sum(e0);
             if (est == GSA_EI_JANON2014) { e1 = warp_sum(e1); e2 = warp_sum(e2); }
@@ -83,9 +99,20 @@ __global__ void __launch_bounds__(256) estimator_y_kernel(EstYArgs a) {
                 const int j = k + 1 + rem;
                 const double *pbk = blk(2 + d + k), *paj = blk(2 + j);
                 double v = 0.0;
-#pragma unroll 4
-                for (int s = lane; s < len; s += 32)
-                    v += ldg_stream(pbk + nout * s) * ldg_stream(paj + nout * s) - sA[s] * sB[s];   // :197
+                for (int s0 = lane; s0 < len; s0 += 32 * KY_U) {
+                    double fb_[KY_U], fa_[KY_U];
+#pragma unroll
+                    for (int u = 0; u < KY_U; ++u) {
+                        const int s = s0 + 32 * u;
+                        fb_[u] = s < len ? ldg_stream(pbk + nout * s) : 0.0;
+                        fa_[u] = s < len ? ldg_stream(paj + nout * s) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < KY_U; ++u) {
+                        const int s = s0 + 32 * u;
+                        if (s < len) v += fb_[u] * fa_[u] - sA[s] * sB[s];                  // :197
+                    }
+                }
                 v = warp_sum(v);
                 if (lane == 0) rec[pb + p] = v;
             }

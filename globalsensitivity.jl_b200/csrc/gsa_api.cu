@@ -333,16 +333,24 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
             a.Y = Yd;
             a.n = n;
             a.nout = nout; a.d = d; a.nstat = nstat; a.est = est; a.step = step;
-            a.ts = (int)std::min<int64_t>(KY_TS_MAX, (n + 31) / 32 * 32);
+            int ts_want = KY_TS_DEFAULT, threads = 256;
+            if (const char* e = getenv("GSA_KY_TS")) ts_want = std::max(32, std::min(KY_TS_LIMIT, atoi(e) / 32 * 32));   // tuning knobs
+            if (const char* e = getenv("GSA_KY_THREADS")) threads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
+            a.ts = (int)std::min<int64_t>(ts_want, (n + 31) / 32 * 32);
             a.tpr = (int)((n + a.ts - 1) / a.ts);
             a.ntiles = a.tpr * o->nboot;
             tpr = a.tpr;
             if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)a.ntiles * recsz))) return rc;
             a.tile_rec = h->tile_rec.as<double>();
-            dim3 grid(std::min(a.ntiles, h->sm_count * 8), nout);
+            const size_t smem = sizeof(double) * 2 * (size_t)a.ts;
+            const void* kern = second ? (const void*)estimator_y_kernel<true> : (const void*)estimator_y_kernel<false>;
+            if (smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int nb = 0;
+            GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem));
+            dim3 grid(std::min(a.ntiles, h->sm_count * std::max(1, nb)), nout);
             GSA_CUDA(cudaEventRecord(h->evk0, h->stream));
-            if (second) estimator_y_kernel<true><<<grid, 256, 0, h->stream>>>(a);
-            else estimator_y_kernel<false><<<grid, 256, 0, h->stream>>>(a);
+            if (second) estimator_y_kernel<true><<<grid, threads, smem, h->stream>>>(a);
+            else estimator_y_kernel<false><<<grid, threads, smem, h->stream>>>(a);
             GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
             h->kernel_timed = true;
             h->last_launches++;
@@ -430,7 +438,7 @@ int gsa_destroy(gsa_handle* h) {
         DeviceGuard guard(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);
         if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-        DevBuf* bufs[] = {&h->tile_rec, &h->partials, &h->params, &h->vtab, &h->lbub, &h->stage[0], &h->stage[1], &h->dev_in[0], &h->dev_in[1], &h->ybuf, &h->aux};
+        DevBuf* bufs[] = {&h->tile_rec, &h->partials, &h->params, &h->vtab, &h->lbub, &h->stage[0], &h->stage[1], &h->dev_in[0], &h->dev_in[1], &h->ybuf, &h->aux, &h->gram};
         for (DevBuf* b : bufs) b->release();
         for (int b = 0; b < 2; ++b) {
             if (h->pinned[b]) cudaFreeHost(h->pinned[b]);

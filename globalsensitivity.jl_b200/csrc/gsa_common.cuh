@@ -128,15 +128,17 @@ __device__ __forceinline__ dd warp_sum_dd(dd v) {
     return v;
 }
 
-// streaming 16-byte read-only load that does not pollute L1
+// streaming read-only loads that do not pollute L1.  Deliberately NOT `asm volatile`: the data is immutable for the
+// lifetime of the kernel, and the scheduler must be free to batch many of these ahead of their uses (memory-level
+// parallelism is what a streaming kernel lives on).
 __device__ __forceinline__ double2 ldg_stream2(const double* p) {
     double2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     return r;
 }
 __device__ __forceinline__ double ldg_stream(const double* p) {
     double r;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
     return r;
 }
 #endif  // __CUDACC__

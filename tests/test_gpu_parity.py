@@ -307,3 +307,35 @@ def test_small_kernels_match_generic(monkeypatch):
         assert_parity(res, ref, what=("fused", force))
         res = g.gsa_sobol_all_y_analysis(g.Sobol(order=[0, 1, 2], nboot=2), Y, d, N // 2)
         assert_parity(res, ref, what=("y", force))
+
+
+@pytest.mark.parametrize("d,nout,N,nboot", [(20, 256, 1 << 15, 1), (5, 3, 20000, 4), (31, 7, 5000, 1), (3, 1, 4097, 2), (12, 40, 30011, 3)])
+def test_linear_gram_kernel(d, nout, N, nboot):
+    """BASELINE config 4 shape (d=20, 256 outputs; smaller N) and odd shapes through the input-moment (Gram) kernel."""
+    rng = np.random.default_rng(d * 1000 + nout)
+    W = rng.normal(size=(nout, d)) * (1.0 + np.arange(d))[None, :] / d
+    lb, ub = -rng.random(d) - 0.5, rng.random(d) + 2.0            # a box with non-zero mean: exercises the shift
+    A, B = gsa_ref.sobol_design(N, lb, ub)
+    ref = gsa_ref.gsa_sobol("linear", W, A, B, nboot=nboot)
+    res = g.gsa(g.DeviceModel("linear", W), g.Sobol(nboot=nboot), A, B, batch=True)
+    if nout == 1:
+        ref.S1, ref.ST = np.ravel(ref.S1), np.ravel(ref.ST)
+        if nboot > 1:
+            ref.S1_Conf_Int, ref.ST_Conf_Int = np.ravel(ref.S1_Conf_Int), np.ravel(ref.ST_Conf_Int)
+    assert_parity(res, ref, what=(d, nout, N, nboot))
+    # analytic: S1 = ST = W^2 sigma^2 / sum(W^2 sigma^2)   (SURVEY Appendix C)
+    if nboot == 1 and N >= 20000:
+        var = (ub - lb) ** 2 / 12.0
+        S = W ** 2 * var[None, :]
+        S = S / S.sum(axis=1, keepdims=True)
+        assert np.abs(np.reshape(res.ST, (nout, d)) - S).max() < 2e-2
+
+
+def test_linear_large_offset_inputs():
+    """mean >> spread: the tile-local shift + double-double recentring keeps the variance exact."""
+    d, nout, N = 6, 5, 50000
+    W = np.arange(1, 31, dtype=np.float64).reshape(nout, d) / 10.0
+    A, B = gsa_ref.sobol_design(N, 1000.0 * np.ones(d), 1001.0 * np.ones(d))
+    ref = gsa_ref.gsa_sobol("linear", W, A, B)
+    res = g.gsa(g.DeviceModel("linear", W), g.Sobol(), A, B, batch=True)
+    assert parity_err(res.S1, ref.S1) < 1e-9 and parity_err(res.ST, ref.ST) < 1e-9      # the oracle's own fB*(fAB-fA) cancels here
