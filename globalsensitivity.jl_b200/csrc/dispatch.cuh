@@ -20,7 +20,9 @@ struct FusedPlan {
     bool second = false;
     int threads = 256;
     size_t smem = 0;
-    int resident = 148, ts_min = 256, ts_max = 1 << 20, ts_gran = 32;
+    int resident = 148, tiles_per_cta = 2, ts_min = 256, ts_max = 1 << 20, ts_gran = 32;
+    const void* lin_kernel = nullptr;
+    size_t lin_smem = 0;
     const void* kernel = nullptr;
 
     int prod_T = 0, prod_CPL = 0;
@@ -142,9 +144,24 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
         return plan_product(h, p);
     if (!generic_only && model == GSA_MODEL_LINEAR && !second && est == GSA_EI_JANSEN1999 && d + 1 <= LIN_DPMAX) {
         p->kind = PLAN_LINEAR;
-        p->lin_DP = (d + 1 + 3) / 4 * 4;
+        p->lin_DP = (d + 1 + 7) / 8 * 8;
         p->threads = LIN_THREADS;
-        p->resident = h->sm_count;          // few, large tiles: every tile costs one moments->records conversion per output
+        const int NB = p->lin_DP / 8, NBD = (d + 7) / 8, np_ = lin_num_pairs(NB, NBD);
+        int lps = 4;
+        while (lps < np_) lps <<= 1;
+        p->lin_smem = sizeof(double) * ((size_t)LIN_S * 3 * NB * LIN_BS + p->lin_DP);
+        const void* kern = nullptr;
+#define GSA_LIN_CASE(NBV, LPSV) if (NB == NBV && lps == LPSV) kern = (const void*)linear_gram_kernel<NBV, LPSV>;
+        GSA_LIN_CASE(1, 4) GSA_LIN_CASE(2, 16) GSA_LIN_CASE(3, 32) GSA_LIN_CASE(4, 64)
+        GSA_LIN_CASE(2, 8) GSA_LIN_CASE(3, 16) GSA_LIN_CASE(4, 32)     // d = 8 / 16 / 24: the delta vector has one block fewer
+#undef GSA_LIN_CASE
+        if (!kern) return fail(GSA_ERR_UNSUPPORTED, "linear kernel: no instantiation for %d blocks / %d pairs", NB, np_);
+        if (p->lin_smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lin_smem));
+        int nbl = 0;
+        GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbl, kern, LIN_THREADS, p->lin_smem));
+        p->lin_kernel = kern;
+        p->resident = h->sm_count * std::max(1, nbl);
+        p->tiles_per_cta = 1;               // few, large tiles: every tile costs one moments->records conversion per output
         p->ts_min = p->ts_gran = LIN_S;
         return GSA_OK;
     }
@@ -154,7 +171,13 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
         // thread-per-sample register kernels: few, large tiles (the per-tile flush costs ~300 instructions per thread)
         p->kind = small_ishi ? PLAN_SMALL_ISHIGAMI : PLAN_SMALL_SOBOLG;
         p->threads = SMALL_THREADS;
-        p->resident = h->sm_count;
+        int occ = 1, rc;
+        TileGeom g0{};
+        if (small_ishi) rc = launch_small_ishigami(h, d, second, est, nullptr, nullptr, 0.0, 0.0, g0, 0, 0, 0, nullptr, &occ);
+        else rc = launch_small_sobolg(h, d, second, est, nullptr, nullptr, nullptr, g0, 0, 0, 0, nullptr, &occ);
+        if (rc) return rc;
+        p->resident = h->sm_count * occ;
+        p->tiles_per_cta = 1;               // the per-tile flush costs ~300 instructions per thread: one big tile per CTA
         p->ts_min = p->ts_gran = SMALL_THREADS;
         return GSA_OK;
     }
@@ -181,13 +204,11 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         if (rc) return rc;
         LinearArgs a;
         a.A = A; a.B = B; a.gram = h->gram.as<double>(); a.g = g; a.d = d; a.t_begin = t0; a.t_end = t1;
-        const int grid_l = std::min(t1 - t0, h->sm_count * 3);
-        switch (lin_DP) {
-#define GSA_LIN_CASE(DPV) case DPV: linear_gram_kernel<DPV><<<grid_l, LIN_THREADS, 0, h->stream>>>(a); break;
-            GSA_LIN_CASE(4) GSA_LIN_CASE(8) GSA_LIN_CASE(12) GSA_LIN_CASE(16) GSA_LIN_CASE(20) GSA_LIN_CASE(24) GSA_LIN_CASE(28) GSA_LIN_CASE(32)
-#undef GSA_LIN_CASE
-            default: return fail(GSA_ERR_UNSUPPORTED, "linear kernel: unsupported padded dimension %d", lin_DP);
-        }
+        const int grid_l = std::min(t1 - t0, resident);
+        const void* kern = lin_kernel;
+        const size_t smem_l = lin_smem;
+        void* kargs[] = {&a};
+        GSA_CUDA(cudaLaunchKernel(kern, dim3(grid_l), dim3(LIN_THREADS), kargs, smem_l, h->stream));
         GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
         h->kernel_timed = true;
         h->last_launches++;

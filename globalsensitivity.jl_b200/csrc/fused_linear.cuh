@@ -10,10 +10,11 @@
 // Cost per sample: O(d^2) FMAs, independent of nout (the reference's path is O(d * nout * (d+2))): the 189 GB
 // `all_y` of config 4 is never formed, and neither is any per-output intermediate.
 //
-// Kernel 1 (gram): lane l of a warp owns ROW l of G and H (extended with a constant-1 coordinate at index d so
-// that first moments come out of the same products); the column values of a sample are broadcast from shared
-// memory with warp-uniform 16-byte loads, so one LDS.128 feeds six DFMA warp instructions.  Warps take
-// different samples of the tile and are combined in order at the end.
+// Kernel 1 (gram): the vectors are extended with a constant-1 coordinate at index d (first moments come out of the same
+// products) and cut into 8-double blocks; every LANE owns one 8x8 block pair -- (a,a) and (b,b) upper triangle, (b,delta),
+// (delta,delta) diagonal -- i.e. 64 register accumulators fed by 16 operands per sample (4 FMA per operand delivered from
+// shared memory; a row-per-lane layout with broadcast loads delivered 1 and ran 3.5x slower, profiles/r1_notes.md).
+// Blocks are stored with a 10-double stride so the per-lane 16-byte loads of a quarter-warp fall in distinct banks.
 // Kernel 2 (records): per (tile, output) turns the tile's moments into the library's standard sufficient-
 // statistics record (double-double sums of y and y^2 recentred exactly), so tiles, replicates and GPUs combine
 // through the same reduce / all-reduce / finalize path as every other model.
@@ -22,28 +23,63 @@
 
 namespace gsa {
 
-constexpr int LIN_THREADS = 256;
-constexpr int LIN_S = 64;      // samples staged per pass (tile granule); wide models stage 48 to stay under 48 KB
-constexpr int LIN_DPMAX = 32;  // d + 1 <= 32
+constexpr int LIN_THREADS = 128;  // ~190 registers/thread: two or three CTAs per SM overlap staging and accumulation
+constexpr int LIN_S = 64;         // samples staged per pass (tile granule)
+constexpr int LIN_DPMAX = 32;     // d + 1 <= 32
+constexpr int LIN_BS = 10;        // shared-memory stride of an 8-double block (padded: conflict-free 16-byte lane loads)
 
 struct LinearArgs {
     const double* A;
     const double* B;
-    double* gram;  // [ntiles][2*DP*DP + DP + DP]: G (DP x DP, row-major), H (DP x DP), D (DP), c (DP; c[d] = #samples)
+    double* gram;  // [ntiles][lin_gram_size(DP)]: G (DP x DP, row-major, full), H (DP x DP), D (DP), c (DP; c[d] = #samples)
     TileGeom g;
     int d, t_begin, t_end;
 };
 
 __host__ __device__ inline int lin_gram_size(int DP) { return 2 * DP * DP + 2 * DP; }
+// 8x8 block pairs of the extended vectors X = [a_ext | b_ext | delta_ext] (NB blocks each):
+//   a x a and b x b upper-triangular block pairs, b x delta (all), delta x delta (diagonal blocks)
+__host__ __device__ inline int lin_num_pairs(int NB, int NBD) { return NB * (NB + 1) + NB * NBD + NBD; }
 
-template <int DP>
+// decode pair p -> (row vector, row block, col vector, col block); vectors: 0 = a, 1 = b, 2 = delta
+__host__ __device__ inline void lin_pair(int p, int NB, int NBD, int& rv, int& rb, int& cv, int& cb) {
+    const int tri = NB * (NB + 1) / 2;
+    if (p < 2 * tri) {
+        rv = cv = p / tri;
+        int q = p % tri;
+        rb = 0;
+        while (q >= NB - rb) { q -= NB - rb; ++rb; }
+        cb = rb + q;
+    } else if (p < 2 * tri + NB * NBD) {
+        const int q = p - 2 * tri;
+        rv = 1; rb = q / NBD; cv = 2; cb = q % NBD;
+    } else {
+        rv = cv = 2;
+        rb = cb = p - 2 * tri - NB * NBD;
+    }
+}
+
+// NB = number of 8-blocks of the extended (d+1)-vector; LPS = lanes per sample (power of two >= number of pairs)
+template <int NB, int LPS>
 __global__ void __launch_bounds__(LIN_THREADS) linear_gram_kernel(LinearArgs a) {
+    constexpr int DP = 8 * NB;
+    constexpr int REC = 3 * NB * LIN_BS;            // doubles per staged sample
+    constexpr int SPW = LPS >= 32 ? 1 : 32 / LPS;   // samples per warp step
+    constexpr int WPS = LPS >= 32 ? LPS / 32 : 1;   // warps per sample
     constexpr int NW = LIN_THREADS / 32;
-    constexpr int REC = 3 * DP;  // per staged sample: a_ext[DP] | b_ext[DP] | delta_ext[DP]
-    constexpr int SS = DP <= 24 ? LIN_S : 48;
-    __shared__ __align__(16) double stage[SS * REC];
-    __shared__ double cshift[DP];
+    constexpr int SLOTS = NW * SPW / WPS;           // samples processed concurrently by the CTA
+    extern __shared__ __align__(16) double lin_sm[];
+    double* stage = lin_sm;                          // [LIN_S][REC]
+    double* cshift = lin_sm + LIN_S * REC;           // [DP]
     const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NBD = (d + 7) / 8, npairs = lin_num_pairs(NB, NBD);
+    // this lane's pair and sample slot
+    const int pair = LPS >= 32 ? (warp % WPS) * 32 + lane : lane % LPS;
+    const int slot = LPS >= 32 ? warp / WPS : warp * SPW + lane / LPS;
+    const bool active = pair < npairs;
+    int rv = 0, rb = 0, cv = 0, cb = 0;
+    if (active) lin_pair(pair, NB, NBD, rv, rb, cv, cb);
+    const int roff = (rv * NB + rb) * LIN_BS, coff = (cv * NB + cb) * LIN_BS;
 
     for (int tile = a.t_begin + blockIdx.x; tile < a.t_end; tile += gridDim.x) {
         int64_t c0, c1;
@@ -54,14 +90,14 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_gram_kernel(LinearArgs a) 
             continue;
         }
         if (threadIdx.x < DP) cshift[threadIdx.x] = threadIdx.x < d ? __ldg(a.A + (size_t)(c0 - a.g.buf_col0) * d + threadIdx.x) : 0.0;
-        double G[DP], H[DP], Dl = 0.0;
+        double acc[64];
 #pragma unroll
-        for (int k = 0; k < DP; ++k) G[k] = H[k] = 0.0;
+        for (int i = 0; i < 64; ++i) acc[i] = 0.0;
         __syncthreads();
 
-        for (int64_t p0 = c0; p0 < c1; p0 += SS) {
-            const int ns = (int)min((int64_t)SS, c1 - p0);
-            // ---- stage: coalesced read of ns rows of A and B, write shifted / differenced records ----
+        for (int64_t p0 = c0; p0 < c1; p0 += LIN_S) {
+            const int ns = (int)min((int64_t)LIN_S, c1 - p0);
+            // ---- stage: coalesced read of ns rows of A and B; write shifted / differenced, block-padded records ----
             const double* ga = a.A + (size_t)(p0 - a.g.buf_col0) * d;
             const double* gb = a.B + (size_t)(p0 - a.g.buf_col0) * d;
             for (int e = threadIdx.x; e < ns * DP; e += LIN_THREADS) {
@@ -75,46 +111,57 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_gram_kernel(LinearArgs a) 
                 } else if (k == d) {
                     va = vb = 1.0;  // constant coordinate: row/column d of G and H carry the first moments
                 }
-                double* r = stage + s * REC;
-                r[k] = va;
-                r[DP + k] = vb;
-                r[2 * DP + k] = vd;
+                double* r = stage + s * REC + (k >> 3) * LIN_BS + (k & 7);
+                r[0] = va;
+                r[NB * LIN_BS] = vb;
+                r[2 * NB * LIN_BS] = vd;
             }
             __syncthreads();
-            // ---- accumulate: warp w takes samples w, w+NW, ...; lane l owns row l ----
-            for (int s = warp; s < ns; s += NW) {
-                const double* r = stage + s * REC;
-                const int l = lane < DP ? lane : 0;
-                const double ra = r[l], rb = r[DP + l], rd = r[2 * DP + l];
-                Dl = fma(rd, rd, Dl);
+            // ---- accumulate: every lane adds the 8x8 outer product of its (row block, column block) ----
+            for (int s = slot; s < ns; s += SLOTS) {
+                if (active) {
+                    const double* r = stage + s * REC;
+                    double rr[8], cc[8];
 #pragma unroll
-                for (int k = 0; k < DP; k += 2) {
-                    const double2 ca = *reinterpret_cast<const double2*>(r + k);            // warp-uniform address
-                    const double2 cb = *reinterpret_cast<const double2*>(r + DP + k);
-                    const double2 cd = *reinterpret_cast<const double2*>(r + 2 * DP + k);
-                    G[k] = fma(ra, ca.x, G[k]);
-                    G[k] = fma(rb, cb.x, G[k]);
-                    G[k + 1] = fma(ra, ca.y, G[k + 1]);
-                    G[k + 1] = fma(rb, cb.y, G[k + 1]);
-                    H[k] = fma(rb, cd.x, H[k]);
-                    H[k + 1] = fma(rb, cd.y, H[k + 1]);
+                    for (int j = 0; j < 4; ++j) {
+                        const double2 x = *reinterpret_cast<const double2*>(r + roff + 2 * j);
+                        const double2 y = *reinterpret_cast<const double2*>(r + coff + 2 * j);
+                        rr[2 * j] = x.x; rr[2 * j + 1] = x.y; cc[2 * j] = y.x; cc[2 * j + 1] = y.y;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[8 * i + j] = fma(rr[i], cc[j], acc[8 * i + j]);
                 }
             }
             __syncthreads();
         }
-        // ---- combine the NW warps in a fixed order: they take turns adding their rows into one buffer (the staging area) ----
-        static_assert(2 * DP * DP + DP <= SS * REC, "staging buffer too small for the warp combine");
-        for (int w = 0; w < NW; ++w) {
-            if (warp == w && lane < DP) {
+        // ---- combine: dense G (a x a + b x b, both triangles), H, D in shared memory; sample slots take turns (fixed order) ----
+        double* G = stage;               // [DP][DP]
+        double* H = stage + DP * DP;     // [DP][DP]
+        double* Dv = H + DP * DP;        // [DP]
+        static_assert(2 * DP * DP + DP <= LIN_S * REC, "staging buffer too small for the combine");
+        for (int i = threadIdx.x; i < 2 * DP * DP + DP; i += LIN_THREADS) stage[i] = 0.0;
+        __syncthreads();
+        for (int turn = 0; turn < SLOTS * 2; ++turn) {
+            // a x a pairs and b x b pairs hit the same G entries: give them separate turns (rv = 0 first, then the rest)
+            const int tslot = turn >> 1, phase = turn & 1;
+            if (active && slot == tslot && ((rv == 0) == (phase == 0))) {
 #pragma unroll
-                for (int k = 0; k < DP; ++k) {
-                    double* pg = stage + lane * DP + k;
-                    double* ph = stage + DP * DP + lane * DP + k;
-                    *pg = w == 0 ? G[k] : *pg + G[k];
-                    *ph = w == 0 ? H[k] : *ph + H[k];
-                }
-                double* pd = stage + 2 * DP * DP + lane;
-                *pd = w == 0 ? Dl : *pd + Dl;
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int l = 8 * rb + i, k = 8 * cb + j;
+                        const double v = acc[8 * i + j];
+                        if (rv == cv && rv < 2) {
+                            G[l * DP + k] += v;
+                            if (rb != cb) G[k * DP + l] += v;   // mirror the off-diagonal blocks
+                        } else if (rv == 1) {
+                            H[l * DP + k] += v;
+                        } else if (i == j) {
+                            Dv[k] += v;
+                        }
+                    }
             }
             __syncthreads();
         }

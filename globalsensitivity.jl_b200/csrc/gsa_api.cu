@@ -158,8 +158,8 @@ static int model_nout(int model, int np, int d, int* nout) {
 }
 
 // Tiles: aim at ~2 tiles per resident CTA; a tile never straddles a replicate.
-static void choose_tiles(int64_t n, int nrep, int resident, int ts_min, int ts_max, int gran, int* ts, int* tpr) {
-    int64_t want_tpr = std::max<int64_t>(1, (2 * (int64_t)resident + nrep - 1) / std::max(nrep, 1));
+static void choose_tiles(int64_t n, int nrep, int resident, int tiles_per_cta, int ts_min, int ts_max, int gran, int* ts, int* tpr) {
+    int64_t want_tpr = std::max<int64_t>(1, ((int64_t)tiles_per_cta * resident + nrep - 1) / std::max(nrep, 1));
     int64_t t = (n + want_tpr - 1) / want_tpr;
     t = (t + gran - 1) / gran * gran;
     t = std::max<int64_t>(t, ts_min);
@@ -224,7 +224,7 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         g.rep_first = (int)(col0 / n);
         const int rep_last = (int)((valid_hi - 1) / n);
         const int nrep = rep_last - g.rep_first + 1;
-        choose_tiles(n, nrep, plan.resident, plan.ts_min, plan.ts_max, plan.ts_gran, &g.ts, &g.tpr);
+        choose_tiles(n, nrep, plan.resident, plan.tiles_per_cta, plan.ts_min, plan.ts_max, plan.ts_gran, &g.ts, &g.tpr);
         g.ntiles = nrep * g.tpr;
         if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)g.ntiles * recsz))) return rc;
 
@@ -323,7 +323,9 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
             // thread-per-sample register kernel: every Y value is read exactly once, straight into registers
             TileGeom g;
             g.n = n; g.col_lo = 0; g.col_hi = (int64_t)o->nboot * n; g.buf_col0 = 0; g.rep_first = 0;
-            choose_tiles(n, o->nboot, std::max(1, h->sm_count / nout), SMALL_THREADS, 1 << 30, SMALL_THREADS, &g.ts, &g.tpr);
+            int occ = 1;
+            if ((rc = launch_small_y(h, d, second, est, Yd, n, nout, step, g, nstat, nullptr, &occ))) return rc;
+            choose_tiles(n, o->nboot, std::max(1, h->sm_count * occ / nout), 1, SMALL_THREADS, 1 << 30, SMALL_THREADS, &g.ts, &g.tpr);
             g.ntiles = g.tpr * o->nboot;
             tpr = g.tpr;
             if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)g.ntiles * recsz))) return rc;

@@ -10,11 +10,16 @@ namespace gsa {
 constexpr int SMALL_DMAX = 12;   // first order only
 constexpr int SMALL_DMAX2 = 8;   // with second order (2D+2 values + 2D + D(D-1)/2 accumulators must fit in registers)
 
+// `occupancy_only` != nullptr: just report the resident CTAs per SM of the kernel that would be launched
 template <class Src, int D, bool SECOND, bool JANSEN>
-int launch_small(gsa_handle* h, SmallArgs<Src>& a) {
+int launch_small(gsa_handle* h, SmallArgs<Src>& a, int* occupancy_only = nullptr) {
     auto kern = small_kernel<Src, D, SECOND, JANSEN>;
     int nb = 0;
     GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SMALL_THREADS, 0));
+    if (occupancy_only) {
+        *occupancy_only = std::max(1, nb);
+        return GSA_OK;
+    }
     const int units = (a.t_end - a.t_begin) * a.nout;
     if (units <= 0) return GSA_OK;
     const int grid = std::min(units, std::max(1, nb) * h->sm_count);
@@ -32,10 +37,10 @@ int launch_small(gsa_handle* h, SmallArgs<Src>& a) {
 
 // declared here, defined in small_y.cu / small_ishigami.cu / small_sobolg.cu
 int launch_small_y(gsa_handle* h, int d, bool second, int est, const double* Y, int64_t n, int nout, int step, const TileGeom& g,
-                   int nstat, double* tile_rec);
+                   int nstat, double* tile_rec, int* occupancy_only = nullptr);
 int launch_small_ishigami(gsa_handle* h, int d, bool second, int est, const double* A, const double* B, double pa, double pb,
-                          const TileGeom& g, int t0, int t1, int nstat, double* tile_rec);
+                          const TileGeom& g, int t0, int t1, int nstat, double* tile_rec, int* occupancy_only = nullptr);
 int launch_small_sobolg(gsa_handle* h, int d, bool second, int est, const double* A, const double* B, const double2* coef,
-                        const TileGeom& g, int t0, int t1, int nstat, double* tile_rec);
+                        const TileGeom& g, int t0, int t1, int nstat, double* tile_rec, int* occupancy_only = nullptr);
 
 }  // namespace gsa
