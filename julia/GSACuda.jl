@@ -1,0 +1,155 @@
+# GSACuda.jl -- the `ccall` shim a GlobalSensitivity.jl maintainer adds to route
+#     gsa(model::DeviceModel, Sobol(...), A, B; batch = true)
+# and the analysis of a precomputed `all_y` through libgsa_cuda.so (include/gsa_cuda.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  It mirrors, call for call, the ctypes
+# binding in globalsensitivity.jl_b200/_lib.py + sobol.py, which IS exercised by tests/ on the B200.
+#
+# Everything that is not Float64 / DeviceModel falls through to the reference's own methods
+# (src/sobol_sensitivity.jl:110-168), because the method below is strictly more specific than `f::Any`.
+module GSACuda
+
+using GlobalSensitivity
+import GlobalSensitivity: gsa, Sobol, SobolResult
+
+const libgsa = get(ENV, "LIBGSA_CUDA", "libgsa_cuda.so")
+
+# ---- mirrors of the C structs (include/gsa_cuda.h) ---------------------------------------------------------
+struct GsaSobolOpts                # gsa_sobol_opts
+    second_order::Cint
+    nboot::Cint
+    conf_level::Cdouble
+    ei_estimator::Cint             # 0 Homma1996, 1 Sobol2007, 2 Jansen1999, 3 Janon2014
+    input_location::Cint           # 0 host, 1 device
+end
+
+struct GsaSobolResult              # gsa_sobol_result: caller-allocated; C_NULL members are skipped
+    S1::Ptr{Cdouble}
+    S1_conf_int::Ptr{Cdouble}
+    S2::Ptr{Cdouble}
+    S2_conf_int::Ptr{Cdouble}
+    ST::Ptr{Cdouble}
+    ST_conf_int::Ptr{Cdouble}
+end
+
+const EI = Dict(:Homma1996 => 0, :Sobol2007 => 1, :Jansen1999 => 2, :Janon2014 => 3)
+
+function check(rc::Cint)
+    rc == 0 && return
+    buf = Vector{UInt8}(undef, 512)
+    ccall((:gsa_last_error, libgsa), Cint, (Ptr{UInt8}, Csize_t), buf, 512)
+    error("libgsa_cuda error $rc: ", unsafe_string(pointer(buf)))
+end
+
+# ---- handle ---------------------------------------------------------------------------------------------------
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    function Handle(device::Integer = -1)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:gsa_create, libgsa), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r))
+        h = new(r[])
+        finalizer(x -> ccall((:gsa_destroy, libgsa), Cint, (Ptr{Cvoid},), x.ptr), h)
+        return h
+    end
+end
+const DEFAULT = Ref{Union{Nothing, Handle}}(nothing)
+default_handle() = something(DEFAULT[], (DEFAULT[] = Handle()))
+
+# ---- the device-model registry replaces the Julia closure `f` -----------------------------------------------
+struct DeviceModel
+    id::Cint
+    params::Vector{Float64}        # a 2-D W is passed as vec(W) (column-major, as the C side expects)
+end
+function DeviceModel(name::AbstractString, params = Float64[])
+    id = Ref{Cint}(0)
+    check(ccall((:gsa_model_lookup, libgsa), Cint, (Cstring, Ref{Cint}), name, id))
+    return DeviceModel(id[], vec(Float64.(params)))
+end
+function nout(m::DeviceModel, d::Integer)
+    n = Ref{Cint}(0)
+    check(ccall((:gsa_model_nout, libgsa), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ref{Cint}),
+                C_NULL, m.id, length(m.params), d, n))
+    return Int(n[])
+end
+
+# ---- result allocation with the reference's shapes (src/sobol_sensitivity.jl:397-404) ------------------------
+function alloc(no, d, nboot, second)
+    multi = no > 1
+    S1 = zeros(no, d); ST = zeros(no, d)
+    S1c = nboot > 1 ? zeros(no, d) : nothing
+    STc = nboot > 1 ? zeros(no, d) : nothing
+    S2 = second ? zeros(d, d, no) : nothing
+    S2c = second && nboot > 1 ? zeros(d, d, no) : nothing
+    p(x) = x === nothing ? Ptr{Cdouble}(C_NULL) : pointer(x)
+    res = GsaSobolResult(p(S1), p(S1c), p(S2), p(S2c), p(ST), p(STc))
+    v(x) = x === nothing ? nothing : (multi ? x : vec(x))
+    m(x) = x === nothing ? nothing : (multi ? x : x[:, :, 1])
+    finish() = SobolResult(v(S1), v(S1c), m(S2), m(S2c), v(ST), v(STc))
+    return res, finish, (S1, S1c, S2, S2c, ST, STc)
+end
+
+# ---- gsa(model, Sobol(...), A, B; batch = true) ----------------------------------------------------------------
+# More specific than `gsa(f, method::Sobol, A::AbstractMatrix{TA}, B::AbstractMatrix; ...)` (reference :110-115).
+function gsa(model::DeviceModel, method::Sobol, A::Matrix{Float64}, B::Matrix{Float64};
+             batch = true, Ei_estimator = :Jansen1999, handle::Handle = default_handle(), kwargs...)
+    size(A) == size(B) || throw(DimensionMismatch("A and B must have the same size"))
+    d, N = size(A)
+    second = 2 in method.order
+    opts = Ref(GsaSobolOpts(second, method.nboot, method.conf_level, EI[Ei_estimator], 0))
+    res, finish, keep = alloc(nout(model, d), d, method.nboot, second)
+    GC.@preserve A B keep model begin
+        check(ccall((:gsa_sobol_run, libgsa), Cint,
+                    (Ptr{Cvoid}, Ref{GsaSobolOpts}, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Int64,
+                     Ref{GsaSobolResult}),
+                    handle.ptr, opts, model.id, model.params, length(model.params), A, B, d, N, Ref(res)))
+    end
+    return finish()
+end
+
+# ---- gsa(model, Sobol(...), p_range; samples): design generated on the GPU (reference :407-417) ---------------
+function generate_design_matrices(n::Integer, lb::Vector{Float64}, ub::Vector{Float64}, num_mats::Integer = 2;
+                                  handle::Handle = default_handle())
+    d = length(lb)
+    mats = [Matrix{Float64}(undef, d, n) for _ in 1:num_mats]
+    ptrs = [pointer(m) for m in mats]
+    GC.@preserve mats begin
+        check(ccall((:gsa_sobol_design, libgsa), Cint,
+                    (Ptr{Cvoid}, Int64, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Int64, Ptr{Ptr{Cdouble}}, Cint),
+                    handle.ptr, n, d, num_mats, lb, ub, 0, n, ptrs, 0))
+    end
+    return mats
+end
+
+function gsa(model::DeviceModel, method::Sobol, p_range::AbstractVector; samples, kwargs...)
+    lb = [float(p[1]) for p in p_range]; ub = [float(p[2]) for p in p_range]
+    AB = generate_design_matrices(samples, lb, ub, 2 * method.nboot)
+    A = reduce(hcat, AB[1:method.nboot]); B = reduce(hcat, AB[(method.nboot + 1):end])
+    return gsa(model, method, A, B; kwargs...)
+end
+
+# ---- estimator-only entry: any Julia closure keeps producing all_y, the GPU replaces gsa_sobol_all_y_analysis ---
+# (reference :169-405).  `all_y` is a Vector (scalar model) or an nout x cols Matrix.
+function gsa_sobol_all_y_analysis(method::Sobol, all_y::VecOrMat{Float64}, d::Integer, n::Integer,
+                                  Ei_estimator = :Jansen1999; handle::Handle = default_handle())
+    multi = all_y isa AbstractMatrix
+    no = multi ? size(all_y, 1) : 1
+    second = 2 in method.order
+    opts = Ref(GsaSobolOpts(second, method.nboot, method.conf_level, EI[Ei_estimator], 0))
+    res, finish, keep = alloc(no, d, method.nboot, second)
+    GC.@preserve all_y keep begin
+        check(ccall((:gsa_sobol_analyze_y, libgsa), Cint,
+                    (Ptr{Cvoid}, Ref{GsaSobolOpts}, Ptr{Cdouble}, Cint, Cint, Int64, Ref{GsaSobolResult}),
+                    handle.ptr, opts, all_y, no, d, n, Ref(res)))
+    end
+    r = finish()
+    # a 1 x cols matrix is still "multioutput" in the reference (:144): keep 1 x d results
+    if multi && no == 1
+        r = SobolResult(reshape(r.S1, 1, :), r.S1_Conf_Int === nothing ? nothing : reshape(r.S1_Conf_Int, 1, :),
+                        r.S2 === nothing ? nothing : reshape(r.S2, d, d, 1),
+                        r.S2_Conf_Int === nothing ? nothing : reshape(r.S2_Conf_Int, d, d, 1),
+                        reshape(r.ST, 1, :), r.ST_Conf_Int === nothing ? nothing : reshape(r.ST_Conf_Int, 1, :))
+    end
+    return r
+end
+
+end # module
