@@ -53,13 +53,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     blob = os.path.join(obj_dir, "directions_blob.o")
     subprocess.check_call(["/usr/bin/gcc", "-c", os.path.join(CSRC, "directions_blob.S"), f'-DGSA_TABLE_PATH="{TABLE}"', "-o", blob])
+    # the generic kernel with an unresolved model, as a relocatable cubin that gsa_model_register_fatbin links at run time
+    ucu = os.path.join(obj_dir, "user_kernel.cu")
+    shutil.copyfile(os.path.join(CSRC, "user_kernel.cu.in"), ucu)
+    ucubin = os.path.join(obj_dir, "user_kernel.cubin")
+    subprocess.check_call([nvcc(), "-ccbin", HOST_CXX, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-rdc=true", "-cubin", "-I", CSRC, "-o", ucubin, ucu])
+    ublob = os.path.join(obj_dir, "user_blob.o")
+    subprocess.check_call(["/usr/bin/gcc", "-c", os.path.join(CSRC, "user_blob.S"), f'-DGSA_USER_CUBIN_PATH="{ucubin}"', "-o", ublob])
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [nvcc(), "-ccbin", HOST_CXX, "-shared", *ARCH, "-o", OUT, *objs, blob, "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    link = [nvcc(), "-ccbin", HOST_CXX, "-shared", *ARCH, "-o", OUT, *objs, blob, ublob, "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     subprocess.check_call(link)
     return OUT
 

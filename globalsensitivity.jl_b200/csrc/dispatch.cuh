@@ -53,18 +53,28 @@ static int plan_generic(gsa_handle* h, FusedPlan* p) {
         return fail(GSA_ERR_UNSUPPORTED, "generic fused kernel supports nout <= %d (got %d)", GENERIC_NOMAX, p->nout);
     if (p->second && p->d * p->nout > GENERIC_YMAX)
         return fail(GSA_ERR_UNSUPPORTED, "generic second-order kernel supports d*nout <= %d (got %d)", GENERIC_YMAX, p->d * p->nout);
-    GenericKernel k = p->second ? generic_kernel_for<true>(p->model) : generic_kernel_for<false>(p->model);
+    const void* k = nullptr;
+    const bool user = p->model >= GSA_MODEL_USER_BASE;
+    if (user) {
+        const int idx = p->model - GSA_MODEL_USER_BASE;
+        if (idx >= (int)h->user_models.size()) return fail(GSA_ERR_INVALID, "unknown user model id %d for this handle", p->model);
+        k = (const void*)(p->second ? h->user_models[idx].k_second : h->user_models[idx].k_first);
+    } else {
+        k = (const void*)(p->second ? generic_kernel_for<true>(p->model) : generic_kernel_for<false>(p->model));
+    }
     if (!k) return fail(GSA_ERR_INVALID, "unknown model id %d", p->model);
     const size_t rec_bytes = sizeof(double) * (size_t)p->nstat * p->nout;
-    int warps = (int)std::min<size_t>(8, (160u << 10) / rec_bytes);
+    int warps = (int)std::min<size_t>(8, ((user ? 48u : 160u) << 10) / rec_bytes);   // linked kernels: stay within the default 48 KB
     if (warps < 1) return fail(GSA_ERR_UNSUPPORTED, "statistics record of %zu bytes does not fit in shared memory", rec_bytes);
     p->kind = PLAN_GENERIC;
-    p->kernel = (const void*)k;
+    p->kernel = k;
     p->threads = 32 * warps;
     p->smem = rec_bytes * warps;
-    if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-    int nb = 0;
-    GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));
+    int nb = 2;
+    if (!user) {
+        if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+        GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));
+    }
     p->resident = std::max(1, nb) * h->sm_count;
     p->ts_min = 32 * warps;
     p->ts_gran = 32 * warps;
@@ -149,7 +159,7 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
         const int NB = p->lin_DP / 8, NBD = (d + 7) / 8, np_ = lin_num_pairs(NB, NBD);
         int lps = 4;
         while (lps < np_) lps <<= 1;
-        p->lin_smem = sizeof(double) * ((size_t)LIN_S * 3 * NB * LIN_BS + p->lin_DP);
+        p->lin_smem = lin_smem_bytes(NB, d);
         const void* kern = nullptr;
 #define GSA_LIN_CASE(NBV, LPSV) if (NB == NBV && lps == LPSV) kern = (const void*)linear_gram_kernel<NBV, LPSV>;
         GSA_LIN_CASE(1, 4) GSA_LIN_CASE(2, 16) GSA_LIN_CASE(3, 32) GSA_LIN_CASE(4, 64)
@@ -192,7 +202,8 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         GenericArgs a;
         a.A = A; a.B = B; a.params = h->params.as<double>(); a.tile_rec = h->tile_rec.as<double>();
         a.g = g; a.d = d; a.np = np; a.nout = nout; a.nstat = nstat; a.est = est; a.t_begin = t0; a.t_end = t1;
-        ((GenericKernel)kernel)<<<grid, threads, smem, h->stream>>>(a);
+        void* kargs[] = {&a};
+        GSA_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, h->stream));   // also takes cudaKernel_t handles
     }
     else if (kind == PLAN_SMALL_ISHIGAMI)
         return launch_small_ishigami(h, d, second, est, A, B, pa, pb, g, t0, t1, nstat, h->tile_rec.as<double>());

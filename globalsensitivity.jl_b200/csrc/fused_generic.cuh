@@ -30,7 +30,7 @@ struct GenericArgs {
 };
 
 template <class Model, bool SECOND>
-__global__ void __launch_bounds__(256) fused_generic_kernel(GenericArgs a) {
+__device__ __forceinline__ void fused_generic_body(const GenericArgs& a) {
     extern __shared__ double smem[];  // [warps][nout*nstat]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int d = a.d, nout = a.nout, nstat = a.nstat, est = a.est;
@@ -57,9 +57,9 @@ __global__ void __launch_bounds__(256) fused_generic_kernel(GenericArgs a) {
             const double* bs = a.B + (size_t)(s - a.g.buf_col0) * d;
             if (active) {
                 for (int k = 0; k < d; ++k) x[k] = __ldg(bs + k);
-                Model::eval(x, d, a.params, a.np, yB);
+                Model::eval(x, d, a.params, a.np, yB, nout);
                 for (int k = 0; k < d; ++k) x[k] = __ldg(as + k);
-                Model::eval(x, d, a.params, a.np, yA);
+                Model::eval(x, d, a.params, a.np, yA, nout);
 #pragma unroll
                 for (int o = 0; o < GENERIC_NOMAX; ++o)
                     if (o < nout) {
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) fused_generic_kernel(GenericArgs a) {
                 if (active) {
                     double keep = x[k];
                     x[k] = __ldg(bs + k);
-                    Model::eval(x, d, a.params, a.np, yk);
+                    Model::eval(x, d, a.params, a.np, yk, nout);
                     x[k] = keep;
                 }
                 for (int o = 0; o < nout; ++o) {
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) fused_generic_kernel(GenericArgs a) {
                     if (active) {
                         double keep = x[k];
                         x[k] = __ldg(as + k);
-                        Model::eval(x, d, a.params, a.np, yk);
+                        Model::eval(x, d, a.params, a.np, yk, nout);
                         x[k] = keep;
                         for (int o = 0; o < nout; ++o) yBA[k * nout + o] = yk[o];
                     }
@@ -152,6 +152,11 @@ __global__ void __launch_bounds__(256) fused_generic_kernel(GenericArgs a) {
         }
         __syncthreads();
     }
+}
+
+template <class Model, bool SECOND>
+__global__ void __launch_bounds__(256) fused_generic_kernel(GenericArgs a) {
+    fused_generic_body<Model, SECOND>(a);
 }
 
 }  // namespace gsa

@@ -24,7 +24,7 @@
 namespace gsa {
 
 constexpr int LIN_THREADS = 128;  // ~190 registers/thread: two or three CTAs per SM overlap staging and accumulation
-constexpr int LIN_S = 64;         // samples staged per pass (tile granule)
+constexpr int LIN_S = 48;         // samples staged per pass (tile granule)
 constexpr int LIN_DPMAX = 32;     // d + 1 <= 32
 constexpr int LIN_BS = 10;        // shared-memory stride of an 8-double block (padded: conflict-free 16-byte lane loads)
 
@@ -36,6 +36,18 @@ struct LinearArgs {
     int d, t_begin, t_end;
 };
 
+#ifdef __CUDACC__
+__device__ __forceinline__ void cp_async8_l(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_l(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+#endif
+// dynamic shared memory of linear_gram_kernel (bytes)
+__host__ __device__ inline size_t lin_smem_bytes(int NB, int d) {
+    return sizeof(double) * ((size_t)LIN_S * 3 * NB * 10 + 8 * NB + 4 * (size_t)LIN_S * d);
+}
 __host__ __device__ inline int lin_gram_size(int DP) { return 2 * DP * DP + 2 * DP; }
 // 8x8 block pairs of the extended vectors X = [a_ext | b_ext | delta_ext] (NB blocks each):
 //   a x a and b x b upper-triangular block pairs, b x delta (all), delta x delta (diagonal blocks)
@@ -69,9 +81,11 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_gram_kernel(LinearArgs a) 
     constexpr int NW = LIN_THREADS / 32;
     constexpr int SLOTS = NW * SPW / WPS;           // samples processed concurrently by the CTA
     extern __shared__ __align__(16) double lin_sm[];
-    double* stage = lin_sm;                          // [LIN_S][REC]
+    double* stage = lin_sm;                          // [LIN_S][REC]   shifted / differenced, block-padded records
     double* cshift = lin_sm + LIN_S * REC;           // [DP]
+    double* raw = cshift + DP;                       // [2][2][LIN_S * d]  raw A and B rows of the next pass (cp.async ring)
     const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rawsz = LIN_S * d;
     const int NBD = (d + 7) / 8, npairs = lin_num_pairs(NB, NBD);
     // this lane's pair and sample slot
     const int pair = LPS >= 32 ? (warp % WPS) * 32 + lane : lane % LPS;
@@ -93,18 +107,42 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_gram_kernel(LinearArgs a) 
         double acc[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) acc[i] = 0.0;
-        __syncthreads();
 
-        for (int64_t p0 = c0; p0 < c1; p0 += LIN_S) {
+        // asynchronous copy of the raw rows of one pass (contiguous ns*d doubles of A and of B) into ring slot `buf`
+        auto prefetch = [&](int64_t p0, int buf) {
+            if (p0 < c1) {
+                const int cnt = (int)min((int64_t)LIN_S, c1 - p0) * d;
+                const double* ga = a.A + (size_t)(p0 - a.g.buf_col0) * d;
+                const double* gb = a.B + (size_t)(p0 - a.g.buf_col0) * d;
+                double* ra = raw + (size_t)buf * 2 * rawsz;
+                double* rbuf = ra + rawsz;
+                const bool al16 = ((reinterpret_cast<uintptr_t>(ga) | reinterpret_cast<uintptr_t>(gb)) & 15) == 0 && (rawsz % 2 == 0);
+                if (al16) {
+                    for (int e = 2 * threadIdx.x; e < cnt; e += 2 * LIN_THREADS) {
+                        if (e + 1 < cnt) { cp_async16_l(ra + e, ga + e); cp_async16_l(rbuf + e, gb + e); }
+                        else { cp_async8_l(ra + e, ga + e); cp_async8_l(rbuf + e, gb + e); }
+                    }
+                } else {
+                    for (int e = threadIdx.x; e < cnt; e += LIN_THREADS) { cp_async8_l(ra + e, ga + e); cp_async8_l(rbuf + e, gb + e); }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        prefetch(c0, 0);
+        int buf = 0;
+        for (int64_t p0 = c0; p0 < c1; p0 += LIN_S, buf ^= 1) {
             const int ns = (int)min((int64_t)LIN_S, c1 - p0);
-            // ---- stage: coalesced read of ns rows of A and B; write shifted / differenced, block-padded records ----
-            const double* ga = a.A + (size_t)(p0 - a.g.buf_col0) * d;
-            const double* gb = a.B + (size_t)(p0 - a.g.buf_col0) * d;
+            prefetch(p0 + LIN_S, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncthreads();   // every thread's copies of this pass are visible; the previous accumulate is finished
+            // ---- transform: raw rows -> shifted / differenced, block-padded records ----
+            const double* ra = raw + (size_t)buf * 2 * rawsz;
+            const double* rbuf = ra + rawsz;
             for (int e = threadIdx.x; e < ns * DP; e += LIN_THREADS) {
                 const int s = e / DP, k = e - s * DP;
                 double va = 0.0, vb = 0.0, vd = 0.0;
                 if (k < d) {
-                    const double xa = ldg_stream(ga + s * d + k), xb = ldg_stream(gb + s * d + k), c = cshift[k];
+                    const double xa = ra[s * d + k], xb = rbuf[s * d + k], c = cshift[k];
                     va = xa - c;
                     vb = xb - c;
                     vd = xb - xa;
@@ -134,8 +172,9 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_gram_kernel(LinearArgs a) 
                         for (int j = 0; j < 8; ++j) acc[8 * i + j] = fma(rr[i], cc[j], acc[8 * i + j]);
                 }
             }
-            __syncthreads();
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
         // ---- combine: dense G (a x a + b x b, both triangles), H, D in shared memory; sample slots take turns (fixed order) ----
         double* G = stage;               // [DP][DP]
         double* H = stage + DP * DP;     // [DP][DP]

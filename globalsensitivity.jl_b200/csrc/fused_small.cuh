@@ -24,19 +24,80 @@ struct SmallShape {
     static constexpr int NPAIR = SECOND ? D * (D - 1) / 2 : 0;
 };
 
+// ---- per-thread asynchronous staging (cp.async / LDGSTS) ---------------------------------------------------------------
+// Every thread copies the data of ITS OWN future samples into a private slot of a shared-memory ring and later reads only
+// that slot back, so the pipeline needs no barrier at all -- only the per-thread cp.async group counter.  This keeps
+// SMALL_NST-1 samples per thread in flight without spending registers on them (the register version of this kernel was
+// latency-bound at 8 warps/SM: 59-65 % long-scoreboard stalls, profiles/r1_notes.md).
+constexpr int SMALL_NST = 3;
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- sources -------------------------------------------------------------------------------------------------------
+// issue(st, ...) : start the asynchronous copy of one sample's raw data into the thread's slot of stage `st`
+// fetch(st, y)   : read the slot back and produce the STEP model values
 template <int D, bool SECOND>
 struct YSource {
     static constexpr bool kIsY = true;
+    static constexpr bool kAsync = true;    // cp.async ring: 4.4 -> 6.1 TB/s at d = 8 (profiles/r1_notes.md)
+    static constexpr int STEP = SmallShape<D, SECOND>::STEP;
+    static constexpr int kStageDoubles = STEP * SMALL_THREADS;   // [block b][thread]
     const double* Y;  // element (o, col) at Y[o + nout*col]
     int64_t n;
     int nout, step;
     // r = replicate, s = sample position inside the replicate, o = output
-    __device__ __forceinline__ void load(int r, int64_t s, int o, double (&y)[SmallShape<D, SECOND>::STEP]) const {
+    __device__ __forceinline__ void issue(double* st, int r, int64_t s, int o) const {
         const double* p = Y + o + (int64_t)nout * ((int64_t)r * step * n + s);
         const int64_t bs = (int64_t)nout * n;
 #pragma unroll
-        for (int b = 0; b < SmallShape<D, SECOND>::STEP; ++b) y[b] = ldg_stream(p + bs * b);
+        for (int b = 0; b < STEP; ++b) cp_async8(st + b * SMALL_THREADS + threadIdx.x, p + bs * b);
+    }
+    __device__ __forceinline__ void fetch(const double* st, double (&y)[STEP]) const {
+#pragma unroll
+        for (int b = 0; b < STEP; ++b) y[b] = st[b * SMALL_THREADS + threadIdx.x];
+    }
+};
+
+// raw A/B rows of a sample: row stride RS doubles in shared memory, chosen so that a quarter-warp's 16-byte reads (even D)
+// or a half-warp's 8-byte reads (odd D) fall in distinct banks
+template <int D>
+struct RowStage {
+    static constexpr int RS = (D % 2) ? D : (((D / 2) % 2) ? D : D + 2);
+    static constexpr int kStageDoubles = 2 * RS * SMALL_THREADS;
+    __device__ __forceinline__ static void issue(double* st, const double* A, const double* B, int64_t row) {
+        double* sa = st + threadIdx.x * RS;
+        double* sb = sa + RS * SMALL_THREADS;
+        const double* pa = A + row * D;
+        const double* pb = B + row * D;
+        if constexpr (D % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < D; i += 2) { cp_async16(sa + i, pa + i); cp_async16(sb + i, pb + i); }
+        } else {
+#pragma unroll
+            for (int i = 0; i < D; ++i) { cp_async8(sa + i, pa + i); cp_async8(sb + i, pb + i); }
+        }
+    }
+    __device__ __forceinline__ static void fetch(const double* st, double (&a)[D], double (&b)[D]) {
+        const double* sa = st + threadIdx.x * RS;
+        const double* sb = sa + RS * SMALL_THREADS;
+        if constexpr (D % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < D; i += 2) {
+                const double2 va = *reinterpret_cast<const double2*>(sa + i), vb = *reinterpret_cast<const double2*>(sb + i);
+                a[i] = va.x; a[i + 1] = va.y; b[i] = vb.x; b[i + 1] = vb.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < D; ++i) { a[i] = sa[i]; b[i] = sb[i]; }
+        }
     }
 };
 
@@ -59,13 +120,25 @@ __device__ __forceinline__ void load_rows(const double* A, const double* B, int6
 template <int D, bool SECOND>
 struct IshigamiSource {
     static constexpr bool kIsY = false;
+    static constexpr bool kAsync = false;   // compute-heavy: the ring did not pay off here (0.140 -> 0.159 ms on config 3)
+    static constexpr int STEP = SmallShape<D, SECOND>::STEP;
+    static constexpr int kStageDoubles = RowStage<D>::kStageDoubles;
     const double* A;
     const double* B;
     int64_t buf_col0;  // global column of row 0 of A/B
     double pa, pb;     // the model's a, b
-    __device__ __forceinline__ void load(int64_t col, double (&y)[SmallShape<D, SECOND>::STEP]) const {
+    __device__ __forceinline__ void issue(double* st, int64_t col) const { RowStage<D>::issue(st, A, B, col - buf_col0); }
+    __device__ __forceinline__ void fetch(const double* st, double (&y)[STEP]) const {
+        double a[D], b[D];
+        RowStage<D>::fetch(st, a, b);
+        eval(a, b, y);
+    }
+    __device__ __forceinline__ void load(int64_t col, double (&y)[STEP]) const {
         double a[D], b[D];
         load_rows<D>(A, B, col - buf_col0, a, b);
+        eval(a, b, y);
+    }
+    __device__ __forceinline__ void eval(double (&a)[D], double (&b)[D], double (&y)[STEP]) const {
         // shared terms: f = s1 + pa*s2^2 + pb*x3^4*s1   (test/sobol_method.jl:4-8)
         const double s1a = sin(a[0]), s1b = sin(b[0]);
         double t = sin(a[1]); const double q2a = pa * (t * t);
@@ -88,13 +161,25 @@ struct IshigamiSource {
 template <int D, bool SECOND>
 struct SobolGSource {
     static constexpr bool kIsY = false;
+    static constexpr bool kAsync = false;
+    static constexpr int STEP = SmallShape<D, SECOND>::STEP;
+    static constexpr int kStageDoubles = RowStage<D>::kStageDoubles;
     const double* A;
     const double* B;
     const double2* coef;  // (c1_k, c0_k): g_k(x) = |x-0.5|*c1_k + c0_k
     int64_t buf_col0;
-    __device__ __forceinline__ void load(int64_t col, double (&y)[SmallShape<D, SECOND>::STEP]) const {
+    __device__ __forceinline__ void issue(double* st, int64_t col) const { RowStage<D>::issue(st, A, B, col - buf_col0); }
+    __device__ __forceinline__ void fetch(const double* st, double (&y)[STEP]) const {
+        double a[D], b[D];
+        RowStage<D>::fetch(st, a, b);
+        eval(a, b, y);
+    }
+    __device__ __forceinline__ void load(int64_t col, double (&y)[STEP]) const {
         double a[D], b[D];
         load_rows<D>(A, B, col - buf_col0, a, b);
+        eval(a, b, y);
+    }
+    __device__ __forceinline__ void eval(double (&a)[D], double (&b)[D], double (&y)[STEP]) const {
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             const double2 c = __ldg(coef + i);
@@ -128,13 +213,23 @@ struct SmallArgs {
     int nout, nstat, est, t_begin, t_end;
 };
 
+// dynamic shared memory: the staging ring, re-used by the tile flush ([SMALL_CH][SMALL_THREADS+1] doubles), + 8 dd slots per warp
+template <class Src>
+constexpr size_t small_smem_bytes() {
+    size_t ring = Src::kAsync ? (size_t)SMALL_NST * Src::kStageDoubles : 0, flush = (size_t)SMALL_CH * (SMALL_THREADS + 1);
+    return sizeof(double) * ((ring > flush ? ring : flush) + (SMALL_THREADS / 32) * 8);
+}
+
 template <class Src, int D, bool SECOND, bool JANSEN>
 __global__ void __launch_bounds__(SMALL_THREADS) small_kernel(SmallArgs<Src> a) {
     using Sh = SmallShape<D, SECOND>;
     constexpr int NE = JANSEN ? 1 : 3;
     constexpr int NACC = D + NE * D + Sh::NPAIR;
-    __shared__ double sm[SMALL_CH][SMALL_THREADS + 1];
-    __shared__ double sdd[SMALL_THREADS / 32][8];
+    constexpr size_t RING = Src::kAsync ? (size_t)SMALL_NST * Src::kStageDoubles : 0, FLUSH = (size_t)SMALL_CH * (SMALL_THREADS + 1);
+    extern __shared__ __align__(16) double small_sm[];
+    double* ring = small_sm;
+    double (*sm)[SMALL_THREADS + 1] = reinterpret_cast<double (*)[SMALL_THREADS + 1]>(small_sm);
+    double (*sdd)[8] = reinterpret_cast<double (*)[8]>(small_sm + (RING > FLUSH ? RING : FLUSH));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int est = a.est;
     const int ntile_units = (a.t_end - a.t_begin) * a.nout;
@@ -149,10 +244,32 @@ __global__ void __launch_bounds__(SMALL_THREADS) small_kernel(SmallArgs<Src> a) 
         for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
         dd sy{0, 0}, syy{0, 0}, sa{0, 0}, saa{0, 0};
 
+        auto issue = [&](int64_t col, int stage) {
+            if (col < c1) {
+                double* st = ring + (size_t)stage * Src::kStageDoubles;
+                if constexpr (Src::kIsY) a.src.issue(st, r, col - (int64_t)r * a.g.n, o);
+                else a.src.issue(st, col);
+            }
+            cp_async_commit();   // always commit (possibly empty) so that the group count stays uniform
+        };
+        // prologue: SMALL_NST-1 samples in flight
+        if constexpr (Src::kAsync) {
+#pragma unroll
+            for (int p = 0; p < SMALL_NST - 1; ++p) issue(c0 + tid + (int64_t)p * SMALL_THREADS, p);
+        }
+        int stage = 0;
         for (int64_t col = c0 + tid; col < c1; col += SMALL_THREADS) {
             double y[Sh::STEP];
-            if constexpr (Src::kIsY) a.src.load(r, col - (int64_t)r * a.g.n, o, y);
-            else a.src.load(col, y);
+            if constexpr (Src::kAsync) {
+                int pstage = stage + SMALL_NST - 1;
+                if (pstage >= SMALL_NST) pstage -= SMALL_NST;
+                issue(col + (int64_t)(SMALL_NST - 1) * SMALL_THREADS, pstage);
+                cp_async_wait<SMALL_NST - 1>();   // this thread's copy for `col` has landed
+                a.src.fetch(ring + (size_t)stage * Src::kStageDoubles, y);
+                if (++stage == SMALL_NST) stage = 0;
+            } else {
+                a.src.load(col, y);
+            }
             const double fa = y[0], fb = y[1];
             dd_add(sy, fa); dd_add(sy, fb);
             dd_add_sq(syy, fa); dd_add_sq(syy, fb);
@@ -182,6 +299,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) small_kernel(SmallArgs<Src> a) 
                     for (int j = k + 1; j < D; ++j, ++p) acc[p] += y[2 + D + k] * y[2 + j] - fafb;   // :197
             }
         }
+        if constexpr (Src::kAsync) cp_async_wait<0>();
 
         // ---- tile flush ----
         double* rec = a.tile_rec + ((size_t)tile * a.nout + o) * a.nstat;

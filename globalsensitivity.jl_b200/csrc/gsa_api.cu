@@ -134,7 +134,13 @@ static int check_opts(const gsa_sobol_opts* o) {
     return GSA_OK;
 }
 
-static int model_nout(int model, int np, int d, int* nout) {
+static int model_nout(gsa_handle* h, int model, int np, int d, int* nout) {
+    if (model >= GSA_MODEL_USER_BASE) {
+        const int idx = model - GSA_MODEL_USER_BASE;
+        if (!h || idx >= (int)h->user_models.size()) return fail(GSA_ERR_INVALID, "unknown user model id %d for this handle", model);
+        *nout = h->user_models[idx].nout;
+        return GSA_OK;
+    }
     switch (model) {
         case GSA_MODEL_ISHIGAMI:
             if (d < 3) return fail(GSA_ERR_INVALID, "ishigami needs d >= 3 (got %d)", d);
@@ -199,7 +205,7 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
     if (!partials) return fail(GSA_ERR_INVALID, "partials is NULL");
     if (ncols > 0 && (!A || !B)) return fail(GSA_ERR_INVALID, "A or B is NULL");
     int nout = 0;
-    if ((rc = model_nout(model, np, d, &nout))) return rc;
+    if ((rc = model_nout(h, model, np, d, &nout))) return rc;
     const bool second = o->second_order != 0;
     const int est = o->ei_estimator;
     const int nstat = stat_count(d, est, second), recsz = nstat * nout;
@@ -442,6 +448,8 @@ int gsa_destroy(gsa_handle* h) {
         if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
         DevBuf* bufs[] = {&h->tile_rec, &h->partials, &h->params, &h->vtab, &h->lbub, &h->stage[0], &h->stage[1], &h->dev_in[0], &h->dev_in[1], &h->ybuf, &h->aux, &h->gram};
         for (DevBuf* b : bufs) b->release();
+        for (auto& um : h->user_models)
+            if (um.lib) cudaLibraryUnload(um.lib);
         for (int b = 0; b < 2; ++b) {
             if (h->pinned[b]) cudaFreeHost(h->pinned[b]);
             if (h->ev_copy[b]) cudaEventDestroy(h->ev_copy[b]);
@@ -485,13 +493,16 @@ int gsa_model_lookup(const char* name, int* id) {
     return fail(GSA_ERR_INVALID, "unknown model '%s'", name);
 }
 
-int gsa_model_nout(gsa_handle*, int model_id, int nparams, int d, int* nout) {
+int gsa_model_nout(gsa_handle* h, int model_id, int nparams, int d, int* nout) {
     if (!nout) return fail(GSA_ERR_INVALID, "nout is NULL");
-    return model_nout(model_id, nparams, d, nout);
+    return model_nout(h, model_id, nparams, d, nout);
 }
 
-int gsa_model_register_fatbin(gsa_handle*, const void*, size_t, const char*, int, int*) {
-    return fail(GSA_ERR_UNSUPPORTED, "user device models are not implemented in this build yet");
+int gsa_model_register_fatbin(gsa_handle* h, const void* image, size_t len, const char* symbol, int nout, int* model_id) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    return register_user_model(h, image, len, symbol, nout, model_id);
 }
 
 int gsa_sobol_nstat(const gsa_sobol_opts* o, int d, int* nstat) {
@@ -616,7 +627,7 @@ int gsa_sobol_run(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const
     DeviceGuard guard(h->device);
     int nout = 0;
     if (d < 1) return fail(GSA_ERR_INVALID, "d must be >= 1");
-    if ((rc = model_nout(model_id, nparams, d, &nout))) return rc;
+    if ((rc = model_nout(h, model_id, nparams, d, &nout))) return rc;
     const int nstat = stat_count(d, opts->ei_estimator, opts->second_order != 0);
     if ((rc = h->partials.reserve(sizeof(double) * (size_t)opts->nboot * nout * nstat))) return rc;
     if ((rc = partials_impl(h, opts, model_id, params, nparams, A, B, d, N, 0, N, h->partials.as<double>()))) return rc;

@@ -9,6 +9,8 @@
 
 #include "../../include/gsa_cuda.h"
 
+struct gsa_handle;
+
 namespace gsa {
 
 void set_error(const char* fmt, ...);
@@ -39,6 +41,15 @@ void direction_numbers(int dim_first, int ndim, uint32_t* V /* ndim x 32 */);
 
 }  // namespace gsa
 
+namespace gsa {
+struct UserModelEntry {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t k_first = nullptr, k_second = nullptr;
+    int nout = 1;
+};
+int register_user_model(gsa_handle* h, const void* image, size_t len, const char* symbol, int nout, int* model_id);
+}  // namespace gsa
+
 struct gsa_handle {
     int device = 0;
     int sm_count = 0;
@@ -48,6 +59,7 @@ struct gsa_handle {
     gsa::DevBuf tile_rec, partials, params, vtab, lbub, stage[2], dev_in[2], ybuf, aux, gram;
     void* pinned[2] = {nullptr, nullptr};
     size_t pinned_cap = 0;
+    std::vector<gsa::UserModelEntry> user_models;
     std::vector<uint32_t> vhost;  // cached direction numbers [vdims][32]
     int vdims = 0;
     float last_ms = 0.f;

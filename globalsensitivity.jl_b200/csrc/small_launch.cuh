@@ -14,8 +14,10 @@ constexpr int SMALL_DMAX2 = 8;   // with second order (2D+2 values + 2D + D(D-1)
 template <class Src, int D, bool SECOND, bool JANSEN>
 int launch_small(gsa_handle* h, SmallArgs<Src>& a, int* occupancy_only = nullptr) {
     auto kern = small_kernel<Src, D, SECOND, JANSEN>;
+    constexpr size_t smem = small_smem_bytes<Src>();
+    if (smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nb = 0;
-    GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SMALL_THREADS, 0));
+    GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SMALL_THREADS, smem));
     if (occupancy_only) {
         *occupancy_only = std::max(1, nb);
         return GSA_OK;
@@ -24,7 +26,7 @@ int launch_small(gsa_handle* h, SmallArgs<Src>& a, int* occupancy_only = nullptr
     if (units <= 0) return GSA_OK;
     const int grid = std::min(units, std::max(1, nb) * h->sm_count);
     GSA_CUDA(cudaEventRecord(h->evk0, h->stream));
-    kern<<<grid, SMALL_THREADS, 0, h->stream>>>(a);
+    kern<<<grid, SMALL_THREADS, smem, h->stream>>>(a);
     GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
     h->kernel_timed = true;
     h->last_launches++;

@@ -1,0 +1,141 @@
+// user_models.cu -- gsa_model_register_fatbin: link a user's `__device__` model into the generic fused kernel.
+//
+// The kernel body with an unresolved `gsa_user_model` symbol is embedded in this library as a relocatable sm_100a cubin
+// (user_blob.S).  Registration links it against the user's image (fatbin / cubin / PTX / LTO-IR / object, auto-detected)
+// with nvJitLink -- loaded with dlopen so that the library itself has no link-time dependency on it -- and loads the
+// result with cudaLibraryLoadData.  If the user's symbol has another name, a six-line PTX trampoline is added to the link.
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gsa_internal.h"
+
+extern "C" const unsigned char gsa_user_kernel_blob[];
+extern "C" const unsigned char gsa_user_kernel_blob_end[];
+
+namespace gsa {
+
+namespace {
+
+// the slice of the nvJitLink API we need (nvJitLink.h), resolved at run time
+typedef void* nvJitLinkHandle;
+enum { NVJL_INPUT_CUBIN = 1, NVJL_INPUT_PTX = 2, NVJL_INPUT_ANY = 10 };
+struct JitLinkApi {
+    void* so = nullptr;
+    int (*Create)(nvJitLinkHandle*, uint32_t, const char**) = nullptr;
+    int (*Destroy)(nvJitLinkHandle*) = nullptr;
+    int (*AddData)(nvJitLinkHandle, int, const void*, size_t, const char*) = nullptr;
+    int (*Complete)(nvJitLinkHandle) = nullptr;
+    int (*GetLinkedCubinSize)(nvJitLinkHandle, size_t*) = nullptr;
+    int (*GetLinkedCubin)(nvJitLinkHandle, void*) = nullptr;
+    int (*GetErrorLogSize)(nvJitLinkHandle, size_t*) = nullptr;
+    int (*GetErrorLog)(nvJitLinkHandle, char*) = nullptr;
+};
+
+void* sym(void* so, const char* base) {
+    // exported names are versioned: __nvJitLinkCreate_12_9 ... _12_0
+    char name[96];
+    for (int minor = 9; minor >= 0; --minor) {
+        snprintf(name, sizeof(name), "__%s_12_%d", base, minor);
+        if (void* p = dlsym(so, name)) return p;
+    }
+    return dlsym(so, base);
+}
+
+int load_api(JitLinkApi& a) {
+    if (a.so) return GSA_OK;
+    const char* names[] = {"libnvJitLink.so.12", "/usr/local/cuda/lib64/libnvJitLink.so.12", "libnvJitLink.so"};
+    for (const char* n : names)
+        if ((a.so = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!a.so) return fail(GSA_ERR_UNSUPPORTED, "cannot load libnvJitLink.so.12 (needed to link user device models): %s", dlerror());
+    a.Create = (decltype(a.Create))sym(a.so, "nvJitLinkCreate");
+    a.Destroy = (decltype(a.Destroy))sym(a.so, "nvJitLinkDestroy");
+    a.AddData = (decltype(a.AddData))sym(a.so, "nvJitLinkAddData");
+    a.Complete = (decltype(a.Complete))sym(a.so, "nvJitLinkComplete");
+    a.GetLinkedCubinSize = (decltype(a.GetLinkedCubinSize))sym(a.so, "nvJitLinkGetLinkedCubinSize");
+    a.GetLinkedCubin = (decltype(a.GetLinkedCubin))sym(a.so, "nvJitLinkGetLinkedCubin");
+    a.GetErrorLogSize = (decltype(a.GetErrorLogSize))sym(a.so, "nvJitLinkGetErrorLogSize");
+    a.GetErrorLog = (decltype(a.GetErrorLog))sym(a.so, "nvJitLinkGetErrorLog");
+    if (!a.Create || !a.Destroy || !a.AddData || !a.Complete || !a.GetLinkedCubinSize || !a.GetLinkedCubin)
+        return fail(GSA_ERR_UNSUPPORTED, "libnvJitLink does not export the expected nvJitLink* entry points");
+    return GSA_OK;
+}
+
+std::string trampoline_ptx(const char* symbol) {
+    const std::string s(symbol);
+    return std::string(".version 8.8\n.target sm_100a\n.address_size 64\n") +
+           ".extern .func " + s + "(.param .b64 a0, .param .b32 a1, .param .b64 a2, .param .b32 a3, .param .b64 a4, .param .b32 a5);\n" +
+           ".visible .func gsa_user_model(.param .b64 b0, .param .b32 b1, .param .b64 b2, .param .b32 b3, .param .b64 b4, .param .b32 b5)\n{\n"
+           "  .reg .b64 %rd<3>;\n  .reg .b32 %r<3>;\n"
+           "  ld.param.u64 %rd0, [b0];\n  ld.param.u32 %r0, [b1];\n  ld.param.u64 %rd1, [b2];\n  ld.param.u32 %r1, [b3];\n"
+           "  ld.param.u64 %rd2, [b4];\n  ld.param.u32 %r2, [b5];\n"
+           "  {\n  .param .b64 c0;\n  .param .b32 c1;\n  .param .b64 c2;\n  .param .b32 c3;\n  .param .b64 c4;\n  .param .b32 c5;\n"
+           "  st.param.b64 [c0], %rd0;\n  st.param.b32 [c1], %r0;\n  st.param.b64 [c2], %rd1;\n  st.param.b32 [c3], %r1;\n"
+           "  st.param.b64 [c4], %rd2;\n  st.param.b32 [c5], %r2;\n"
+           "  call.uni " + s + ", (c0, c1, c2, c3, c4, c5);\n  }\n  ret;\n}\n";
+}
+
+JitLinkApi g_api;
+std::mutex g_api_mu;
+
+}  // namespace
+
+int register_user_model(gsa_handle* h, const void* image, size_t len, const char* symbol, int nout, int* model_id) {
+    if (!image || len == 0 || !symbol || !*symbol || !model_id) return fail(GSA_ERR_INVALID, "image, symbol or model_id is NULL/empty");
+    if (nout < 1 || nout > 4) return fail(GSA_ERR_UNSUPPORTED, "user models support 1..4 outputs (got %d)", nout);
+    for (const char* c = symbol; *c; ++c)
+        if (!((*c >= 'a' && *c <= 'z') || (*c >= 'A' && *c <= 'Z') || (*c >= '0' && *c <= '9') || *c == '_' || *c == '$'))
+            return fail(GSA_ERR_INVALID, "symbol '%s' is not a plain C identifier (declare the model extern \"C\")", symbol);
+    {
+        std::lock_guard<std::mutex> lk(g_api_mu);
+        int rc = load_api(g_api);
+        if (rc) return rc;
+    }
+    const JitLinkApi& a = g_api;
+    nvJitLinkHandle jl = nullptr;
+    const char* opts[] = {"-arch=sm_100a"};
+    int e = a.Create(&jl, 1, opts);
+    if (e) return fail(GSA_ERR_CUDA, "nvJitLinkCreate failed (%d)", e);
+    auto log_and_fail = [&](const char* what, int code) {
+        std::string log;
+        size_t n = 0;
+        if (a.GetErrorLogSize && a.GetErrorLog && a.GetErrorLogSize(jl, &n) == 0 && n > 1) {
+            log.resize(n);
+            a.GetErrorLog(jl, &log[0]);
+        }
+        a.Destroy(&jl);
+        return fail(GSA_ERR_INVALID, "%s failed (%d): %.380s", what, code, log.c_str());
+    };
+    const size_t blob_len = (size_t)(gsa_user_kernel_blob_end - gsa_user_kernel_blob);
+    if ((e = a.AddData(jl, NVJL_INPUT_CUBIN, gsa_user_kernel_blob, blob_len, "gsa_user_kernel"))) return log_and_fail("nvJitLinkAddData(kernel)", e);
+    if ((e = a.AddData(jl, NVJL_INPUT_ANY, image, len, "user_model"))) return log_and_fail("nvJitLinkAddData(user image)", e);
+    std::string ptx;
+    if (strcmp(symbol, "gsa_user_model") != 0) {
+        ptx = trampoline_ptx(symbol);
+        if ((e = a.AddData(jl, NVJL_INPUT_PTX, ptx.c_str(), ptx.size() + 1, "gsa_trampoline"))) return log_and_fail("nvJitLinkAddData(trampoline)", e);
+    }
+    if ((e = a.Complete(jl))) return log_and_fail("nvJitLinkComplete (is the model built with -rdc=true for sm_100a, with the expected signature?)", e);
+    size_t cs = 0;
+    if ((e = a.GetLinkedCubinSize(jl, &cs))) return log_and_fail("nvJitLinkGetLinkedCubinSize", e);
+    std::vector<char> cubin(cs);
+    if ((e = a.GetLinkedCubin(jl, cubin.data()))) return log_and_fail("nvJitLinkGetLinkedCubin", e);
+    a.Destroy(&jl);
+
+    UserModelEntry um;
+    um.nout = nout;
+    GSA_CUDA(cudaLibraryLoadData(&um.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    cudaError_t ce = cudaLibraryGetKernel(&um.k_first, um.lib, "gsa_user_fused_first");
+    if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&um.k_second, um.lib, "gsa_user_fused_second");
+    if (ce != cudaSuccess) {
+        cudaLibraryUnload(um.lib);
+        return cuda_fail(ce, "cudaLibraryGetKernel");
+    }
+    h->user_models.push_back(um);
+    *model_id = GSA_MODEL_USER_BASE + (int)h->user_models.size() - 1;
+    return GSA_OK;
+}
+
+}  // namespace gsa

@@ -62,13 +62,35 @@ class DeviceModel:
 
     def __post_init__(self):
         self.params = np.ascontiguousarray(np.asarray(self.params, dtype=np.float64).ravel(order="F"))
+        self.handle = None            # user models live in the handle they were registered with
+        if self.name.startswith("user:"):
+            return                    # model_id is filled in by from_fatbin
         mid = C.c_int()
         check(lib().gsa_model_lookup(self.name.encode(), C.byref(mid)))
         self.model_id = mid.value
 
+    @classmethod
+    def from_fatbin(cls, image, symbol: str, nout: int = 1, params=(), handle: "Optional[GsaHandle]" = None) -> "DeviceModel":
+        """A user-supplied model: `image` (bytes or a path) is a fatbin / cubin / PTX / LTO-IR built with
+        `nvcc -rdc=true -gencode arch=compute_100a,code=sm_100a` that defines
+
+            extern "C" __device__ void <symbol>(const double* x, int d, const double* p, int np, double* y, int nout);
+
+        It is linked into the generic fused kernel with nvJitLink (gsa_model_register_fatbin)."""
+        if isinstance(image, (str, bytes)) and not isinstance(image, bytes):
+            with open(image, "rb") as f:
+                image = f.read()
+        h = handle or default_handle()
+        m = cls("user:" + symbol, params)
+        mid = C.c_int()
+        buf = C.create_string_buffer(bytes(image), len(image))
+        check(lib().gsa_model_register_fatbin(h.ptr, buf, len(image), symbol.encode(), int(nout), C.byref(mid)))
+        m.model_id, m.handle = mid.value, h
+        return m
+
     def nout(self, d: int) -> int:
         n = C.c_int()
-        check(lib().gsa_model_nout(None, self.model_id, self.params.size, d, C.byref(n)))
+        check(lib().gsa_model_nout(self.handle.ptr if self.handle else None, self.model_id, self.params.size, d, C.byref(n)))
         return n.value
 
 
@@ -281,7 +303,7 @@ def gsa(f, method: Sobol, A, B=None, *, batch: bool = False, Ei_estimator="Janse
     given, gsa(f, method::Sobol, p_range; samples) (:407-417) with the design generated on the GPU."""
     if not isinstance(method, Sobol):
         raise TypeError("only the Sobol method is implemented by this package")
-    h = handle or default_handle()
+    h = handle or getattr(f, "handle", None) or default_handle()
     if B is None:
         if samples is None:
             raise TypeError("gsa(f, Sobol(), p_range; samples) needs `samples`")
@@ -355,7 +377,7 @@ def sobol_partials(f: DeviceModel, method: Sobol, A_local, B_local, N: int, col0
     The sums are additive: `torch.distributed.all_reduce(partials)` then `sobol_finalize`.  Runs on torch's
     current CUDA stream; asynchronous."""
     import torch
-    h = handle or default_handle()
+    h = handle or getattr(f, "handle", None) or default_handle()
     Am, Bm = _Mat(A_local), _Mat(B_local)
     d = Am.d
     nout = f.nout(d)

@@ -339,3 +339,49 @@ def test_linear_large_offset_inputs():
     ref = gsa_ref.gsa_sobol("linear", W, A, B)
     res = g.gsa(g.DeviceModel("linear", W), g.Sobol(), A, B, batch=True)
     assert parity_err(res.S1, ref.S1) < 1e-9 and parity_err(res.ST, ref.ST) < 1e-9      # the oracle's own fB*(fAB-fA) cancels here
+
+
+USER_MODEL_CU = r'''
+extern "C" __device__ void my_model(const double* x, int d, const double* p, int np, double* y, int nout) {
+    double s = 0.0;
+    for (int i = 0; i < d; ++i) s += p[i] * x[i] * x[i];
+    y[0] = s + x[0] * x[1];
+    if (nout > 1) y[1] = sin(x[0]) + x[d - 1];
+}
+extern "C" __device__ void gsa_user_model(const double* x, int d, const double* p, int np, double* y, int nout) {
+    y[0] = x[0] + p[0] * x[1] * x[2];
+}
+'''
+
+
+def test_user_device_model_from_fatbin(tmp_path):
+    """A user `__device__` model compiled to a relocatable fatbin, linked into the fused kernel with nvJitLink
+    (BASELINE north star: 'user-supplied __device__ models linked from a fatbin')."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    src = tmp_path / "um.cu"
+    src.write_text(USER_MODEL_CU)
+    fat = tmp_path / "um.fatbin"
+    subprocess.check_call([nvcc, "-ccbin", "/usr/bin/g++", "-rdc=true", "-fatbin", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-o", str(fat), str(src)])
+    d, N = 5, 20011
+    p = np.array([0.5, 1.0, 1.5, 2.0, 2.5])
+    A, B = gsa_ref.sobol_design(N, -np.ones(d), 2 * np.ones(d))
+
+    def f2(X):
+        return np.stack([(p[:, None] * X * X).sum(axis=0) + X[0] * X[1], np.sin(X[0]) + X[d - 1]])
+
+    # symbol with its own name -> goes through the PTX trampoline; 2 outputs, second order, replicates
+    m = g.DeviceModel.from_fatbin(str(fat), "my_model", nout=2, params=p)
+    res = g.gsa(m, g.Sobol(order=[0, 1, 2], nboot=3), A, B, batch=True)
+    ref = so.gsa_sobol(f2, A, B, order=(0, 1, 2), nboot=3)
+    assert res.S1.shape == (2, d) and res.S2.shape == (d, d, 2)
+    assert_parity(res, ref, tol=1e-11)        # the model itself is evaluated by different libm's (sin): a few ulp per value
+    # the default symbol name, one output, another estimator
+    m1 = g.DeviceModel.from_fatbin(fat.read_bytes(), "gsa_user_model", nout=1, params=[3.0])
+    res = g.gsa(m1, g.Sobol(), A, B, batch=True, Ei_estimator="Sobol2007")
+    ref = so.gsa_sobol(lambda X: X[0] + 3.0 * X[1] * X[2], A, B, Ei_estimator="Sobol2007")
+    assert_parity(res, ref)
+    with pytest.raises(g.GsaError, match="nvJitLink"):
+        g.DeviceModel.from_fatbin(fat.read_bytes(), "no_such_symbol", nout=1)
