@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -47,9 +48,18 @@ void* sym(void* so, const char* base) {
 
 int load_api(JitLinkApi& a) {
     if (a.so) return GSA_OK;
-    const char* names[] = {"libnvJitLink.so.12", "/usr/local/cuda/lib64/libnvJitLink.so.12", "libnvJitLink.so"};
-    for (const char* n : names)
-        if ((a.so = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+    // The linker must be at least as new as the nvcc that built the embedded kernel (CUDA 12.9): prefer the toolkit's copy
+    // over whatever libnvJitLink.so.12 the host process may already have loaded (PyTorch bundles an older one, which
+    // rejects a 12.9 cubin as "bad input").  A path with a slash is opened as its own object even if the soname matches.
+    std::vector<std::string> names;
+    if (const char* e = getenv("GSA_NVJITLINK")) names.push_back(e);
+    for (const char* env : {"CUDA_HOME", "CUDA_PATH"})
+        if (const char* e = getenv(env)) names.push_back(std::string(e) + "/lib64/libnvJitLink.so.12");
+    names.push_back("/usr/local/cuda/lib64/libnvJitLink.so.12");
+    names.push_back("libnvJitLink.so.12");
+    names.push_back("libnvJitLink.so");
+    for (const std::string& n : names)
+        if ((a.so = dlopen(n.c_str(), RTLD_NOW | RTLD_LOCAL))) break;
     if (!a.so) return fail(GSA_ERR_UNSUPPORTED, "cannot load libnvJitLink.so.12 (needed to link user device models): %s", dlerror());
     a.Create = (decltype(a.Create))sym(a.so, "nvJitLinkCreate");
     a.Destroy = (decltype(a.Destroy))sym(a.so, "nvJitLinkDestroy");
@@ -118,6 +128,15 @@ int register_user_model(gsa_handle* h, const void* image, size_t len, const char
         if ((e = a.AddData(jl, NVJL_INPUT_PTX, ptx.c_str(), ptx.size() + 1, "gsa_trampoline"))) return log_and_fail("nvJitLinkAddData(trampoline)", e);
     }
     if ((e = a.Complete(jl))) return log_and_fail("nvJitLinkComplete (is the model built with -rdc=true for sm_100a, with the expected signature?)", e);
+    {   // nvJitLinkComplete can report success while the log carries an error (seen with a doubly defined symbol, and the
+        // resulting image faults at run time): refuse any link whose error log is not clean
+        size_t n = 0;
+        if (a.GetErrorLogSize && a.GetErrorLog && a.GetErrorLogSize(jl, &n) == 0 && n > 1) {
+            std::string log(n, '\0');
+            a.GetErrorLog(jl, &log[0]);
+            if (log.find("error") != std::string::npos) return log_and_fail("nvJitLinkComplete (reported errors)", 0);
+        }
+    }
     size_t cs = 0;
     if ((e = a.GetLinkedCubinSize(jl, &cs))) return log_and_fail("nvJitLinkGetLinkedCubinSize", e);
     std::vector<char> cubin(cs);

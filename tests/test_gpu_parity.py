@@ -348,6 +348,9 @@ extern "C" __device__ void my_model(const double* x, int d, const double* p, int
     y[0] = s + x[0] * x[1];
     if (nout > 1) y[1] = sin(x[0]) + x[d - 1];
 }
+'''
+
+USER_MODEL_DEFAULT_NAME_CU = r'''
 extern "C" __device__ void gsa_user_model(const double* x, int d, const double* p, int np, double* y, int nout) {
     y[0] = x[0] + p[0] * x[1] * x[2];
 }
@@ -360,11 +363,15 @@ def test_user_device_model_from_fatbin(tmp_path):
     import shutil
     import subprocess
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    src = tmp_path / "um.cu"
-    src.write_text(USER_MODEL_CU)
-    fat = tmp_path / "um.fatbin"
-    subprocess.check_call([nvcc, "-ccbin", "/usr/bin/g++", "-rdc=true", "-fatbin", "-gencode", "arch=compute_100a,code=sm_100a",
-                           "-o", str(fat), str(src)])
+    def build(name, text):
+        src = tmp_path / (name + ".cu")
+        src.write_text(text)
+        out = tmp_path / (name + ".fatbin")
+        subprocess.check_call([nvcc, "-ccbin", "/usr/bin/g++", "-rdc=true", "-fatbin", "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-o", str(out), str(src)])
+        return out
+
+    fat, fat1 = build("um", USER_MODEL_CU), build("um1", USER_MODEL_DEFAULT_NAME_CU)
     d, N = 5, 20011
     p = np.array([0.5, 1.0, 1.5, 2.0, 2.5])
     A, B = gsa_ref.sobol_design(N, -np.ones(d), 2 * np.ones(d))
@@ -379,9 +386,11 @@ def test_user_device_model_from_fatbin(tmp_path):
     assert res.S1.shape == (2, d) and res.S2.shape == (d, d, 2)
     assert_parity(res, ref, tol=1e-11)        # the model itself is evaluated by different libm's (sin): a few ulp per value
     # the default symbol name, one output, another estimator
-    m1 = g.DeviceModel.from_fatbin(fat.read_bytes(), "gsa_user_model", nout=1, params=[3.0])
+    m1 = g.DeviceModel.from_fatbin(fat1.read_bytes(), "gsa_user_model", nout=1, params=[3.0])
     res = g.gsa(m1, g.Sobol(), A, B, batch=True, Ei_estimator="Sobol2007")
     ref = so.gsa_sobol(lambda X: X[0] + 3.0 * X[1] * X[2], A, B, Ei_estimator="Sobol2007")
     assert_parity(res, ref)
     with pytest.raises(g.GsaError, match="nvJitLink"):
-        g.DeviceModel.from_fatbin(fat.read_bytes(), "no_such_symbol", nout=1)
+        g.DeviceModel.from_fatbin(fat.read_bytes(), "no_such_symbol", nout=1)          # undefined reference
+    with pytest.raises(g.GsaError, match="nvJitLink"):
+        g.DeviceModel.from_fatbin(fat1.read_bytes(), "other_name", nout=1)             # trampoline would redefine gsa_user_model
