@@ -57,6 +57,11 @@ SIGNATURES = {
     "gsa_sobol_finalize": [_op, _vp, _i, _i, _i64, _rp],
     "gsa_sobol_analyze_y": [_vp, _op, _vp, _i, _i, _i64, _rp],
     "gsa_sobol_all_points": [_vp, _op, _vp, _vp, _i, _i64, _vp, _i],
+    "gsa_multi_create": [C.POINTER(C.c_int), _i, C.POINTER(_vp)],
+    "gsa_multi_destroy": [_vp],
+    "gsa_multi_device_count": [_vp, _ip],
+    "gsa_multi_handle": [_vp, _i, C.POINTER(_vp)],
+    "gsa_multi_sobol_run": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
     "gsa_last_timing": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _ip],
 }
 

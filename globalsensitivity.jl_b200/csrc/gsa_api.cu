@@ -230,7 +230,24 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         g.rep_first = (int)(col0 / n);
         const int rep_last = (int)((valid_hi - 1) / n);
         const int nrep = rep_last - g.rep_first + 1;
-        choose_tiles(n, nrep, plan.resident, plan.tiles_per_cta, plan.ts_min, plan.ts_max, plan.ts_gran, &g.ts, &g.tpr);
+        const size_t col_bytes = sizeof(double) * (size_t)d;
+        bool devp = false;
+        const bool host_in = o->input_location != GSA_LOC_DEVICE;
+        const bool pinned = host_in && is_device_or_pinned(A, &devp) && is_device_or_pinned(B, &devp);
+        // Host designs are streamed in column chunks (256 MB per matrix from pinned memory, 64 MB through the staging
+        // buffers otherwise).  The kernel of a chunk only sees that chunk's tiles, so the tiles must be small enough that one
+        // chunk holds at least a full wave of them -- with shard-sized tiles each chunk kernel ran on ONE CTA and the whole
+        // pipeline sat at 25 GB/s instead of the 55 GB/s PCIe delivers (profiles/r1_notes.md).
+        const int64_t chunk_cols_target = std::max<int64_t>(plan.ts_min, (int64_t)(((pinned ? 256u : 64u) << 20) / col_bytes));
+        if (host_in) {
+            int64_t ts = (chunk_cols_target + plan.resident - 1) / plan.resident;
+            ts = (ts + plan.ts_gran - 1) / plan.ts_gran * plan.ts_gran;
+            ts = std::max<int64_t>(plan.ts_min, std::min<int64_t>(ts, plan.ts_max));
+            g.ts = (int)std::min<int64_t>(ts, std::max<int64_t>(plan.ts_min, (n + plan.ts_gran - 1) / plan.ts_gran * plan.ts_gran));
+            g.tpr = (int)std::max<int64_t>(1, (n + g.ts - 1) / g.ts);
+        } else {
+            choose_tiles(n, nrep, plan.resident, plan.tiles_per_cta, plan.ts_min, plan.ts_max, plan.ts_gran, &g.ts, &g.tpr);
+        }
         g.ntiles = nrep * g.tpr;
         if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)g.ntiles * recsz))) return rc;
 
@@ -239,10 +256,6 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         } else {
             // Stream the host design through two device buffers: the H2D copy of chunk i+1 (copy stream)
             // overlaps the kernel of chunk i.  Chunk boundaries are tile boundaries.
-            bool devp = false;
-            const bool pinned = is_device_or_pinned(A, &devp) && is_device_or_pinned(B, &devp);
-            const size_t col_bytes = sizeof(double) * (size_t)d;
-            const int64_t chunk_cols_target = std::max<int64_t>(g.ts, (int64_t)((96u << 20) / col_bytes));
             int tiles_per_chunk = (int)std::max<int64_t>(1, chunk_cols_target / g.ts);
             const size_t buf_bytes = 2 * col_bytes * (size_t)tiles_per_chunk * g.ts;
             for (int b = 0; b < 2; ++b)
@@ -369,6 +382,13 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
     GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
     return GSA_OK;
 }
+
+// entry points for multi.cu
+int partials_entry(gsa_handle* h, const gsa_sobol_opts* o, int model, const double* params, int np, const double* A, const double* B,
+                   int d, int64_t N, int64_t col0, int64_t ncols, double* partials) {
+    return partials_impl(h, o, model, params, np, A, B, d, N, col0, ncols, partials);
+}
+int model_nout_entry(gsa_handle* h, int model, int np, int d, int* nout) { return model_nout(h, model, np, d, nout); }
 
 // all_points writer (fuse_designs, reference :94-108 + :116-134)
 __global__ void __launch_bounds__(256) all_points_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ P,

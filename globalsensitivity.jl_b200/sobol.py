@@ -133,6 +133,48 @@ class GsaHandle:
         return ms.value, kms.value, n.value
 
 
+class GsaMulti:
+    """Single-process, multi-device form (gsa_multi): one handle and one NCCL communicator per device.
+
+        m = GsaMulti([0, 1, 2, 3]);  res = m.gsa(DeviceModel("sobol_g", a), Sobol(), A, B)      # A, B on the host"""
+
+    def __init__(self, devices=None, ndev: Optional[int] = None):
+        if devices is None:
+            if ndev is None:
+                import torch
+                ndev = torch.cuda.device_count()
+            devices = list(range(ndev))
+        self.devices = list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        self._m = C.c_void_p()
+        check(lib().gsa_multi_create(arr, len(self.devices), C.byref(self._m)))
+
+    def close(self):
+        if getattr(self, "_m", None) and self._m.value:
+            lib().gsa_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def gsa(self, f: "DeviceModel", method: "Sobol", A, B, *, batch: bool = True, Ei_estimator="Jansen1999") -> "SobolResult":
+        Am, Bm = _Mat(A), _Mat(B)
+        if Am.loc != LOC_HOST or Bm.loc != LOC_HOST:
+            raise ValueError("GsaMulti.gsa takes host designs (each device streams its own column shard)")
+        if (Am.d, Am.N) != (Bm.d, Bm.N):
+            raise ValueError("A and B must have the same shape")
+        d, N = Am.d, Am.N
+        nout = f.nout(d)
+        o = _opts(method, Ei_estimator, LOC_HOST)
+        rc, finish, _ = _alloc_result(nout, d, method.nboot, 2 in method.order, nout > 1)
+        check(lib().gsa_multi_sobol_run(self._m, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size, Am.ptr, Bm.ptr,
+                                        d, N, C.byref(rc)))
+        return finish()
+
+
 _default = {}
 
 

@@ -63,6 +63,7 @@ enum {
 };
 
 typedef struct gsa_handle gsa_handle; /* opaque */
+typedef struct gsa_multi gsa_multi;   /* opaque: one handle + one NCCL communicator per device of a single process */
 
 /* mirrors `struct Sobol` (reference :77-83) + the call's keyword arguments (:112) */
 typedef struct gsa_sobol_opts {
@@ -156,6 +157,20 @@ GSA_API int gsa_sobol_all_points(gsa_handle* h, const gsa_sobol_opts* opts, cons
  * and its dominant kernel alone (the last fused / estimator launch; 0 if none); plus the number of kernels
  * the call launched.  Used by bench.py's roofline line. */
 GSA_API int gsa_last_timing(gsa_handle* h, float* total_ms, float* kernel_ms, int* launches);
+
+/* ---- single-process, multi-device form (a plain Julia `ccall` from one process) ------------------ */
+/* devices == NULL: devices 0..ndev-1.  Creates one gsa_handle per device and, for ndev > 1, NCCL communicators
+ * (ncclCommInitAll; libnccl.so.2 is loaded with dlopen). */
+GSA_API int gsa_multi_create(const int* devices, int ndev, gsa_multi** out);
+GSA_API int gsa_multi_destroy(gsa_multi* m);
+GSA_API int gsa_multi_device_count(gsa_multi* m, int* ndev);
+/* the i-th per-device handle (owned by `m`), e.g. for gsa_sobol_design on that device */
+GSA_API int gsa_multi_handle(gsa_multi* m, int i, gsa_handle** out);
+/* gsa(model, Sobol(...), A, B; batch=true) (:110-149 + :169-405) with the HOST design sharded by contiguous column ranges
+ * over the devices: every device streams and reduces its shard, ONE grouped ncclAllReduce(sum, fp64) of the
+ * nboot*nout*nstat partial sums crosses NVLink, then the host epilogue. */
+GSA_API int gsa_multi_sobol_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams,
+                        const double* A, const double* B, int d, int64_t N, gsa_sobol_result* out);
 
 #ifdef __cplusplus
 }

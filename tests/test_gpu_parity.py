@@ -394,3 +394,43 @@ def test_user_device_model_from_fatbin(tmp_path):
         g.DeviceModel.from_fatbin(fat.read_bytes(), "no_such_symbol", nout=1)          # undefined reference
     with pytest.raises(g.GsaError, match="nvJitLink"):
         g.DeviceModel.from_fatbin(fat1.read_bytes(), "other_name", nout=1)             # trampoline would redefine gsa_user_model
+
+
+def test_multi_device_single_process(ishigami_design):
+    """gsa_multi: one process, all visible GPUs, one grouped ncclAllReduce of the partial sums.  Runs with
+    a single device too (then no collective is issued)."""
+    import torch
+    ndev = torch.cuda.device_count()
+    m = g.GsaMulti(ndev=ndev)
+    A, B = ishigami_design
+    ref = gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=(0, 1, 2), nboot=20)
+    res = m.gsa(g.DeviceModel("ishigami", [7.0, 0.1]), g.Sobol(order=[0, 1, 2], nboot=20), A, B)
+    assert_parity(res, ref, what=("multi", ndev))
+    d, N = 100, 100003
+    a = np.array([0.0, 1.0, 4.5, 9.0] + [99.0] * 96)
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, nboot=3)
+    res = m.gsa(g.DeviceModel("sobol_g", a), g.Sobol(nboot=3), A, B)
+    assert_parity(res, ref, what=("multi sobol_g", ndev))
+    W = np.arange(1, 61, dtype=np.float64).reshape(6, 10) / 7.0
+    A, B = gsa_ref.sobol_design(30001, -np.ones(10), np.ones(10))
+    ref = gsa_ref.gsa_sobol("linear", W, A, B)
+    res = m.gsa(g.DeviceModel("linear", W), g.Sobol(), A, B)
+    assert_parity(res, ref, what=("multi linear", ndev))
+    m.close()
+
+
+def test_streamed_host_inputs_large():
+    """Host designs larger than one streaming chunk (pinned: 256 MB per matrix; pageable: 64 MB): many chunk kernels."""
+    import torch
+    d, N = 100, 700001                       # 560 MB per matrix
+    a = np.array([0.0, 1.0, 4.5, 9.0] + [99.0] * 96)
+    model, method = g.DeviceModel("sobol_g", a), g.Sobol(nboot=2)
+    A, B = g.generate_design_matrices(N, np.zeros(d), np.ones(d), 2, device=True)
+    dev = g.gsa(model, method, A, B, batch=True)
+    An, Bn = A.cpu().numpy(), B.cpu().numpy()
+    pageable = g.gsa(model, method, An, Bn, batch=True)
+    Ap, Bp = A.t().contiguous().cpu().pin_memory().t(), B.t().contiguous().cpu().pin_memory().t()
+    pinned = g.gsa(model, method, Ap, Bp, batch=True)
+    for r in (pageable, pinned):
+        assert_parity(r, dev, tol=1e-13)     # same sums up to the tile decomposition
