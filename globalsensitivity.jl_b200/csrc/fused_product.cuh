@@ -43,6 +43,10 @@ __global__ void __launch_bounds__(PROD_THREADS) fused_product_kernel(ProductArgs
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & (T - 1);
     const int grp = threadIdx.x / T;  // sample group within the CTA
+    // The sample loop below has a per-GROUP trip count (a tile's length need not be a multiple of the groups per CTA), so the
+    // butterfly inside it must name only the T lanes of the group: a full-mask shuffle would wait forever for the lanes of a
+    // group that has already left the loop (found the hard way: a hang on N = 100003, nboot = 3).
+    const unsigned gmask = T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (lane & ~(T - 1)));
     for (int i = threadIdx.x; i < SLOTS; i += PROD_THREADS) scoef[i] = i < d ? a.coef[i] : make_double2(0.0, 1.0);
     __syncthreads();
 
@@ -80,8 +84,8 @@ __global__ void __launch_bounds__(PROD_THREADS) fused_product_kernel(ProductArgs
             double others = 1.0, yA = LA, yB = LB;
 #pragma unroll
             for (int o = 1; o < T; o <<= 1) {
-                const double pa = __shfl_xor_sync(0xffffffffu, yA, o);
-                const double pb = __shfl_xor_sync(0xffffffffu, yB, o);
+                const double pa = __shfl_xor_sync(gmask, yA, o);
+                const double pb = __shfl_xor_sync(gmask, yB, o);
                 others *= pa;
                 yA *= pa;
                 yB *= pb;

@@ -283,6 +283,7 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
                 }
                 if (c1 <= c0) continue;
                 const size_t bytes = col_bytes * (size_t)(c1 - c0);
+                if (getenv("GSA_DEBUG")) fprintf(stderr, "[gsa] chunk %d tiles [%d,%d) cols [%lld,%lld) bytes %zu buf %zu pinned %d ts %d tpr %d\n", ci, t0, t1, (long long)c0, (long long)c1, bytes, buf_bytes, (int)pinned, g.ts, g.tpr);
                 double* dA = h->dev_in[b].as<double>();
                 double* dB = dA + (size_t)d * (size_t)tiles_per_chunk * g.ts;
                 const double* hA = A + (size_t)d * (size_t)(c0 - col0);

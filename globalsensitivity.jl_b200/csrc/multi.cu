@@ -8,7 +8,9 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -22,6 +24,8 @@ int model_nout_entry(gsa_handle* h, int model, int np, int d, int* nout);
 }  // namespace gsa
 
 using namespace gsa;
+
+#define MDBG(...) do { if (getenv("GSA_DEBUG")) { fprintf(stderr, "[gsa_multi] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
 
 namespace {
 struct NcclApi {
@@ -130,6 +134,7 @@ int gsa_multi_sobol_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, 
     if (!m || !opts || !out) return fail(GSA_ERR_INVALID, "NULL argument to gsa_multi_sobol_run");
     if (opts->input_location != GSA_LOC_HOST) return fail(GSA_ERR_INVALID, "gsa_multi_sobol_run takes host designs (input_location = GSA_LOC_HOST)");
     if (model_id >= GSA_MODEL_USER_BASE) return fail(GSA_ERR_UNSUPPORTED, "user models are registered per handle; not supported by the multi-device entry yet");
+    MDBG("run: enter");
     std::lock_guard<std::mutex> lk(m->mu);
     const int G = (int)m->h.size();
     int nout = 0, rc;
@@ -146,8 +151,10 @@ int gsa_multi_sobol_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, 
             gsa_handle* hh = m->h[g];
             const int64_t base = N / G, rem = N % G;
             const int64_t col0 = g * base + std::min<int64_t>(g, rem), ncols = base + (g < rem ? 1 : 0);
+            MDBG("worker %d: start", g);
             std::lock_guard<std::mutex> hl(hh->mu);
             cudaSetDevice(hh->device);
+            MDBG("worker %d: device set", g);
             int r = hh->partials.reserve(sizeof(double) * cnt);
             if (r == GSA_OK)
                 r = partials_entry(hh, opts, model_id, params, nparams, A ? A + (size_t)d * col0 : nullptr, B ? B + (size_t)d * col0 : nullptr, d, N,
@@ -158,9 +165,11 @@ int gsa_multi_sobol_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, 
                 errs[g] = buf;
             }
             rcs[g] = r;
+            MDBG("worker %d: done rc=%d", g, r);
         });
     }
     for (auto& t : th) t.join();
+    MDBG("joined");
     for (int g = 0; g < G; ++g)
         if (rcs[g] != GSA_OK) return fail(rcs[g], "device %d: %s", m->h[g]->device, errs[g].c_str());
     if (G > 1) {   // the single collective of the path
@@ -173,9 +182,18 @@ int gsa_multi_sobol_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, 
     }
     gsa_handle* h0 = m->h[0];
     cudaSetDevice(h0->device);
+    if (getenv("GSA_DEBUG")) {
+        for (int it = 0; it < 20; ++it) {
+            cudaError_t q1 = cudaStreamQuery(h0->stream), q2 = cudaStreamQuery(h0->copy_stream);
+            MDBG("query: stream %d copy %d", (int)q1, (int)q2);
+            if (q1 == cudaSuccess && q2 == cudaSuccess) break;
+            std::this_thread::sleep_for(std::chrono::milliseconds(250));
+        }
+    }
     std::vector<double> host(cnt);
     GSA_CUDA(cudaMemcpyAsync(host.data(), h0->partials.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h0->stream));
     GSA_CUDA(cudaStreamSynchronize(h0->stream));
+    MDBG("partials on host");
     for (int g = 1; g < G; ++g) {
         cudaSetDevice(m->h[g]->device);
         GSA_CUDA(cudaStreamSynchronize(m->h[g]->stream));

@@ -193,6 +193,25 @@ def default_handle(device: int = -1) -> GsaHandle:
 # ---------------------------------------------------------------------------------------------------
 # array plumbing
 # ---------------------------------------------------------------------------------------------------
+class _TorchStream:
+    """Run the handle's work on torch's current CUDA stream while device tensors are involved, so that it is ordered
+    with whatever produced them (the handle-owned stream is non-blocking and would not wait for torch's kernels)."""
+
+    def __init__(self, h: "GsaHandle", active: bool):
+        self.h, self.active = h, active
+
+    def __enter__(self):
+        if self.active:
+            import torch
+            self.h.set_stream(torch.cuda.current_stream().cuda_stream)
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self.h.set_stream(None)
+        return False
+
+
 def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
@@ -276,11 +295,8 @@ def generate_design_matrices(n: int, lb, ub, num_mats: int = 2, *, device: bool 
         mats = [torch.empty((ncols, d), dtype=torch.float64, device="cuda") for _ in range(num_mats)]
         for m in range(num_mats):
             ptrs[m] = mats[m].data_ptr()
-        h.set_stream(torch.cuda.current_stream().cuda_stream)
-        try:
+        with _TorchStream(h, True):
             check(lib().gsa_sobol_design(h.ptr, n, d, num_mats, lb.ctypes.data, ub.ctypes.data, col0, ncols, ptrs, LOC_DEVICE))
-        finally:
-            h.set_stream(None)
         return [m.t() for m in mats]
     mats = [np.empty((d, ncols), dtype=np.float64, order="F") for _ in range(num_mats)]
     for m in range(num_mats):
@@ -318,7 +334,8 @@ def gsa_sobol_all_y_analysis(method: Sobol, all_y, d: int, n: int, Ei_estimator=
         raise ValueError(f"all_y has {cols} columns, expected nboot*n*step = {method.nboot * n * step}")
     o = _opts(method, Ei_estimator, loc)
     rc, finish, _ = _alloc_result(nout, d, method.nboot, second, multi)
-    check(lib().gsa_sobol_analyze_y(h.ptr, C.byref(o), ptr, nout, d, n, C.byref(rc)))
+    with _TorchStream(h, loc == LOC_DEVICE):
+        check(lib().gsa_sobol_analyze_y(h.ptr, C.byref(o), ptr, nout, d, n, C.byref(rc)))
     del keep
     return finish()
 
@@ -331,8 +348,8 @@ def _all_points(h: GsaHandle, method: Sobol, A: _Mat, B: _Mat, want_torch: bool)
     if want_torch:
         import torch
         P = torch.empty((cols, A.d), dtype=torch.float64, device="cuda")
-        check(lib().gsa_sobol_all_points(h.ptr, C.byref(o), A.ptr, B.ptr, A.d, A.N, P.data_ptr(), LOC_DEVICE))
-        h.synchronize()
+        with _TorchStream(h, True):
+            check(lib().gsa_sobol_all_points(h.ptr, C.byref(o), A.ptr, B.ptr, A.d, A.N, P.data_ptr(), LOC_DEVICE))
         return P.t()
     P = np.empty((A.d, cols), dtype=np.float64, order="F")
     check(lib().gsa_sobol_all_points(h.ptr, C.byref(o), A.ptr, B.ptr, A.d, A.N, P.ctypes.data, LOC_HOST))
@@ -375,8 +392,9 @@ def gsa(f, method: Sobol, A, B=None, *, batch: bool = False, Ei_estimator="Janse
         nout = f.nout(d)
         o = _opts(method, Ei_estimator, Am.loc)
         rc, finish, _ = _alloc_result(nout, d, method.nboot, second, nout > 1)
-        check(lib().gsa_sobol_run(h.ptr, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size,
-                                  Am.ptr, Bm.ptr, d, N, C.byref(rc)))
+        with _TorchStream(h, Am.loc == LOC_DEVICE):
+            check(lib().gsa_sobol_run(h.ptr, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size,
+                                      Am.ptr, Bm.ptr, d, N, C.byref(rc)))
         return finish()
 
     if not callable(f):
@@ -427,12 +445,9 @@ def sobol_partials(f: DeviceModel, method: Sobol, A_local, B_local, N: int, col0
     ns = nstat(method, d, Ei_estimator)
     if out is None:
         out = torch.empty((method.nboot, nout, ns), dtype=torch.float64, device="cuda")
-    h.set_stream(torch.cuda.current_stream().cuda_stream)
-    try:
+    with _TorchStream(h, True):
         check(lib().gsa_sobol_partials(h.ptr, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size, Am.ptr, Bm.ptr,
                                        d, N, col0, Am.N, out.data_ptr()))
-    finally:
-        h.set_stream(None)
     return out
 
 

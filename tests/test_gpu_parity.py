@@ -432,5 +432,21 @@ def test_streamed_host_inputs_large():
     pageable = g.gsa(model, method, An, Bn, batch=True)
     Ap, Bp = A.t().contiguous().cpu().pin_memory().t(), B.t().contiguous().cpu().pin_memory().t()
     pinned = g.gsa(model, method, Ap, Bp, batch=True)
-    for r in (pageable, pinned):
-        assert_parity(r, dev, tol=1e-13)     # same sums up to the tile decomposition
+    ref = gsa_ref.gsa_sobol("sobol_g", a, An, Bn, nboot=2)
+    for name, r in (("device", dev), ("pageable", pageable), ("pinned", pinned)):
+        assert_parity(r, ref, what=name)
+
+
+@pytest.mark.parametrize("d,N,nboot", [(100, 100003, 3), (100, 1000 + 7, 1), (20, 4099, 2), (40, 33334, 1), (128, 700, 1), (200, 531, 1)])
+def test_product_kernel_ragged_tiles(d, N, nboot):
+    """Tile lengths that are not a multiple of the sample groups per CTA: the lanes of a warp then leave the sample loop at
+    different iterations (regression test for a full-mask shuffle inside that loop, which hung)."""
+    a = np.array(([0.0, 1.0, 4.5, 9.0] + [99.0] * d)[:d])
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, nboot=nboot)
+    res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(nboot=nboot), A, B, batch=True)            # host input: streamed tiles
+    assert_parity(res, ref, what=(d, N, nboot, "host"))
+    import torch
+    At, Bt = torch.from_numpy(np.ascontiguousarray(A)).cuda(), torch.from_numpy(np.ascontiguousarray(B)).cuda()
+    res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(nboot=nboot), At, Bt, batch=True)          # device input: shard-sized tiles
+    assert_parity(res, ref, what=(d, N, nboot, "device"))
