@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <cstdint>
 #include <algorithm>
 
 #include "gsa_internal.h"
@@ -272,16 +273,18 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
             int ci = 0;
             for (int t0 = 0; t0 < g.ntiles; t0 += tiles_per_chunk, ++ci) {
                 const int t1 = std::min(g.ntiles, t0 + tiles_per_chunk), b = ci & 1;
-                int64_t c0, c1, tmp;
-                tile_range(g, t0, c0, tmp);
-                tile_range(g, t1 - 1, tmp, c1);
-                // tiles in between may be clipped to empty; take the hull of non-empty ones
+                // columns needed by this chunk = hull of its NON-EMPTY tiles (tiles clipped away by the shard bounds are empty)
+                int64_t c0 = INT64_MAX, c1 = INT64_MIN;
                 for (int t = t0; t < t1; ++t) {
                     int64_t a0, a1;
                     tile_range(g, t, a0, a1);
                     if (a1 > a0) { c0 = std::min(c0, a0); c1 = std::max(c1, a1); }
                 }
-                if (c1 <= c0) continue;
+                if (c1 <= c0) {   // nothing of this chunk lies in the shard: its tile records are all-zero
+                    GSA_CUDA(cudaMemsetAsync(h->tile_rec.as<double>() + (size_t)t0 * recsz, 0, sizeof(double) * (size_t)(t1 - t0) * recsz, h->stream));
+                    --ci;         // keep the buffer parity in step with the chunks that really use a buffer
+                    continue;
+                }
                 const size_t bytes = col_bytes * (size_t)(c1 - c0);
                 if (getenv("GSA_DEBUG")) fprintf(stderr, "[gsa] chunk %d tiles [%d,%d) cols [%lld,%lld) bytes %zu buf %zu pinned %d ts %d tpr %d\n", ci, t0, t1, (long long)c0, (long long)c1, bytes, buf_bytes, (int)pinned, g.ts, g.tpr);
                 double* dA = h->dev_in[b].as<double>();

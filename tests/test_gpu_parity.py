@@ -450,3 +450,22 @@ def test_product_kernel_ragged_tiles(d, N, nboot):
     At, Bt = torch.from_numpy(np.ascontiguousarray(A)).cuda(), torch.from_numpy(np.ascontiguousarray(B)).cuda()
     res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(nboot=nboot), At, Bt, batch=True)          # device input: shard-sized tiles
     assert_parity(res, ref, what=(d, N, nboot, "device"))
+
+
+def test_sharded_host_inputs_with_empty_chunks():
+    """Host shards that start in the middle of a replicate: whole streaming chunks of the shard's tile range are empty
+    (regression test: their tile records must be zeroed, and the copy hull must ignore empty tiles)."""
+    import torch
+    d, N, nboot, world = 100, 400000, 2, 3
+    a = np.array([0.0, 1.0, 4.5, 9.0] + [99.0] * 96)
+    model, method = g.DeviceModel("sobol_g", a), g.Sobol(nboot=nboot)
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, nboot=nboot)
+    total = None
+    for rank in range(world):
+        c0, nc = g.shard_columns(N, rank, world)
+        Al, Bl = np.asfortranarray(A[:, c0:c0 + nc]), np.asfortranarray(B[:, c0:c0 + nc])      # exactly the shard, nothing beyond it
+        p = g.sobol_partials(model, method, Al, Bl, N, c0)
+        total = p.clone() if total is None else total + p
+    torch.cuda.synchronize()
+    assert_parity(g.sobol_finalize(method, total, d, N), ref)
