@@ -222,9 +222,12 @@ def gpu_arm(args):
     if rank == 0:
         clocks = sampler.stop(tw0, tw1)
     t = torch.tensor([ms_total, float(np.mean(kernel_ms))], dtype=torch.float64, device="cuda")
+    per_rank = [t.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, kms = float(t[0]), float(t[1])
+    per_rank_kernel_ms = [round(float(x[1]), 4) for x in per_rank]
     value = w["rows"] * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: public API with HOST (pinned) inputs; H2D of the whole shard inside the timed region ---------------
@@ -279,7 +282,7 @@ def gpu_arm(args):
         roofline = {"bound": "hbm", "kernel": "fused_product_kernel<T,CPL> (design swap + Sobol-G + Jansen sums)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
-                    "k1_design_ms": k1_ms, "k1_design_gbs": 16.0 * d * ncols / (k1_ms * 1e-3) / 1e9}
+                    "per_rank_kernel_ms": per_rank_kernel_ms, "k1_design_ms": k1_ms, "k1_design_gbs": 16.0 * d * ncols / (k1_ms * 1e-3) / 1e9}
         cb = None if args.no_cpu else cpu_sample(args.cpu_log2n, 2)
         Vi = 1.0 / (3.0 * (1.0 + np.array(SOBOL_G_A)) ** 2)
         V = np.prod(1.0 + Vi) - 1.0

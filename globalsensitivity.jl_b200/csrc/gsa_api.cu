@@ -247,13 +247,28 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
             g.ts = (int)std::min<int64_t>(ts, std::max<int64_t>(plan.ts_min, (n + plan.ts_gran - 1) / plan.ts_gran * plan.ts_gran));
             g.tpr = (int)std::max<int64_t>(1, (n + g.ts - 1) / g.ts);
         } else {
-            choose_tiles(n, nrep, plan.resident, plan.tiles_per_cta, plan.ts_min, plan.ts_max, plan.ts_gran, &g.ts, &g.tpr);
+            // Size the tiles from the columns THIS SHARD holds (a shard can be a thin slice of a huge replicate: sizing them
+            // from the replicate length left 3/4 of the CTAs idle on 8 GPUs, profiles/r1_notes.md): tiles_per_cta * resident
+            // tiles over the shard's columns.
+            const int64_t cols_local = valid_hi - col0;
+            int64_t ts = (cols_local + (int64_t)plan.tiles_per_cta * plan.resident - 1) / ((int64_t)plan.tiles_per_cta * plan.resident);
+            ts = (ts + plan.ts_gran - 1) / plan.ts_gran * plan.ts_gran;
+            ts = std::max<int64_t>(plan.ts_min, std::min<int64_t>(ts, plan.ts_max));
+            g.ts = (int)std::min<int64_t>(ts, std::max<int64_t>(plan.ts_min, (n + plan.ts_gran - 1) / plan.ts_gran * plan.ts_gran));
+            g.tpr = (int)std::max<int64_t>(1, (n + g.ts - 1) / g.ts);
         }
         g.ntiles = nrep * g.tpr;
+        if ((int64_t)nrep * g.tpr > (int64_t)INT32_MAX / 2) return fail(GSA_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)nrep * g.tpr);
         if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)g.ntiles * recsz))) return rc;
+        // tiles that intersect the shard form one contiguous index range [t_lo, t_hi); the others are all-zero records
+        const int t_lo = (int)((col0 - (int64_t)g.rep_first * n) / g.ts);
+        const int t_hi = (rep_last - g.rep_first) * g.tpr + (int)((valid_hi - 1 - (int64_t)rep_last * n) / g.ts) + 1;
+        if (t_lo > 0) GSA_CUDA(cudaMemsetAsync(h->tile_rec.p, 0, sizeof(double) * (size_t)t_lo * recsz, h->stream));
+        if (t_hi < g.ntiles)
+            GSA_CUDA(cudaMemsetAsync(h->tile_rec.as<double>() + (size_t)t_hi * recsz, 0, sizeof(double) * (size_t)(g.ntiles - t_hi) * recsz, h->stream));
 
         if (o->input_location == GSA_LOC_DEVICE) {
-            if ((rc = plan.launch(h, A, B, g, 0, g.ntiles))) return rc;
+            if ((rc = plan.launch(h, A, B, g, t_lo, t_hi))) return rc;
         } else {
             // Stream the host design through two device buffers: the H2D copy of chunk i+1 (copy stream)
             // overlaps the kernel of chunk i.  Chunk boundaries are tile boundaries.
@@ -271,8 +286,8 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
                 h->pinned_cap = buf_bytes;
             }
             int ci = 0;
-            for (int t0 = 0; t0 < g.ntiles; t0 += tiles_per_chunk, ++ci) {
-                const int t1 = std::min(g.ntiles, t0 + tiles_per_chunk), b = ci & 1;
+            for (int t0 = t_lo; t0 < t_hi; t0 += tiles_per_chunk, ++ci) {
+                const int t1 = std::min(t_hi, t0 + tiles_per_chunk), b = ci & 1;
                 // columns needed by this chunk = hull of its NON-EMPTY tiles (tiles clipped away by the shard bounds are empty)
                 int64_t c0 = INT64_MAX, c1 = INT64_MIN;
                 for (int t = t0; t < t1; ++t) {
