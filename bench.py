@@ -279,8 +279,16 @@ def gpu_arm(args):
         peak, peak_src = peaks()
         alg_bytes = 16.0 * d * ncols                          # per launch on one GPU: A and B shards read once
         achieved = alg_bytes / (kms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per launch from the committed ncu capture (measured at N=2^22, scaled by the algorithmic bytes)
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tr = json.load(f)["fused_product_kernel"]
+            traffic, traffic_src = tr["dram_bytes_per_algorithmic_byte"] * alg_bytes, tr["source"]
+        except (OSError, KeyError, ValueError):
+            pass
         roofline = {"bound": "hbm", "kernel": "fused_product_kernel<T,CPL> (design swap + Sobol-G + Jansen sums)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
                     "per_rank_kernel_ms": per_rank_kernel_ms, "k1_design_ms": k1_ms, "k1_design_gbs": 16.0 * d * ncols / (k1_ms * 1e-3) / 1e9}
         cb = None if args.no_cpu else cpu_sample(args.cpu_log2n, 2)

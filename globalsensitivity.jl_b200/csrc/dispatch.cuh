@@ -250,7 +250,8 @@ inline int FusedPlan::prepare(gsa_handle* h, const double* params, int np_) {
         pa = params[0];
         pb = params[1];
     }
-    if (kind == PLAN_PRODUCT || kind == PLAN_SMALL_SOBOLG) {
+    if ((kind == PLAN_PRODUCT || kind == PLAN_SMALL_SOBOLG) && h->aux_kind != PLAN_PRODUCT) {
+        // (upload_params resets aux_kind whenever the parameters change)
         // g_k(x) = (|4x-2| + a_k)/(1 + a_k) = |x - 0.5| * 4/(1+a_k) + a_k/(1+a_k)
         std::vector<double> c(2 * (size_t)d);
         for (int k = 0; k < d; ++k) {
@@ -261,6 +262,8 @@ inline int FusedPlan::prepare(gsa_handle* h, const double* params, int np_) {
         if (rc) return rc;
         GSA_CUDA(cudaMemcpyAsync(h->aux.p, c.data(), sizeof(double) * c.size(), cudaMemcpyHostToDevice, h->stream));
         GSA_CUDA(cudaStreamSynchronize(h->stream));   // c is a stack-lifetime staging vector
+        GSA_CUDA(cudaEventRecord(h->ev_params, h->stream));
+        h->aux_kind = PLAN_PRODUCT;
     }
     (void)np_;
     return GSA_OK;

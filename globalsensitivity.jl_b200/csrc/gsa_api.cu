@@ -179,9 +179,17 @@ static int upload_params(gsa_handle* h, const double* params, int np) {
     int rc = h->params.reserve(sizeof(double) * std::max(np, 1));
     if (rc) return rc;
     if (np > 0) {
-        bool dev;
-        is_device_or_pinned(params, &dev);
-        GSA_CUDA(cudaMemcpyAsync(h->params.p, params, sizeof(double) * np, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        // parameters are host memory (include/gsa_cuda.h); identical parameters are not uploaded again
+        if ((int)h->params_cache.size() == np && memcmp(h->params_cache.data(), params, sizeof(double) * np) == 0) {
+            // the cached upload may have been issued on another stream (gsa_set_stream): order this call after it
+            GSA_CUDA(cudaStreamWaitEvent(h->stream, h->ev_params, 0));
+            return GSA_OK;
+        }
+        GSA_CUDA(cudaStreamSynchronize(h->stream));   // params_cache is about to be overwritten: no copy from it may be in flight
+        h->params_cache.assign(params, params + np);
+        h->aux_kind = -1;
+        GSA_CUDA(cudaMemcpyAsync(h->params.p, h->params_cache.data(), sizeof(double) * np, cudaMemcpyHostToDevice, h->stream));
+        GSA_CUDA(cudaEventRecord(h->ev_params, h->stream));
     }
     return GSA_OK;
 }
@@ -466,6 +474,7 @@ int gsa_create(int device, gsa_handle** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&h->evk0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->evk1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_params, cudaEventDisableTiming);
     for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
         e = cudaEventCreateWithFlags(&h->ev_copy[b], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming);
@@ -498,6 +507,7 @@ int gsa_destroy(gsa_handle* h) {
         if (h->ev1) cudaEventDestroy(h->ev1);
         if (h->evk0) cudaEventDestroy(h->evk0);
         if (h->evk1) cudaEventDestroy(h->evk1);
+        if (h->ev_params) cudaEventDestroy(h->ev_params);
         if (h->own_stream) cudaStreamDestroy(h->own_stream);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     }

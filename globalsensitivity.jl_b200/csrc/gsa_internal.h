@@ -54,12 +54,14 @@ struct gsa_handle {
     int device = 0;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, ev_params = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     std::mutex mu;
     gsa::DevBuf tile_rec, partials, params, vtab, lbub, stage[2], dev_in[2], ybuf, aux, gram;
     void* pinned[2] = {nullptr, nullptr};
     size_t pinned_cap = 0;
     std::vector<gsa::UserModelEntry> user_models;
+    std::vector<double> params_cache;   // host copy of what h->params currently holds (skip re-uploads of identical parameters)
+    int aux_kind = -1;                  // what h->aux holds for params_cache (plan kind), -1 = nothing
     std::vector<uint32_t> vhost;  // cached direction numbers [vdims][32]
     int vdims = 0;
     float last_ms = 0.f;

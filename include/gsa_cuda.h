@@ -123,7 +123,8 @@ GSA_API int gsa_sobol_design(gsa_handle* h, int64_t n, int d, int num_mats, cons
 /* Doubles per (replicate, output) sufficient-statistics record for these options. */
 GSA_API int gsa_sobol_nstat(const gsa_sobol_opts* opts, int d, int* nstat);
 
-/* gsa(model, Sobol(...), A, B; batch=true)  (:110-149 + :169-405) on one GPU.  A, B are d x N. */
+/* gsa(model, Sobol(...), A, B; batch=true)  (:110-149 + :169-405) on one GPU.  A, B are d x N.
+ * `params` (here and below) is always HOST memory. */
 GSA_API int gsa_sobol_run(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams,
                   const double* A, const double* B, int d, int64_t N, gsa_sobol_result* out);
 
