@@ -26,6 +26,9 @@ struct FusedPlan {
     const void* kernel = nullptr;
 
     int prod_T = 0, prod_CPL = 0;
+    bool gen = false;            // the design is generated inside the kernel (gsa_sobol_*_generated)
+    uint64_t gen_first = 0;
+    int gen_nboot = 1, gen_unit_box = 0;
     double pa = 0.0, pb = 0.0;   // Ishigami parameters (small kernel)
     int lin_DP = 0;              // padded d+1 of the linear (Gram) kernel
 
@@ -85,33 +88,37 @@ static int plan_generic(gsa_handle* h, FusedPlan* p) {
 using ProductKernel = void (*)(ProductArgs);
 static const int kProdCpl[] = {1, 2, 3, 4, 6, 8, 10, 13};
 
-template <int T>
+template <int T, bool GEN>
 static ProductKernel product_kernel_T(int cpl) {
     switch (cpl) {
-        case 8: return fused_product_kernel<T, 8>;
-        case 10: return fused_product_kernel<T, 10>;
-        case 13: return fused_product_kernel<T, 13>;
+        case 8: return fused_product_kernel<T, 8, GEN>;
+        case 10: return fused_product_kernel<T, 10, GEN>;
+        case 13: return fused_product_kernel<T, 13, GEN>;
         default: return nullptr;
     }
 }
-static ProductKernel product_kernel_for(int T, int cpl) {
+template <bool GEN>
+static ProductKernel product_kernel_sel(int T, int cpl) {
     switch (T) {
         case 1:
             switch (cpl) {
-                case 1: return fused_product_kernel<1, 1>;
-                case 2: return fused_product_kernel<1, 2>;
-                case 3: return fused_product_kernel<1, 3>;
-                case 4: return fused_product_kernel<1, 4>;
-                case 6: return fused_product_kernel<1, 6>;
-                default: return product_kernel_T<1>(cpl);
+                case 1: return fused_product_kernel<1, 1, GEN>;
+                case 2: return fused_product_kernel<1, 2, GEN>;
+                case 3: return fused_product_kernel<1, 3, GEN>;
+                case 4: return fused_product_kernel<1, 4, GEN>;
+                case 6: return fused_product_kernel<1, 6, GEN>;
+                default: return product_kernel_T<1, GEN>(cpl);
             }
-        case 2: return product_kernel_T<2>(cpl);
-        case 4: return product_kernel_T<4>(cpl);
-        case 8: return product_kernel_T<8>(cpl);
-        case 16: return product_kernel_T<16>(cpl);
-        case 32: return product_kernel_T<32>(cpl);
+        case 2: return product_kernel_T<2, GEN>(cpl);
+        case 4: return product_kernel_T<4, GEN>(cpl);
+        case 8: return product_kernel_T<8, GEN>(cpl);
+        case 16: return product_kernel_T<16, GEN>(cpl);
+        case 32: return product_kernel_T<32, GEN>(cpl);
         default: return nullptr;
     }
+}
+static ProductKernel product_kernel_for(int T, int cpl, bool gen = false) {
+    return gen ? product_kernel_sel<true>(T, cpl) : product_kernel_sel<false>(T, cpl);
 }
 
 static bool product_shape(int d, int* T, int* cpl) {
@@ -133,10 +140,10 @@ static bool product_shape(int d, int* T, int* cpl) {
 
 static int plan_product(gsa_handle* h, FusedPlan* p) {
     p->kind = PLAN_PRODUCT;
-    p->kernel = (const void*)product_kernel_for(p->prod_T, p->prod_CPL);
+    p->kernel = (const void*)product_kernel_for(p->prod_T, p->prod_CPL, p->gen);
     p->threads = PROD_THREADS;
     const int slots = p->prod_T * p->prod_CPL;
-    p->smem = sizeof(double) * (2 * slots + (PROD_THREADS / 32) * (2 * slots + 8));
+    p->smem = sizeof(double) * (2 * slots + (PROD_THREADS / 32) * (2 * slots + 8) + (p->gen ? 2 * slots + (32 * (2 * slots + 1) + 1) / 2 : 0));
     if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
     int nb = 0;
     GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));
@@ -145,13 +152,17 @@ static int plan_product(gsa_handle* h, FusedPlan* p) {
     return GSA_OK;
 }
 
-static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool second, int est, FusedPlan* p) {
+static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool second, int est, FusedPlan* p, bool gen = false) {
+    p->gen = gen;
     p->model = model; p->d = d; p->nout = nout; p->np = np; p->second = second; p->est = est;
     p->nstat = stat_count(d, est, second);
     const char* force = getenv("GSA_FORCE_GENERIC");   // testing knob: always take the generic kernel
     const bool generic_only = force && atoi(force) != 0;
     if (!generic_only && model == GSA_MODEL_SOBOL_G && !second && est == GSA_EI_JANSEN1999 && product_shape(d, &p->prod_T, &p->prod_CPL))
         return plan_product(h, p);
+    if (gen)
+        return fail(GSA_ERR_UNSUPPORTED, "fused design generation is implemented for product-form models (sobol_g), S1/ST, Jansen1999, d <= 416; "
+                                         "use gsa_sobol_design + gsa_sobol_run for this request");
     if (!generic_only && model == GSA_MODEL_LINEAR && !second && est == GSA_EI_JANSEN1999 && d + 1 <= LIN_DPMAX) {
         p->kind = PLAN_LINEAR;
         p->lin_DP = (d + 1 + 7) / 8 * 8;
@@ -236,6 +247,7 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         ProductArgs a;
         a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = h->tile_rec.as<double>();
         a.g = g; a.d = d; a.nstat = nstat; a.t_begin = t0; a.t_end = t1;
+        a.V = h->vtab.as<uint32_t>(); a.box = h->lbub.as<double2>(); a.first = gen_first; a.nboot = gen_nboot; a.unit_box = gen_unit_box;
         ((ProductKernel)kernel)<<<grid, threads, smem, h->stream>>>(a);
     }
     GSA_CUDA(cudaEventRecord(h->evk1, h->stream));

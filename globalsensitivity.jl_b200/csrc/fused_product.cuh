@@ -27,18 +27,38 @@ struct ProductArgs {
     double* tile_rec;     // [ntiles][nstat]
     TileGeom g;
     int d, nstat, t_begin, t_end;
+    // GEN only (K1 fused in: the design is generated, never read): gsa(f, ::Sobol, p_range; samples) (:407-417)
+    const uint32_t* V;    // [2*nboot*d][32] direction numbers of the 2*nboot*d-dimensional sequence
+    const double2* box;   // [d] (ub-lb, lb)
+    uint64_t first;       // 0-based sequence index of sample 0 of every replicate: 2^floor(log2 samples)
+    int nboot, unit_box;  // unit_box: lb = 0, ub = 1 for every coordinate (the affine map is the identity)
 };
 
 constexpr int PROD_THREADS = 128;  // ~160 registers/thread at CPL = 13: three CTAs (12 warps) per SM
 
-template <int T, int CPL>
+// shared memory of fused_product_kernel in doubles (GEN adds the box table and the transposed direction numbers)
+template <int T, int CPL, bool GEN>
+constexpr size_t product_smem_doubles() {
+    size_t n = 2 * T * CPL + (PROD_THREADS / 32) * (2 * T * CPL + 8);
+    if (GEN) n += 2 * T * CPL + (32 * (2 * T * CPL + 1) + 1) / 2;
+    return n;
+}
+
+// GEN = true: the kernel GENERATES the Sobol points of the samples it evaluates (K1 fused into K2+K3): no HBM reads at all.
+// A group then owns a CONTIGUOUS run of samples, so consecutive points differ by one direction number per coordinate
+// (Gray code: x ^= V[j][ctz(q+1)]); the table of the replicate's 2d dimensions sits transposed in shared memory.
+template <int T, int CPL, bool GEN>
 __global__ void __launch_bounds__(PROD_THREADS) fused_product_kernel(ProductArgs a) {
     constexpr int NW = PROD_THREADS / 32;
-    constexpr int SLOTS = T * CPL;       // padded coordinate count
-    constexpr int RED = 2 * SLOTS + 8;   // per-warp reduction record: V[SLOTS], E[SLOTS], 4 dd pairs
+    constexpr int NG = PROD_THREADS / T;  // sample groups per CTA
+    constexpr int SLOTS = T * CPL;        // padded coordinate count
+    constexpr int VROW = 2 * SLOTS + 1;   // row stride of the transposed direction-number table (+1: bank skew)
+    constexpr int RED = 2 * SLOTS + 8;    // per-warp reduction record: V[SLOTS], E[SLOTS], 4 dd pairs
     extern __shared__ double smem_p[];
     double2* scoef = reinterpret_cast<double2*>(smem_p);  // [SLOTS]
     double* sred = smem_p + 2 * SLOTS;                     // [NW][RED]
+    double2* sbox = reinterpret_cast<double2*>(sred + NW * RED);                  // GEN: [SLOTS] (ub-lb, lb)
+    uint32_t* Vs = reinterpret_cast<uint32_t*>(sred + NW * RED + 2 * SLOTS);      // GEN: [32][VROW], slot = coordinate (A) | SLOTS + coordinate (B)
     const int d = a.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & (T - 1);
@@ -47,7 +67,11 @@ __global__ void __launch_bounds__(PROD_THREADS) fused_product_kernel(ProductArgs
     // butterfly inside it must name only the T lanes of the group: a full-mask shuffle would wait forever for the lanes of a
     // group that has already left the loop (found the hard way: a hang on N = 100003, nboot = 3).
     const unsigned gmask = T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (lane & ~(T - 1)));
-    for (int i = threadIdx.x; i < SLOTS; i += PROD_THREADS) scoef[i] = i < d ? a.coef[i] : make_double2(0.0, 1.0);
+    for (int i = threadIdx.x; i < SLOTS; i += PROD_THREADS) {
+        scoef[i] = i < d ? a.coef[i] : make_double2(0.0, 1.0);
+        if (GEN) sbox[i] = i < d ? a.box[i] : make_double2(0.0, 0.0);
+    }
+    int vs_rep = -1;  // replicate whose direction numbers are in Vs
     __syncthreads();
 
     for (int tile = a.t_begin + blockIdx.x; tile < a.t_end; tile += gridDim.x) {
@@ -60,16 +84,67 @@ __global__ void __launch_bounds__(PROD_THREADS) fused_product_kernel(ProductArgs
         // T == 1: the single lane carries yA in (sA1, sA2) and yB in (sB1, sB2).
         dd sA1{0.0, 0.0}, sA2{0.0, 0.0}, sB1{0.0, 0.0}, sB2{0.0, 0.0};
 
-        for (int64_t s = c0 + grp; s < c1; s += PROD_THREADS / T) {
-            const double* as = a.A + (size_t)(s - a.g.buf_col0) * d + t;
-            const double* bs = a.B + (size_t)(s - a.g.buf_col0) * d + t;
-            double gA[CPL], gB[CPL], P[CPL];
+        // sample range of this group: strided over the tile (loads coalesce across groups) or, when generating, one contiguous run
+        int64_t s_begin = c0 + grp, s_end = c1, s_step = NG;
+        uint32_t xa[GEN ? CPL : 1], xb[GEN ? CPL : 1];
+        uint64_t q = 0;
+        if constexpr (GEN) {
+            const int rep = a.g.rep_first + tile / a.g.tpr;
+            if (rep != vs_rep) {   // (block-uniform) transpose the replicate's 2d table rows into shared memory
+                __syncthreads();
+                for (int idx = threadIdx.x; idx < 32 * 2 * SLOTS; idx += PROD_THREADS) {
+                    const int slot = idx >> 5, b = idx & 31, k = slot < SLOTS ? slot : slot - SLOTS;
+                    const int dim = (slot < SLOTS ? rep : a.nboot + rep) * d + k;
+                    Vs[b * VROW + slot] = k < d ? __ldg(a.V + (size_t)32 * dim + b) : 0u;   // padded coordinates stay at x = 0
+                }
+                vs_rep = rep;
+                __syncthreads();
+            }
+            const int64_t per = (c1 - c0 + NG - 1) / NG;
+            s_begin = c0 + grp * per;
+            s_end = s_begin + per < c1 ? s_begin + per : c1;
+            s_step = 1;
+            q = a.first + (uint64_t)(s_begin - (int64_t)rep * a.g.n);
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                // padded coordinates (k >= d) re-read coordinate 0 of the row and get coef (0, 1), i.e. g = 1
-                const int off = (t + T * i) < d ? T * i : -t;
-                gA[i] = ldg_stream(as + off);
-                gB[i] = ldg_stream(bs + off);
+            for (int i = 0; i < CPL; ++i) xa[i] = xb[i] = 0u;
+            if (s_begin < s_end)
+                for (uint64_t gq = q ^ (q >> 1); gq; gq &= gq - 1) {   // random-access start of the run
+                    const uint32_t* row = Vs + (__ffsll((long long)gq) - 1) * VROW + t;
+#pragma unroll
+                    for (int i = 0; i < CPL; ++i) { xa[i] ^= row[T * i]; xb[i] ^= row[SLOTS + T * i]; }
+                }
+        }
+        for (int64_t s = s_begin; s < s_end; s += s_step) {
+            double gA[CPL], gB[CPL], P[CPL];
+            if constexpr (GEN) {
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) {
+                    gA[i] = (double)xa[i] * 0x1p-32;   // exact
+                    gB[i] = (double)xb[i] * 0x1p-32;
+                }
+                if (!a.unit_box) {
+#pragma unroll
+                    for (int i = 0; i < CPL; ++i) {
+                        const double2 bx = sbox[t + T * i];
+                        gA[i] = __dadd_rn(__dmul_rn(bx.x, gA[i]), bx.y);   // (ub-lb)*u + lb, rounded like the design kernel
+                        gB[i] = __dadd_rn(__dmul_rn(bx.x, gB[i]), bx.y);
+                    }
+                }
+                // advance to the next point of the run: one direction number per coordinate
+                const uint32_t* row = Vs + (__ffsll((long long)~q) - 1 > 31 ? 31 : __ffsll((long long)~q) - 1) * VROW + t;
+                ++q;
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) { xa[i] ^= row[T * i]; xb[i] ^= row[SLOTS + T * i]; }
+            } else {
+                const double* as = a.A + (size_t)(s - a.g.buf_col0) * d + t;
+                const double* bs = a.B + (size_t)(s - a.g.buf_col0) * d + t;
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) {
+                    // padded coordinates (k >= d) re-read coordinate 0 of the row and get coef (0, 1), i.e. g = 1
+                    const int off = (t + T * i) < d ? T * i : -t;
+                    gA[i] = ldg_stream(as + off);
+                    gB[i] = ldg_stream(bs + off);
+                }
             }
             double LA = 1.0, LB = 1.0;
 #pragma unroll

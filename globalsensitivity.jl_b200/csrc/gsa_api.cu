@@ -205,14 +205,32 @@ static int run_reduce(gsa_handle* h, int recsz, int nstat, int tpr, int rep_firs
 // ------------------------------------------------------------------------------------------------
 // K2..K4 driver
 // ------------------------------------------------------------------------------------------------
+// design generated inside the fused kernel instead of read from A/B (gsa_sobol_*_generated)
+struct GenSpec {
+    const double* lb;
+    const double* ub;
+    int64_t samples;
+};
+
+static int ensure_directions(gsa_handle* h, int dT) {
+    if (h->vdims >= dT) return GSA_OK;
+    h->vhost.resize((size_t)dT * 32);
+    direction_numbers(0, dT, h->vhost.data());
+    int rc = h->vtab.reserve(sizeof(uint32_t) * 32 * (size_t)dT);
+    if (rc) return rc;
+    GSA_CUDA(cudaMemcpyAsync(h->vtab.p, h->vhost.data(), sizeof(uint32_t) * 32 * (size_t)dT, cudaMemcpyHostToDevice, h->stream));
+    h->vdims = dT;
+    return GSA_OK;
+}
+
 static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, const double* params, int np, const double* A,
-                         const double* B, int d, int64_t N, int64_t col0, int64_t ncols, double* partials) {
+                         const double* B, int d, int64_t N, int64_t col0, int64_t ncols, double* partials, const GenSpec* gen = nullptr) {
     int rc = check_opts(o);
     if (rc) return rc;
     if (d < 1) return fail(GSA_ERR_INVALID, "d must be >= 1");
     if (N < 0 || col0 < 0 || ncols < 0 || col0 + ncols > N) return fail(GSA_ERR_INVALID, "column range [%lld, %lld) outside the d x %lld design", (long long)col0, (long long)(col0 + ncols), (long long)N);
     if (!partials) return fail(GSA_ERR_INVALID, "partials is NULL");
-    if (ncols > 0 && (!A || !B)) return fail(GSA_ERR_INVALID, "A or B is NULL");
+    if (ncols > 0 && !gen && (!A || !B)) return fail(GSA_ERR_INVALID, "A or B is NULL");
     int nout = 0;
     if ((rc = model_nout(h, model, np, d, &nout))) return rc;
     const bool second = o->second_order != 0;
@@ -221,7 +239,27 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
     const int64_t n = N / o->nboot;
 
     FusedPlan plan;
-    if ((rc = plan_fused(h, model, d, nout, np, second, est, &plan))) return rc;
+    if ((rc = plan_fused(h, model, d, nout, np, second, est, &plan, gen != nullptr))) return rc;
+    if (gen) {
+        if ((int64_t)2 * o->nboot * d > 21201)
+            return fail(GSA_ERR_INVALID, "2*nboot*d = %lld exceeds the 21201 dimensions of the Joe-Kuo table", (long long)2 * o->nboot * d);
+        if (gen->samples < 1 || gen->samples >= ((int64_t)1 << 31)) return fail(GSA_ERR_INVALID, "samples must be in [1, 2^31)");
+        if ((rc = ensure_directions(h, 2 * o->nboot * d))) return rc;
+        if ((rc = h->lbub.reserve(sizeof(double) * 2 * (size_t)d))) return rc;
+        std::vector<double> box(2 * (size_t)d);
+        plan.gen_unit_box = 1;
+        for (int i = 0; i < d; ++i) {
+            box[2 * i] = gen->ub[i] - gen->lb[i];
+            box[2 * i + 1] = gen->lb[i];
+            if (gen->lb[i] != 0.0 || gen->ub[i] != 1.0) plan.gen_unit_box = 0;
+        }
+        GSA_CUDA(cudaMemcpyAsync(h->lbub.p, box.data(), sizeof(double) * box.size(), cudaMemcpyHostToDevice, h->stream));
+        GSA_CUDA(cudaStreamSynchronize(h->stream));   // box is a stack-lifetime staging vector
+        uint64_t first = 1;
+        while ((first << 1) <= (uint64_t)gen->samples) first <<= 1;   // 2^floor(log2 samples)
+        plan.gen_first = first;
+        plan.gen_nboot = o->nboot;
+    }
 
     h->last_launches = 0;
     h->kernel_timed = false;
@@ -241,7 +279,7 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         const int nrep = rep_last - g.rep_first + 1;
         const size_t col_bytes = sizeof(double) * (size_t)d;
         bool devp = false;
-        const bool host_in = o->input_location != GSA_LOC_DEVICE;
+        const bool host_in = !gen && o->input_location != GSA_LOC_DEVICE;
         const bool pinned = host_in && is_device_or_pinned(A, &devp) && is_device_or_pinned(B, &devp);
         // Host designs are streamed in column chunks (256 MB per matrix from pinned memory, 64 MB through the staging
         // buffers otherwise).  The kernel of a chunk only sees that chunk's tiles, so the tiles must be small enough that one
@@ -275,7 +313,7 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         if (t_hi < g.ntiles)
             GSA_CUDA(cudaMemsetAsync(h->tile_rec.as<double>() + (size_t)t_hi * recsz, 0, sizeof(double) * (size_t)(g.ntiles - t_hi) * recsz, h->stream));
 
-        if (o->input_location == GSA_LOC_DEVICE) {
+        if (!host_in) {
             if ((rc = plan.launch(h, A, B, g, t_lo, t_hi))) return rc;
         } else {
             // Stream the host design through two device buffers: the H2D copy of chunk i+1 (copy stream)
@@ -573,13 +611,7 @@ int gsa_sobol_design(gsa_handle* h, int64_t n, int d, int num_mats, const double
     DeviceGuard guard(h->device);
     const int dT = d * num_mats;
     int rc;
-    if (h->vdims < dT) {
-        h->vhost.resize((size_t)dT * 32);
-        direction_numbers(0, dT, h->vhost.data());
-        if ((rc = h->vtab.reserve(sizeof(uint32_t) * 32 * (size_t)dT))) return rc;
-        GSA_CUDA(cudaMemcpyAsync(h->vtab.p, h->vhost.data(), sizeof(uint32_t) * 32 * (size_t)dT, cudaMemcpyHostToDevice, h->stream));
-        h->vdims = dT;
-    }
+    if ((rc = ensure_directions(h, dT))) return rc;
     if ((rc = h->lbub.reserve(sizeof(double) * 2 * (size_t)d))) return rc;
     std::vector<double> sc(2 * (size_t)d);
     for (int i = 0; i < d; ++i) {
@@ -642,6 +674,37 @@ int gsa_sobol_partials(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, 
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->device);
     return partials_impl(h, opts, model_id, params, nparams, A, B, d, N, col0, ncols, partials_dev);
+}
+
+static int fetch_and_finalize(gsa_handle* h, const gsa_sobol_opts* opts, int nout, int d, int64_t n, gsa_sobol_result* out);
+
+int gsa_sobol_partials_generated(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams, const double* lb,
+                                 const double* ub, int d, int64_t samples, int64_t col0, int64_t ncols, double* partials_dev) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    if (!lb || !ub || !opts) return fail(GSA_ERR_INVALID, "lb, ub or opts is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    GenSpec gs{lb, ub, samples};
+    return partials_impl(h, opts, model_id, params, nparams, nullptr, nullptr, d, (int64_t)opts->nboot * samples, col0, ncols, partials_dev, &gs);
+}
+
+int gsa_sobol_run_generated(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams, const double* lb,
+                            const double* ub, int d, int64_t samples, gsa_sobol_result* out) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    if (!out || !lb || !ub) return fail(GSA_ERR_INVALID, "result, lb or ub is NULL");
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    int nout = 0;
+    if (d < 1) return fail(GSA_ERR_INVALID, "d must be >= 1");
+    if ((rc = model_nout(h, model_id, nparams, d, &nout))) return rc;
+    const int nstat = stat_count(d, opts->ei_estimator, opts->second_order != 0);
+    if ((rc = h->partials.reserve(sizeof(double) * (size_t)opts->nboot * nout * nstat))) return rc;
+    GenSpec gs{lb, ub, samples};
+    const int64_t N = (int64_t)opts->nboot * samples;
+    if ((rc = partials_impl(h, opts, model_id, params, nparams, nullptr, nullptr, d, N, 0, N, h->partials.as<double>(), &gs))) return rc;
+    return fetch_and_finalize(h, opts, nout, d, samples, out);
 }
 
 int gsa_sobol_partials_y(gsa_handle* h, const gsa_sobol_opts* opts, const double* Y, int nout, int d, int64_t n, double* partials_dev) {

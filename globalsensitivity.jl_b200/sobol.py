@@ -357,7 +357,7 @@ def _all_points(h: GsaHandle, method: Sobol, A: _Mat, B: _Mat, want_torch: bool)
 
 
 def gsa(f, method: Sobol, A, B=None, *, batch: bool = False, Ei_estimator="Jansen1999", samples: Optional[int] = None,
-        handle: Optional[GsaHandle] = None) -> SobolResult:
+        handle: Optional[GsaHandle] = None, fused_design: bool = True) -> SobolResult:
     """gsa(f, method::Sobol, A, B; batch, Ei_estimator) (reference :110-168), or, when `B is None` and `samples` is
     given, gsa(f, method::Sobol, p_range; samples) (:407-417) with the design generated on the GPU."""
     if not isinstance(method, Sobol):
@@ -370,6 +370,19 @@ def gsa(f, method: Sobol, A, B=None, *, batch: bool = False, Ei_estimator="Janse
         lb = [float(p[0]) for p in p_range]
         ub = [float(p[1]) for p in p_range]
         dev = isinstance(f, DeviceModel)
+        if dev and fused_design:
+            # fused design generation: the kernel generates the points it evaluates (no A/B in memory at all)
+            d = len(lb)
+            nout = f.nout(d)
+            o = _opts(method, Ei_estimator, LOC_DEVICE)
+            rc, finish, _ = _alloc_result(nout, d, method.nboot, 2 in method.order, nout > 1)
+            lbv, ubv = np.ascontiguousarray(lb, dtype=np.float64), np.ascontiguousarray(ub, dtype=np.float64)
+            code = lib().gsa_sobol_run_generated(h.ptr, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size,
+                                                 lbv.ctypes.data, ubv.ctypes.data, d, int(samples), C.byref(rc))
+            if code == _lib.GSA_OK:
+                return finish()
+            if code != 3:            # GSA_ERR_UNSUPPORTED: no generating kernel for this model/options -> materialise the design
+                check(code)
         AB = generate_design_matrices(samples, lb, ub, 2 * method.nboot, device=dev, handle=h)     # :408-413
         if dev:
             import torch
@@ -448,6 +461,24 @@ def sobol_partials(f: DeviceModel, method: Sobol, A_local, B_local, N: int, col0
     with _TorchStream(h, True):
         check(lib().gsa_sobol_partials(h.ptr, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size, Am.ptr, Bm.ptr,
                                        d, N, col0, Am.N, out.data_ptr()))
+    return out
+
+
+def sobol_partials_generated(f: DeviceModel, method: Sobol, lb, ub, samples: int, col0: int, ncols: int, *,
+                             Ei_estimator="Jansen1999", handle: Optional[GsaHandle] = None, out=None):
+    """Like sobol_partials, but the shard's design is generated inside the fused kernel (gsa_sobol_partials_generated):
+    global columns [col0, col0+ncols) of the nboot*samples-column design of gsa(f, ::Sobol, p_range; samples)."""
+    import torch
+    h = handle or getattr(f, "handle", None) or default_handle()
+    lbv, ubv = np.ascontiguousarray(lb, dtype=np.float64), np.ascontiguousarray(ub, dtype=np.float64)
+    d = lbv.size
+    nout = f.nout(d)
+    o = _opts(method, Ei_estimator, LOC_DEVICE)
+    if out is None:
+        out = torch.empty((method.nboot, nout, nstat(method, d, Ei_estimator)), dtype=torch.float64, device="cuda")
+    with _TorchStream(h, True):
+        check(lib().gsa_sobol_partials_generated(h.ptr, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size,
+                                                 lbv.ctypes.data, ubv.ctypes.data, d, int(samples), col0, ncols, out.data_ptr()))
     return out
 
 

@@ -136,6 +136,18 @@ GSA_API int gsa_sobol_partials(gsa_handle* h, const gsa_sobol_opts* opts, int mo
                        int nparams, const double* A, const double* B, int d, int64_t N, int64_t col0,
                        int64_t ncols, double* partials_dev);
 
+/* gsa(model, Sobol(...), p_range; samples) (:407-417) WITHOUT materialising A and B: the fused kernel generates the Sobol points
+ * of the samples it evaluates (K1 fused into K2+K3), so the path has no HBM reads and no design memory at all.  The design is
+ * the reference's: one 2*nboot*d-dimensional sequence, replicate r = dimensions [r*d, (r+1)*d) (A) and [(nboot+r)*d, ...) (B)
+ * at sample indices 0..samples-1, i.e. N = nboot*samples columns; the points are bit-identical to gsa_sobol_design's.
+ * Available where a generating kernel exists (product-form models, S1/ST, Jansen1999); otherwise GSA_ERR_UNSUPPORTED and the
+ * caller uses gsa_sobol_design + gsa_sobol_run.  The sharded form takes the global column range [col0, col0+ncols). */
+GSA_API int gsa_sobol_run_generated(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams,
+                            const double* lb, const double* ub, int d, int64_t samples, gsa_sobol_result* out);
+GSA_API int gsa_sobol_partials_generated(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params,
+                                 int nparams, const double* lb, const double* ub, int d, int64_t samples, int64_t col0,
+                                 int64_t ncols, double* partials_dev);
+
 /* Same sums from a precomputed model output `Y` = f(all_points), nout x (nboot*n*step), block order
  * [A | B | AB_1..AB_d (| BA_1..BA_d)] per replicate (:105-107, :181-190): the estimator-only kernel. */
 GSA_API int gsa_sobol_partials_y(gsa_handle* h, const gsa_sobol_opts* opts, const double* Y, int nout, int d,

@@ -469,3 +469,37 @@ def test_sharded_host_inputs_with_empty_chunks():
         total = p.clone() if total is None else total + p
     torch.cuda.synchronize()
     assert_parity(g.sobol_finalize(method, total, d, N), ref)
+
+
+@pytest.mark.parametrize("d,samples,nboot,unit", [(100, 20000, 1, True), (100, 4099, 3, False), (13, 30011, 5, True), (40, 1 << 14, 2, False),
+                                                    (3, 1000, 7, True), (200, 777, 1, True), (20, 1, 1, True)])
+def test_fused_design_generation(d, samples, nboot, unit):
+    """gsa(model, Sobol(nboot), p_range; samples) with the design generated inside the fused kernel (no A/B in memory): against the
+    oracle's p_range entry (:407-417) and against the materialised-design path of this library."""
+    a = np.array(([0.0, 1.0, 4.5, 9.0] + [99.0] * d)[:d])
+    p_range = [[0.0, 1.0]] * d if unit else [[-0.25 - 0.01 * k, 1.5 + 0.02 * k] for k in range(d)]
+    # the G-function is defined on the unit cube; on another box it is just a product-form test function
+    ref = so.gsa_sobol_p_range(lambda X: so.sobol_g_batch(X, a), p_range, samples, nboot=nboot)
+    model, method = g.DeviceModel("sobol_g", a), g.Sobol(nboot=nboot)
+    fused = g.gsa(model, method, p_range, samples=samples, batch=True)
+    mat = g.gsa(model, method, p_range, samples=samples, batch=True, fused_design=False)
+    if samples > 1:
+        assert_parity(fused, ref, what=("fused", d, samples, nboot))
+        assert_parity(mat, ref, what=("materialised", d, samples, nboot))
+    else:
+        assert np.all(np.isnan(fused.S1)) and np.all(np.isnan(mat.S1))     # a single sample: Var = 0/0, as in the reference
+    # sharded: two column ranges that cut a replicate
+    import torch
+    N = nboot * samples
+    total = None
+    for rank in range(2):
+        c0, nc = g.shard_columns(N, rank, 2)
+        p = g.sobol_partials_generated(model, method, [q[0] for q in p_range], [q[1] for q in p_range], samples, c0, nc)
+        total = p.clone() if total is None else total + p
+    torch.cuda.synchronize()
+    if samples > 1:
+        assert_parity(g.sobol_finalize(method, total, d, N), ref, what=("fused sharded", d, samples, nboot))
+    # second order has no generating kernel: falls back to the materialised design transparently
+    if d <= 13 and samples > 1:
+        ref2 = so.gsa_sobol_p_range(lambda X: so.sobol_g_batch(X, a), p_range, samples, order=(0, 1, 2), nboot=nboot)
+        assert_parity(g.gsa(model, g.Sobol(order=[0, 1, 2], nboot=nboot), p_range, samples=samples, batch=True), ref2)
