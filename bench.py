@@ -230,6 +230,35 @@ def gpu_arm(args):
     per_rank_kernel_ms = [round(float(x[1]), 4) for x in per_rank]
     value = w["rows"] * args.steps / (ms_total * 1e-3)
 
+    # ---- extra: the same analysis with the design GENERATED inside the fused kernel (gsa(model, Sobol(), p_range; samples)):
+    #      no A/B in memory, no HBM reads.  Reported beside the headline, not instead of it. --------------------------------
+    gen = None
+    if not args.no_gen:
+        def gen_step():
+            g.sobol_partials_generated(model, method, lb, ub, N, col0, ncols, handle=h, out=partials)
+            if world > 1:
+                dist.all_reduce(partials)
+            host_part.copy_(partials, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return g.sobol_finalize(method, host_part.numpy(), d, N)
+
+        for _ in range(args.warmup):
+            res_g = gen_step()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            res_g = gen_step()
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gen = {"value": w["rows"] * args.steps / (float(tg[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(tg[0]) / args.steps,
+               "hbm_bytes_read": 0, "note": "K1 fused into the product kernel: the Sobol points are generated in registers "
+               "(bit-identical to the materialised design), gsa_sobol_partials_generated",
+               "max_abs_diff_vs_resident": float(max(np.abs(res_g.S1 - res.S1).max(), np.abs(res_g.ST - res.ST).max()))}
+
     # ---- e2e: public API with HOST (pinned) inputs; H2D of the whole shard inside the timed region ---------------
     e2e = None
     if not args.no_e2e:
@@ -297,7 +326,7 @@ def gpu_arm(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": w, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-                "roofline": roofline, "cpu_baseline": cb, "clocks": clocks,
+                "roofline": roofline, "generated_design": gen, "cpu_baseline": cb, "clocks": clocks,
                 "check": {"S1_0": float(res.S1[0]), "S1_0_analytic": float(Vi[0] / V), "ST_0": float(res.ST[0]),
                           "ST_0_analytic": float(Vi[0] * np.prod(1 + Vi) / (1 + Vi[0]) / V)}}
         print(json.dumps(line), flush=True)
@@ -317,6 +346,7 @@ def main():
     ap.add_argument("--e2e-warmup", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gen", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

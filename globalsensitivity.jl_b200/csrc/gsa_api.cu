@@ -454,6 +454,11 @@ int partials_entry(gsa_handle* h, const gsa_sobol_opts* o, int model, const doub
     return partials_impl(h, o, model, params, np, A, B, d, N, col0, ncols, partials);
 }
 int model_nout_entry(gsa_handle* h, int model, int np, int d, int* nout) { return model_nout(h, model, np, d, nout); }
+int partials_generated_entry(gsa_handle* h, const gsa_sobol_opts* o, int model, const double* params, int np, const double* lb,
+                             const double* ub, int d, int64_t samples, int64_t col0, int64_t ncols, double* partials) {
+    GenSpec gs{lb, ub, samples};
+    return partials_impl(h, o, model, params, np, nullptr, nullptr, d, (int64_t)o->nboot * samples, col0, ncols, partials, &gs);
+}
 
 // all_points writer (fuse_designs, reference :94-108 + :116-134)
 __global__ void __launch_bounds__(256) all_points_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ P,
@@ -647,13 +652,19 @@ int gsa_sobol_design(gsa_handle* h, int64_t n, int d, int num_mats, const double
             a.ncols = nc;
             a.d = d;
             a.dT = d * nm;
-            // P*dT threads ~ 2 full waves of 2048 threads per SM
+            // two dimensions per thread (16-byte stores) when d is even and the outputs are 16-byte aligned
+            bool vec2 = d % 2 == 0 && !getenv("GSA_DESIGN_SCALAR");
+            for (int m = 0; m < nm; ++m) vec2 = vec2 && (reinterpret_cast<uintptr_t>(a.out[m]) % 16 == 0);
+            const int64_t units = vec2 ? a.dT / 2 : a.dT;     // work items per point
+            const int tpb = vec2 ? DESIGN_THREADS2 : DESIGN_THREADS;
+            // P*units threads ~ 2 full waves of 2048 threads per SM
             const int64_t want = (int64_t)h->sm_count * 2048 * 2;
             int lp = 0;
-            while (((int64_t)1 << lp) * a.dT < want && ((int64_t)1 << lp) < nc) ++lp;
+            while (((int64_t)1 << lp) * units < want && ((int64_t)1 << lp) < nc) ++lp;
             a.lp = lp;
-            const int64_t threads = ((int64_t)1 << lp) * a.dT;
-            sobol_design_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, h->stream>>>(a);
+            const int64_t threads = ((int64_t)1 << lp) * units;
+            if (vec2) sobol_design_kernel2<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, h->stream>>>(a);
+            else sobol_design_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, h->stream>>>(a);
             h->last_launches++;
             GSA_CUDA(cudaGetLastError());
         }

@@ -21,6 +21,8 @@ namespace gsa {
 int partials_entry(gsa_handle* h, const gsa_sobol_opts* o, int model, const double* params, int np, const double* A, const double* B,
                    int d, int64_t N, int64_t col0, int64_t ncols, double* partials);
 int model_nout_entry(gsa_handle* h, int model, int np, int d, int* nout);
+int partials_generated_entry(gsa_handle* h, const gsa_sobol_opts* o, int model, const double* params, int np, const double* lb,
+                             const double* ub, int d, int64_t samples, int64_t col0, int64_t ncols, double* partials);
 }  // namespace gsa
 
 using namespace gsa;
@@ -127,12 +129,13 @@ int gsa_multi_handle(gsa_multi* m, int i, gsa_handle** out) {
     return GSA_OK;
 }
 
+}  // extern "C"
+
 // gsa(model, Sobol(...), A, B; batch=true) with the design sharded over the devices of `m`.  A, B: d x N in HOST memory
-// (input_location must be GSA_LOC_HOST; pinned memory is streamed without staging).
-int gsa_multi_sobol_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams, const double* A,
-                        const double* B, int d, int64_t N, gsa_sobol_result* out) {
-    if (!m || !opts || !out) return fail(GSA_ERR_INVALID, "NULL argument to gsa_multi_sobol_run");
-    if (opts->input_location != GSA_LOC_HOST) return fail(GSA_ERR_INVALID, "gsa_multi_sobol_run takes host designs (input_location = GSA_LOC_HOST)");
+// (input_location must be GSA_LOC_HOST; pinned memory is streamed without staging); or, with lb/ub, the generated design.
+static int multi_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams, const double* A,
+                     const double* B, const double* lb, const double* ub, int64_t samples, int d, int64_t N, gsa_sobol_result* out) {
+    const bool generated = lb != nullptr;
     if (model_id >= GSA_MODEL_USER_BASE) return fail(GSA_ERR_UNSUPPORTED, "user models are registered per handle; not supported by the multi-device entry yet");
     MDBG("run: enter");
     std::lock_guard<std::mutex> lk(m->mu);
@@ -156,7 +159,9 @@ int gsa_multi_sobol_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, 
             cudaSetDevice(hh->device);
             MDBG("worker %d: device set", g);
             int r = hh->partials.reserve(sizeof(double) * cnt);
-            if (r == GSA_OK)
+            if (r == GSA_OK && generated)
+                r = partials_generated_entry(hh, opts, model_id, params, nparams, lb, ub, d, samples, col0, ncols, hh->partials.as<double>());
+            else if (r == GSA_OK)
                 r = partials_entry(hh, opts, model_id, params, nparams, A ? A + (size_t)d * col0 : nullptr, B ? B + (size_t)d * col0 : nullptr, d, N,
                                    col0, ncols, hh->partials.as<double>());
             if (r != GSA_OK) {
@@ -199,6 +204,24 @@ int gsa_multi_sobol_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, 
         GSA_CUDA(cudaStreamSynchronize(m->h[g]->stream));
     }
     return finalize_host(*opts, host.data(), nout, d, N / opts->nboot, out);
+}
+
+extern "C" {
+
+int gsa_multi_sobol_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams, const double* A,
+                        const double* B, int d, int64_t N, gsa_sobol_result* out) {
+    if (!m || !opts || !out) return fail(GSA_ERR_INVALID, "NULL argument to gsa_multi_sobol_run");
+    if (opts->input_location != GSA_LOC_HOST) return fail(GSA_ERR_INVALID, "gsa_multi_sobol_run takes host designs (input_location = GSA_LOC_HOST)");
+    return multi_run(m, opts, model_id, params, nparams, A, B, nullptr, nullptr, 0, d, N, out);
+}
+
+// gsa(model, Sobol(...), p_range; samples) (:407-417) over all devices with the design generated inside the fused kernel:
+// nothing but lb/ub goes in and nothing but the partial sums comes out.
+int gsa_multi_sobol_run_generated(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams,
+                                  const double* lb, const double* ub, int d, int64_t samples, gsa_sobol_result* out) {
+    if (!m || !opts || !out || !lb || !ub) return fail(GSA_ERR_INVALID, "NULL argument to gsa_multi_sobol_run_generated");
+    if (opts->nboot < 1 || samples < 1) return fail(GSA_ERR_INVALID, "nboot and samples must be >= 1");
+    return multi_run(m, opts, model_id, params, nparams, nullptr, nullptr, lb, ub, samples, d, (int64_t)opts->nboot * samples, out);
 }
 
 }  // extern "C"

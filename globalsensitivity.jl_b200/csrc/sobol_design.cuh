@@ -65,4 +65,53 @@ __global__ void __launch_bounds__(DESIGN_THREADS) sobol_design_kernel(DesignArgs
     }
 }
 
+// Two adjacent dimensions per thread (d even): the index arithmetic, the trailing-ones scan and the store instruction are
+// shared by two coordinates (one 16-byte store), which roughly halves the instructions per point -- the one-dimension kernel
+// above is issue-limited (61 % issue-active at 5.2 TB/s, profiles/r1_k1_design_after.txt).
+constexpr int DESIGN_THREADS2 = 128;
+
+__global__ void __launch_bounds__(DESIGN_THREADS2) sobol_design_kernel2(DesignArgs a) {
+    constexpr int ROW = 2 * DESIGN_THREADS2 + 2;   // even row stride: the (x0, x1) pair of a thread is one aligned 8-byte word
+    __shared__ __align__(8) uint32_t Vs[32 * ROW];
+    const int64_t P = (int64_t)1 << a.lp;
+    const int dT2 = a.dT / 2;
+    const int64_t total = P * dT2;
+    const int64_t f0 = (int64_t)blockIdx.x * DESIGN_THREADS2;
+    for (int idx = threadIdx.x; idx < 32 * 2 * DESIGN_THREADS2; idx += DESIGN_THREADS2) {
+        const int slot = idx >> 5, b = idx & 31;
+        const int64_t fs = f0 + (slot >> 1);
+        if (fs < total) Vs[b * ROW + slot] = __ldg(a.V + 32 * (2 * (int)(fs % dT2) + (slot & 1)) + b);
+    }
+    __syncthreads();
+    const int64_t f = f0 + threadIdx.x;
+    if (f >= total) return;
+    const int64_t p0 = f / dT2;
+    const int j = 2 * (int)(f - p0 * dT2);
+    if (p0 >= a.ncols) return;
+    const int m = j / a.d, i = j - m * a.d;   // d is even: both dimensions belong to matrix m
+    const double sc0 = __ldg(a.scale + i), lo0 = __ldg(a.lb + i), sc1 = __ldg(a.scale + i + 1), lo1 = __ldg(a.lb + i + 1);
+    double* out = a.out[m] + i;
+    const uint2* Vp = reinterpret_cast<const uint2*>(Vs) + threadIdx.x;   // row b at Vp[b * ROW / 2]
+
+    uint64_t q = a.first + (uint64_t)p0;
+    uint2 x = make_uint2(0u, 0u);
+    for (uint64_t g = q ^ (q >> 1); g; g &= g - 1) {
+        const uint2 v = Vp[(__ffsll((long long)g) - 1) * (ROW / 2)];
+        x.x ^= v.x; x.y ^= v.y;
+    }
+    const uint2 vlow = a.lp > 0 ? Vp[(a.lp - 1) * (ROW / 2)] : make_uint2(0u, 0u);
+
+    for (int64_t p = p0; p < a.ncols; p += P) {
+        double2 r;
+        r.x = __dadd_rn(__dmul_rn(sc0, (double)x.x * 0x1p-32), lo0);   // (ub-lb)*u + lb, mul and add rounded separately
+        r.y = __dadd_rn(__dmul_rn(sc1, (double)x.y * 0x1p-32), lo1);
+        *reinterpret_cast<double2*>(out + (size_t)a.d * p) = r;
+        const uint64_t h = q >> a.lp;
+        const int c = __ffsll((long long)~h) - 1;                       // trailing ones of h
+        const uint2 v = Vp[min(a.lp + c, 31) * (ROW / 2)];              // (clamp only matters for the unused last update)
+        x.x ^= vlow.x ^ v.x; x.y ^= vlow.y ^ v.y;
+        q += (uint64_t)P;
+    }
+}
+
 }  // namespace gsa

@@ -174,6 +174,17 @@ class GsaMulti:
                                         d, N, C.byref(rc)))
         return finish()
 
+    def gsa_p_range(self, f: "DeviceModel", method: "Sobol", p_range, samples: int, *, Ei_estimator="Jansen1999") -> "SobolResult":
+        """gsa(f, Sobol(...), p_range; samples) over all devices with the design generated inside the fused kernel."""
+        lb = np.ascontiguousarray([float(p[0]) for p in p_range]); ub = np.ascontiguousarray([float(p[1]) for p in p_range])
+        d = lb.size
+        nout = f.nout(d)
+        o = _opts(method, Ei_estimator, LOC_DEVICE)
+        rc, finish, _ = _alloc_result(nout, d, method.nboot, 2 in method.order, nout > 1)
+        check(lib().gsa_multi_sobol_run_generated(self._m, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size,
+                                                  lb.ctypes.data, ub.ctypes.data, d, int(samples), C.byref(rc)))
+        return finish()
+
 
 _default = {}
 

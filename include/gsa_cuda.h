@@ -185,6 +185,10 @@ GSA_API int gsa_multi_handle(gsa_multi* m, int i, gsa_handle** out);
 GSA_API int gsa_multi_sobol_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams,
                         const double* A, const double* B, int d, int64_t N, gsa_sobol_result* out);
 
+/* the same over the devices of `m` with the design generated inside the fused kernel (see gsa_sobol_run_generated) */
+GSA_API int gsa_multi_sobol_run_generated(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, const double* params,
+                                  int nparams, const double* lb, const double* ub, int d, int64_t samples, gsa_sobol_result* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -417,6 +417,11 @@ def test_multi_device_single_process(ishigami_design):
     ref = gsa_ref.gsa_sobol("linear", W, A, B)
     res = m.gsa(g.DeviceModel("linear", W), g.Sobol(), A, B)
     assert_parity(res, ref, what=("multi linear", ndev))
+    # generated design over all devices (nothing but lb/ub goes in)
+    a = np.array([0.0, 1.0, 4.5, 9.0] + [99.0] * 16)
+    ref = so.gsa_sobol_p_range(lambda X: so.sobol_g_batch(X, a), [[0.0, 1.0]] * 20, 30011, nboot=3)
+    res = m.gsa_p_range(g.DeviceModel("sobol_g", a), g.Sobol(nboot=3), [[0.0, 1.0]] * 20, 30011)
+    assert_parity(res, ref, what=("multi generated", ndev))
     m.close()
 
 
