@@ -508,3 +508,65 @@ def test_fused_design_generation(d, samples, nboot, unit):
     if d <= 13 and samples > 1:
         ref2 = so.gsa_sobol_p_range(lambda X: so.sobol_g_batch(X, a), p_range, samples, order=(0, 1, 2), nboot=nboot)
         assert_parity(g.gsa(model, g.Sobol(order=[0, 1, 2], nboot=nboot), p_range, samples=samples, batch=True), ref2)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE shapes at (near) full size
+def test_config3_full_size_vs_oracle():
+    """BASELINE config 3 at full size: Sobol G d=8, order=[0,1,2], N=2^22, against the oracle and the analytic indices."""
+    d, N = 8, 1 << 22
+    a = np.array([0.0, 1.0, 4.5, 9.0, 99.0, 99.0, 99.0, 99.0])
+    A, B = g.generate_design_matrices(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, order=(0, 1, 2))
+    res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2]), A, B, batch=True)
+    assert_parity(res, ref)
+    Y = gsa_ref.model_batch("sobol_g", a, gsa_ref.all_points(A, B, 1, True))        # 604 MB: the estimator-only kernel on it
+    assert_parity(g.gsa_sobol_all_y_analysis(g.Sobol(order=[0, 1, 2]), Y, d, N), ref)
+    Vi = 1.0 / (3.0 * (1.0 + a) ** 2)
+    V = np.prod(1.0 + Vi) - 1.0
+    assert np.abs(res.S1 - Vi / V).max() < 2e-4 and np.abs(res.ST - Vi * np.prod(1.0 + Vi) / (1.0 + Vi) / V).max() < 2e-4
+    assert abs(res.S2[0, 1] - Vi[0] * Vi[1] / V) < 2e-4
+
+
+def test_config5_shape_properties():
+    """BASELINE config 5's shape (Sobol G, d=100, S1/ST) at N=2^22 (6.7 GB): size-independent properties instead of the oracle --
+    shard additivity, generated == materialised design, analytic indices."""
+    import torch
+    d, N = 100, 1 << 22
+    a = np.array([0.0, 1.0, 4.5, 9.0] + [99.0] * 96)
+    model, method = g.DeviceModel("sobol_g", a), g.Sobol()
+    lb, ub = np.zeros(d), np.ones(d)
+    A, B = g.generate_design_matrices(N, lb, ub, 2, device=True)
+    whole = g.gsa(model, method, A, B, batch=True)
+    total = None
+    for rank in range(8):
+        c0, nc = g.shard_columns(N, rank, 8)
+        p = g.sobol_partials(model, method, A[:, c0:c0 + nc], B[:, c0:c0 + nc], N, c0)
+        total = p.clone() if total is None else total + p
+    torch.cuda.synchronize()
+    assert_parity(g.sobol_finalize(method, total, d, N), whole)
+    assert_parity(g.gsa(model, method, [[0.0, 1.0]] * d, samples=N, batch=True), whole)      # design generated in the kernel
+    Vi = 1.0 / (3.0 * (1.0 + a) ** 2)
+    V = np.prod(1.0 + Vi) - 1.0
+    assert np.abs(whole.S1 - Vi / V).max() < 1e-4 and np.abs(whole.ST - Vi * np.prod(1.0 + Vi) / (1.0 + Vi) / V).max() < 1e-4
+
+
+def test_config4_full_size_analytic():
+    """BASELINE config 4 at full size (linear, d=20, 256 outputs, N=2^22; the reference's all_y would be 189 GB): analytic
+    S1 = ST = W^2 sigma^2 / sum W^2 sigma^2 and shard additivity."""
+    import torch
+    d, nout, N = 20, 256, 1 << 22
+    o, i = np.meshgrid(np.arange(1, nout + 1), np.arange(1, d + 1), indexing="ij")
+    W = 1.0 + ((o * 31 + i * 17) % 13) / 13.0
+    model, method = g.DeviceModel("linear", W), g.Sobol()
+    A, B = g.generate_design_matrices(N, np.zeros(d), np.ones(d), 2, device=True)
+    res = g.gsa(model, method, A, B, batch=True)
+    S = W ** 2 / (W ** 2).sum(axis=1, keepdims=True)
+    assert res.S1.shape == (nout, d)
+    assert np.abs(res.S1 - S).max() < 2e-4 and np.abs(res.ST - S).max() < 2e-4
+    total = None
+    for rank in range(3):
+        c0, nc = g.shard_columns(N, rank, 3)
+        p = g.sobol_partials(model, method, A[:, c0:c0 + nc], B[:, c0:c0 + nc], N, c0)
+        total = p.clone() if total is None else total + p
+    torch.cuda.synchronize()
+    assert_parity(g.sobol_finalize(method, total, d, N), res)
