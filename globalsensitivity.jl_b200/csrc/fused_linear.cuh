@@ -242,14 +242,16 @@ __global__ void __launch_bounds__(256) linear_records_kernel(LinearRecArgs a) {
             double* rec = a.tile_rec + ((size_t)tile * a.nout + o) * a.nstat;
             for (int i = 0; i < a.nstat; ++i) rec[i] = 0.0;
             if (m == 0.0) continue;
+            double w[LIN_DPMAX];                           // this output's row of W (coalesced loads across outputs)
+            for (int l = 0; l < d; ++l) w[l] = __ldg(a.W + o + (size_t)a.nout * l);
             // y0 = w.c ; S' = sum_l w_l G[l][d] ; Q' = w' G w (l,k < d)
             double y0 = 0.0, S1 = 0.0, Q = 0.0;
             for (int l = 0; l < d; ++l) {
-                const double wl = __ldg(a.W + o + (size_t)a.nout * l);
+                const double wl = w[l];
                 y0 = fma(wl, c[l], y0);
                 S1 = fma(wl, G[l * DP + d], S1);
                 double row = 0.0;
-                for (int k = 0; k < d; ++k) row = fma(__ldg(a.W + o + (size_t)a.nout * k), G[l * DP + k], row);
+                for (int k = 0; k < d; ++k) row = fma(w[k], G[l * DP + k], row);
                 Q = fma(wl, row, Q);
             }
             // un-shift exactly: sum y = S' + 2m y0 ; sum y^2 = Q' + 2 y0 S' + 2m y0^2   (double-double)
@@ -261,9 +263,9 @@ __global__ void __launch_bounds__(256) linear_records_kernel(LinearRecArgs a) {
             dd_add_dd(syy, dd_mul_d(t, 2.0 * m));
             rec[0] = sy.hi; rec[1] = sy.lo; rec[2] = syy.hi; rec[3] = syy.lo;
             for (int k = 0; k < d; ++k) {
-                const double wk = __ldg(a.W + o + (size_t)a.nout * k);
+                const double wk = w[k];
                 double hv = y0 * H[d * DP + k];            // y0 * sum delta_k   (row d of H: b_ext[d] = 1)
-                for (int l = 0; l < d; ++l) hv = fma(__ldg(a.W + o + (size_t)a.nout * l), H[l * DP + k], hv);
+                for (int l = 0; l < d; ++l) hv = fma(w[l], H[l * DP + k], hv);
                 rec[stat_v(k)] = wk * hv;                  // sum yB (yAB_k - yA)       (:192)
                 rec[stat_e(d, 0, k)] = wk * wk * D[k];     // sum (yA - yAB_k)^2        (:213)
             }

@@ -34,6 +34,9 @@ struct ProductArgs {
     int nboot, unit_box;  // unit_box: lb = 0, ub = 1 for every coordinate (the affine map is the identity)
 };
 
+#ifndef PROD_GEN_MINBLOCKS
+#define PROD_GEN_MINBLOCKS 3   // 168 registers (a few spilled words) and 12 warps/SM vs 205 registers and 8 warps/SM
+#endif
 constexpr int PROD_THREADS = 128;  // ~160 registers/thread at CPL = 13: three CTAs (12 warps) per SM
 
 // shared memory of fused_product_kernel in doubles (GEN adds the box table and the transposed direction numbers)
@@ -48,7 +51,7 @@ constexpr size_t product_smem_doubles() {
 // A group then owns a CONTIGUOUS run of samples, so consecutive points differ by one direction number per coordinate
 // (Gray code: x ^= V[j][ctz(q+1)]); the table of the replicate's 2d dimensions sits transposed in shared memory.
 template <int T, int CPL, bool GEN>
-__global__ void __launch_bounds__(PROD_THREADS) fused_product_kernel(ProductArgs a) {
+__global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fused_product_kernel(ProductArgs a) {
     constexpr int NW = PROD_THREADS / 32;
     constexpr int NG = PROD_THREADS / T;  // sample groups per CTA
     constexpr int SLOTS = T * CPL;        // padded coordinate count

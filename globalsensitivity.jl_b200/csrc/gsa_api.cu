@@ -195,8 +195,13 @@ static int upload_params(gsa_handle* h, const double* params, int np) {
 }
 
 static int run_reduce(gsa_handle* h, int recsz, int nstat, int tpr, int rep_first, int nrep, double* partials) {
-    dim3 grid((recsz + RT_X - 1) / RT_X, nrep), block(RT_X, RT_Y);
-    reduce_tiles_kernel<<<grid, block, 0, h->stream>>>(h->tile_rec.as<double>(), partials, recsz, nstat, tpr, rep_first);
+    if (tpr <= 16) {
+        const int64_t n = (int64_t)nrep * recsz;
+        reduce_tiles_flat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->tile_rec.as<double>(), partials, recsz, nstat, tpr, rep_first, nrep);
+    } else {
+        dim3 grid((recsz + RT_X - 1) / RT_X, nrep), block(RT_X, RT_Y);
+        reduce_tiles_kernel<<<grid, block, 0, h->stream>>>(h->tile_rec.as<double>(), partials, recsz, nstat, tpr, rep_first);
+    }
     h->last_launches++;
     GSA_CUDA(cudaGetLastError());
     return GSA_OK;
