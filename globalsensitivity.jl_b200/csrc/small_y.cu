@@ -20,7 +20,11 @@ int launch_small_y(gsa_handle* h, int d, bool second, int est, const double* Y, 
     case DD: return second ? go<(DD <= SMALL_DMAX2 ? DD : 1), true>(h, est, Y, n, nout, step, g, nstat, tile_rec, occ) : go<DD, false>(h, est, Y, n, nout, step, g, nstat, tile_rec, occ);
         GSA_SMALL_D_CASES(CASE)
 #undef CASE
-        default: return fail(GSA_ERR_UNSUPPORTED, "small estimator kernel supports d <= %d", SMALL_DMAX);
+#define CASE(DD) \
+    case DD: return second ? fail(GSA_ERR_UNSUPPORTED, "small second-order kernel supports d <= %d", SMALL_DMAX2) : go<DD, false>(h, est, Y, n, nout, step, g, nstat, tile_rec, occ);
+        GSA_SMALL_D_CASES_Y(CASE)
+#undef CASE
+        default: return fail(GSA_ERR_UNSUPPORTED, "small estimator kernel supports d <= %d", SMALL_DMAX_Y);
     }
 }
 

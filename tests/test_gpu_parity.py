@@ -570,3 +570,17 @@ def test_config4_full_size_analytic():
         total = p.clone() if total is None else total + p
     torch.cuda.synchronize()
     assert_parity(g.sobol_finalize(method, total, d, N), res)
+
+
+@pytest.mark.parametrize("d", [13, 16, 17, 24, 32, 33])
+def test_analyze_y_mid_d_first_order(d):
+    """First-order estimator-on-Y for 12 < d <= 32 runs on the register kernel (Jansen) -- d = 33 and the three-term estimators
+    beyond d = 16 take the shared-memory kernel; all must agree with the oracle."""
+    N, nboot = 6007, 2
+    a = np.linspace(0.0, 30.0, d)
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    Y = gsa_ref.model_batch("sobol_g", a, gsa_ref.all_points(A, B, nboot, False))
+    for est in so.EI_ESTIMATORS:
+        ref = gsa_ref.analyze_y(Y, d, N // nboot, nboot=nboot, Ei_estimator=est)
+        res = g.gsa_sobol_all_y_analysis(g.Sobol(nboot=nboot), Y, d, N // nboot, est)
+        assert_parity(res, ref, what=(d, est))
