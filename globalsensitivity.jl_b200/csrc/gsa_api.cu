@@ -408,7 +408,7 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
         const char* force = getenv("GSA_FORCE_GENERIC");
         // register kernel: d <= 8 with second order; first order d <= 24 (Jansen: 6.4-6.5 TB/s; at d = 32 it spills and drops to 4.0 TB/s)
         // or 16 (the three-term estimators need 4d accumulators)
-        const bool small = d <= (second ? SMALL_DMAX2 : (est == GSA_EI_JANSEN1999 ? 24 : 16)) && !(force && atoi(force) != 0);
+        const bool small = d <= (second ? SMALL_DMAX2 : (est == GSA_EI_JANSEN1999 ? SMALL_DMAX_Y : 16)) && !(force && atoi(force) != 0);
         int tpr = 1;
         if (small) {
             // thread-per-sample register kernel: every Y value is read exactly once, straight into registers

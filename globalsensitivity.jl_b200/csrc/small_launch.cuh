@@ -8,7 +8,7 @@
 namespace gsa {
 
 constexpr int SMALL_DMAX = 12;   // first order only (fused sources)
-constexpr int SMALL_DMAX_Y = 32; // estimator-on-Y, first order: D+2 staged values + 2D accumulators still fit in registers
+constexpr int SMALL_DMAX_Y = 24; // estimator-on-Y, first order: D+2 staged values + 2D accumulators still fit in registers
 constexpr int SMALL_DMAX2 = 8;   // with second order (2D+2 values + 2D + D(D-1)/2 accumulators must fit in registers)
 
 // `occupancy_only` != nullptr: just report the resident CTAs per SM of the kernel that would be launched
@@ -37,9 +37,8 @@ int launch_small(gsa_handle* h, SmallArgs<Src>& a, int* occupancy_only = nullptr
 
 // expands CASE(D) for D = 1..12
 #define GSA_SMALL_D_CASES(CASE) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
-// expands CASE(D) for D = 13..32 (estimator-on-Y, first order only)
-#define GSA_SMALL_D_CASES_Y(CASE) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17) CASE(18) CASE(19) CASE(20) CASE(21) CASE(22) CASE(23) CASE(24) \
-    CASE(25) CASE(26) CASE(27) CASE(28) CASE(29) CASE(30) CASE(31) CASE(32)
+// expands CASE(D) for D = 13..24 (estimator-on-Y, first order only)
+#define GSA_SMALL_D_CASES_Y(CASE) CASE(13) CASE(14) CASE(15) CASE(16) CASE(17) CASE(18) CASE(19) CASE(20) CASE(21) CASE(22) CASE(23) CASE(24)
 
 // declared here, defined in small_y.cu / small_ishigami.cu / small_sobolg.cu
 int launch_small_y(gsa_handle* h, int d, bool second, int est, const double* Y, int64_t n, int nout, int step, const TileGeom& g,

@@ -281,10 +281,10 @@ def test_ishigami_small_kernels(est, d, second, nboot):
     assert_parity(res, ref, what=(est, d, second, nboot))
 
 
-@pytest.mark.parametrize("second", [False, True])
-def test_analyze_y_large_d(second):
-    """d > 12 takes the shared-memory estimator kernel (estimator_y.cuh) instead of the register kernel."""
-    d, N, nboot = 14, 9001, 2
+@pytest.mark.parametrize("second,d", [(False, 14), (True, 9), (True, 14), (True, 20), (True, 24), (True, 26), (False, 40)])
+def test_analyze_y_large_d(second, d):
+    """Beyond the register kernel's range (d > 24, or d > 8 with second order): the shared-memory estimator kernel (estimator_y.cuh)."""
+    N, nboot = 9001, 2
     a = np.linspace(0.0, 20.0, d)
     A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
     order = (0, 1, 2) if second else (0, 1)
