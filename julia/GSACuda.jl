@@ -120,11 +120,22 @@ function generate_design_matrices(n::Integer, lb::Vector{Float64}, ub::Vector{Fl
     return mats
 end
 
-function gsa(model::DeviceModel, method::Sobol, p_range::AbstractVector; samples, kwargs...)
+function gsa(model::DeviceModel, method::Sobol, p_range::AbstractVector; samples, Ei_estimator = :Jansen1999,
+             handle::Handle = default_handle(), kwargs...)
     lb = [float(p[1]) for p in p_range]; ub = [float(p[2]) for p in p_range]
-    AB = generate_design_matrices(samples, lb, ub, 2 * method.nboot)
+    # first choice: the design is generated inside the fused kernel (no A/B in memory at all) ...
+    d = length(lb); second = 2 in method.order
+    opts = Ref(GsaSobolOpts(second, method.nboot, method.conf_level, EI[Ei_estimator], 1))
+    res, finish, keep = alloc(nout(model, d), d, method.nboot, second)
+    rc = GC.@preserve keep model lb ub ccall((:gsa_sobol_run_generated, libgsa), Cint,
+        (Ptr{Cvoid}, Ref{GsaSobolOpts}, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Int64, Ref{GsaSobolResult}),
+        handle.ptr, opts, model.id, model.params, length(model.params), lb, ub, d, samples, Ref(res))
+    rc == 0 && return finish()
+    rc == 3 || check(rc)              # GSA_ERR_UNSUPPORTED: no generating kernel for this model/options
+    # ... otherwise materialise the design on the GPU, as the reference does on the CPU (:408-415)
+    AB = generate_design_matrices(samples, lb, ub, 2 * method.nboot; handle = handle)
     A = reduce(hcat, AB[1:method.nboot]); B = reduce(hcat, AB[(method.nboot + 1):end])
-    return gsa(model, method, A, B; kwargs...)
+    return gsa(model, method, A, B; Ei_estimator = Ei_estimator, handle = handle, kwargs...)
 end
 
 # ---- estimator-only entry: any Julia closure keeps producing all_y, the GPU replaces gsa_sobol_all_y_analysis ---
@@ -150,6 +161,32 @@ function gsa_sobol_all_y_analysis(method::Sobol, all_y::VecOrMat{Float64}, d::In
                         reshape(r.ST, 1, :), r.ST_Conf_Int === nothing ? nothing : reshape(r.ST_Conf_Int, 1, :))
     end
     return r
+end
+
+# ---- one process, all GPUs (gsa_multi_*): contiguous column shards, one grouped ncclAllReduce of the partial sums ----------------
+mutable struct Multi
+    ptr::Ptr{Cvoid}
+    function Multi(devices::Vector{<:Integer} = Int[])
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        devs = Cint.(devices)
+        check(ccall((:gsa_multi_create, libgsa), Cint, (Ptr{Cint}, Cint, Ref{Ptr{Cvoid}}),
+                    isempty(devs) ? C_NULL : devs, max(length(devs), 1), r))
+        m = new(r[])
+        finalizer(x -> ccall((:gsa_multi_destroy, libgsa), Cint, (Ptr{Cvoid},), x.ptr), m)
+        return m
+    end
+end
+
+function gsa(m::Multi, model::DeviceModel, method::Sobol, A::Matrix{Float64}, B::Matrix{Float64}; Ei_estimator = :Jansen1999)
+    d, N = size(A); second = 2 in method.order
+    opts = Ref(GsaSobolOpts(second, method.nboot, method.conf_level, EI[Ei_estimator], 0))
+    res, finish, keep = alloc(nout(model, d), d, method.nboot, second)
+    GC.@preserve A B keep model begin
+        check(ccall((:gsa_multi_sobol_run, libgsa), Cint,
+                    (Ptr{Cvoid}, Ref{GsaSobolOpts}, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Int64, Ref{GsaSobolResult}),
+                    m.ptr, opts, model.id, model.params, length(model.params), A, B, d, N, Ref(res)))
+    end
+    return finish()
 end
 
 end # module
