@@ -7,12 +7,13 @@
 #include "gsa_internal.h"
 #include "fused_generic.cuh"
 #include "fused_product.cuh"
+#include "fused_product2.cuh"
 #include "small_launch.cuh"
 #include "fused_linear.cuh"
 
 namespace gsa {
 
-enum { PLAN_GENERIC = 0, PLAN_PRODUCT = 1, PLAN_SMALL_ISHIGAMI = 2, PLAN_SMALL_SOBOLG = 3, PLAN_LINEAR = 4 };
+enum { PLAN_GENERIC = 0, PLAN_PRODUCT = 1, PLAN_SMALL_ISHIGAMI = 2, PLAN_SMALL_SOBOLG = 3, PLAN_LINEAR = 4, PLAN_PRODUCT2 = 5 };
 
 struct FusedPlan {
     int kind = PLAN_GENERIC;
@@ -186,6 +187,35 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
         p->ts_min = p->ts_gran = LIN_S;
         return GSA_OK;
     }
+    {
+        const char* e2 = getenv("GSA_PRODUCT2");   // tuning knob: 0 / 1 forces the lane-per-coordinate second-order kernel off / on
+        // (d <= 8 stays on the thread-per-sample register kernel: 0.14 vs 0.30 ms on config 3 -- with one coordinate per lane the
+        // shuffles and the per-lane double-double sums dominate; for 8 < d <= 32 it is 3x faster than the generic kernel)
+        const bool want2 = e2 ? atoi(e2) != 0 : d > SMALL_DMAX2;
+        if (!generic_only && model == GSA_MODEL_SOBOL_G && second && est == GSA_EI_JANSEN1999 && d >= 2 && d <= 32 && want2) {
+            int T = 2;
+            while (T < d) T <<= 1;
+            p->kind = PLAN_PRODUCT2;
+            p->prod_T = T;
+            p->threads = PROD2_THREADS;
+            const void* k = nullptr;
+            size_t sm = 0;
+            switch (T) {
+#define GSA_P2(TV) case TV: k = (const void*)fused_product2_kernel<TV>; sm = product2_smem_bytes<TV>(); break;
+                GSA_P2(2) GSA_P2(4) GSA_P2(8) GSA_P2(16) GSA_P2(32)
+#undef GSA_P2
+            }
+            p->kernel = k;
+            p->smem = sm;
+            if (sm > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            int nb = 0;
+            GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, PROD2_THREADS, sm));
+            p->resident = std::max(1, nb) * h->sm_count;
+            p->tiles_per_cta = 2;
+            p->ts_min = p->ts_gran = PROD2_THREADS / T;
+            return GSA_OK;
+        }
+    }
     const bool small_ishi = model == GSA_MODEL_ISHIGAMI && (d == 3 || d == 4);
     const bool small_g = model == GSA_MODEL_SOBOL_G && d <= (second ? SMALL_DMAX2 : SMALL_DMAX);
     if (!generic_only && (small_ishi || small_g)) {
@@ -243,6 +273,13 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         GSA_CUDA(cudaGetLastError());
         return GSA_OK;
     }
+    else if (kind == PLAN_PRODUCT2) {
+        Product2Args a;
+        a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = h->tile_rec.as<double>();
+        a.g = g; a.d = d; a.nstat = nstat; a.est = est; a.t_begin = t0; a.t_end = t1;
+        void* kargs[] = {&a};
+        GSA_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, h->stream));
+    }
     else if (kind == PLAN_PRODUCT) {
         ProductArgs a;
         a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = h->tile_rec.as<double>();
@@ -262,7 +299,7 @@ inline int FusedPlan::prepare(gsa_handle* h, const double* params, int np_) {
         pa = params[0];
         pb = params[1];
     }
-    if ((kind == PLAN_PRODUCT || kind == PLAN_SMALL_SOBOLG) && h->aux_kind != PLAN_PRODUCT) {
+    if ((kind == PLAN_PRODUCT || kind == PLAN_PRODUCT2 || kind == PLAN_SMALL_SOBOLG) && h->aux_kind != PLAN_PRODUCT) {
         // (upload_params resets aux_kind whenever the parameters change)
         // g_k(x) = (|4x-2| + a_k)/(1 + a_k) = |x - 0.5| * 4/(1+a_k) + a_k/(1+a_k)
         std::vector<double> c(2 * (size_t)d);

@@ -109,7 +109,8 @@ def test_ci_properties_issue_181(ishigami_design):
 
 
 @pytest.mark.parametrize("d,N,nboot,second", [(8, 1 << 16, 1, True), (8, 50000, 7, True), (3, 1000, 1, False), (13, 4099, 3, False),
-                                               (40, 3001, 2, True), (100, 2000, 1, False), (128, 700, 1, False), (1, 999, 1, True)])
+                                               (40, 3001, 2, True), (100, 2000, 1, False), (128, 700, 1, False), (1, 999, 1, True),
+                                               (2, 5003, 1, True), (5, 30011, 3, True), (20, 20011, 2, True), (32, 7001, 1, True), (33, 3001, 1, True)])
 def test_sobol_g(d, N, nboot, second):
     a = np.array(([0.0, 1.0, 4.5, 9.0] + [99.0] * d)[:d])
     A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
@@ -293,6 +294,17 @@ def test_analyze_y_large_d(second, d):
         ref = gsa_ref.analyze_y(Y, d, N // nboot, order=order, nboot=nboot, Ei_estimator=est)
         res = g.gsa_sobol_all_y_analysis(g.Sobol(order=order, nboot=nboot), Y, d, N // nboot, est)
         assert_parity(res, ref, what=(est, second))
+
+
+def test_product2_kernel_small_d(monkeypatch):
+    """The lane-per-coordinate second-order kernel is only selected for 8 < d <= 32; force it on for small d too."""
+    monkeypatch.setenv("GSA_PRODUCT2", "1")
+    for d, N, nboot in ((2, 5003, 1), (3, 4099, 2), (8, 1 << 16, 3), (7, 30011, 1)):
+        a = np.array(([0.0, 1.0, 4.5, 9.0] + [99.0] * d)[:d])
+        A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+        ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, order=(0, 1, 2), nboot=nboot)
+        res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2], nboot=nboot), A, B, batch=True)
+        assert_parity(res, ref, what=(d, N, nboot))
 
 
 def test_small_kernels_match_generic(monkeypatch):
