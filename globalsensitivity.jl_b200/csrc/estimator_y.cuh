@@ -40,19 +40,23 @@ __global__ void __launch_bounds__(1024) estimator_y_kernel(EstYArgs a) {
         auto blk = [&](int b) { return base + nout * n * b; };
         double* rec = a.tile_rec + ((size_t)t * a.nout + o) * a.nstat;
 
-        dd sy{0, 0}, syy{0, 0}, sa{0, 0}, saa{0, 0};
+        ShiftSums accA, accB;   // shifted + compensated sums of fA, fA^2 and fB, fB^2
         const double *pA = blk(0), *pB = blk(1);
         for (int s = threadIdx.x; s < len; s += blockDim.x) {
             double fa = ldg_stream(pA + nout * s), fb = ldg_stream(pB + nout * s);
             sA[s] = fa; sB[s] = fb;
-            dd_add(sy, fa); dd_add(sy, fb);
-            dd_add_sq(syy, fa); dd_add_sq(syy, fb);
-            dd_add(sa, fa); dd_add_sq(saa, fa);
+            accA.add(fa);
+            accB.add(fb);
         }
         __syncthreads();
         // dd sums: warp butterfly, then warp 0 combines the warps through shared memory (reuse after sync below)
         __shared__ double sdd[32][8];
         {
+            dd sy, syy, sa, saa, sb, sbb;
+            accA.to_dd(sa, saa);
+            accB.to_dd(sb, sbb);
+            sy = sa; syy = saa;
+            dd_add_dd(sy, sb); dd_add_dd(syy, sbb);
             dd r0 = warp_sum_dd(sy), r1 = warp_sum_dd(syy), r2 = warp_sum_dd(sa), r3 = warp_sum_dd(saa);
             if (lane == 0) {
                 sdd[warp][0] = r0.hi; sdd[warp][1] = r0.lo; sdd[warp][2] = r1.hi; sdd[warp][3] = r1.lo;

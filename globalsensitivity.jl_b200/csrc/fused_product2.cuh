@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(PROD2_THREADS) fused_product2_kernel(Product2A
         double V = 0.0, E = 0.0, P[NP];
 #pragma unroll
         for (int k = 0; k < NP; ++k) P[k] = 0.0;
-        dd s1{0.0, 0.0}, s2{0.0, 0.0};   // lane 0: yA, lane 1: yB (as in fused_product.cuh)
+        ShiftSums acc;   // lane 0: yA, lane 1: yB (as in fused_product.cuh); shifted + compensated, un-shifted at the flush
 
         for (int64_t s = c0 + grp; s < c1; s += NG) {
             const size_t row = (size_t)(s - a.g.buf_col0) * d;
@@ -67,9 +67,10 @@ __global__ void __launch_bounds__(PROD2_THREADS) fused_product2_kernel(Product2A
                 const double v = __shfl_sync(gmask, yba, k, T);      // yBA_k of this sample
                 if (k < t) P[k] += v * yab - fafb;                   // :197
             }
-            const double y = t == 0 ? yA : yB;   // lanes >= 2 accumulate a copy that is never used
-            dd_add(s1, y); dd_add_sq(s2, y);
+            acc.add(t == 0 ? yA : yB);   // lanes >= 2 accumulate a copy that is never used
         }
+        dd s1, s2;
+        acc.to_dd(s1, s2);
         // ---- flush: over the groups of the warp (xor offsets >= T keep t), then over warps in order ----
 #pragma unroll
         for (int o = T; o < 32; o <<= 1) {

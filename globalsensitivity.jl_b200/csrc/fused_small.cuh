@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) small_kernel(SmallArgs<Src> a) 
         double acc[NACC];
 #pragma unroll
         for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-        dd sy{0, 0}, syy{0, 0}, sa{0, 0}, saa{0, 0};
+        ShiftSums accA, accB;   // running sums of yA, yA^2 and yB, yB^2 (shifted + compensated; un-shifted exactly at the flush)
 
         auto issue = [&](int64_t col, int stage) {
             if (col < c1) {
@@ -271,9 +271,8 @@ __global__ void __launch_bounds__(SMALL_THREADS) small_kernel(SmallArgs<Src> a) 
                 a.src.load(col, y);
             }
             const double fa = y[0], fb = y[1];
-            dd_add(sy, fa); dd_add(sy, fb);
-            dd_add_sq(syy, fa); dd_add_sq(syy, fb);
-            dd_add(sa, fa); dd_add_sq(saa, fa);
+            accA.add(fa);
+            accB.add(fb);
 #pragma unroll
             for (int k = 0; k < D; ++k) {
                 const double fab = y[2 + k];
@@ -304,6 +303,11 @@ __global__ void __launch_bounds__(SMALL_THREADS) small_kernel(SmallArgs<Src> a) 
         // ---- tile flush ----
         double* rec = a.tile_rec + ((size_t)tile * a.nout + o) * a.nstat;
         {
+            dd sy, syy, sa, saa, sb, sbb;
+            accA.to_dd(sa, saa);
+            accB.to_dd(sb, sbb);
+            sy = sa; syy = saa;
+            dd_add_dd(sy, sb); dd_add_dd(syy, sbb);
             dd r0 = warp_sum_dd(sy), r1 = warp_sum_dd(syy), r2 = warp_sum_dd(sa), r3 = warp_sum_dd(saa);
             if (lane == 0) {
                 sdd[warp][0] = r0.hi; sdd[warp][1] = r0.lo; sdd[warp][2] = r1.hi; sdd[warp][3] = r1.lo;

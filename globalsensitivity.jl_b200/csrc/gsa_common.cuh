@@ -104,6 +104,51 @@ __host__ __device__ inline void dd_add_dd(dd& acc, dd b) {
     acc = quick_two_sum(s.hi, s.lo);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Shifted, compensated running sums of y and y^2 for ONE thread: sum (y - c) and sum (y - c)^2 with c = the thread's first
+// value, each Kahan-compensated (10 flops per value instead of the 24 of dd_add + dd_add_sq).  Because the sums are taken
+// about a value of the data itself they do not suffer from mean^2 >> var; to_dd() then un-shifts them EXACTLY (double-double)
+// into sum y and sum y^2, so everything downstream (tile / replicate / rank reductions, finalize) is unchanged.
+// ------------------------------------------------------------------------------------------------
+struct ShiftSums {
+    double c = 0.0, s = 0.0, sc = 0.0, q = 0.0, qc = 0.0;
+    int n = 0;
+    __host__ __device__ inline void add(double y) {
+        c = n == 0 ? y : c;
+        ++n;
+        const double t = y - c;
+        double v = t - sc, w = s + v;
+        sc = (w - s) - v;
+        s = w;
+        v = t * t - qc;
+        w = q + v;
+        qc = (w - q) - v;
+        q = w;
+    }
+    // S = sum y = s' + n c ;  Q = sum y^2 = q' + 2 c s' + n c^2     (s' = s - sc, q' = q - qc)
+    __host__ __device__ inline void to_dd(dd& S, dd& Q) const {
+#ifdef __CUDA_ARCH__
+#define GSA_FMA(a, b, c_) __fma_rn(a, b, c_)
+#else
+#define GSA_FMA(a, b, c_) __builtin_fma(a, b, c_)
+#endif
+        const dd sp = quick_two_sum(s, -sc), qp = quick_two_sum(q, -qc);
+        const double dn = (double)n;
+        double p = dn * c, e = GSA_FMA(dn, c, -p);          // n*c exactly
+        S = sp;
+        dd_add_dd(S, dd{p, e});
+        double c2 = c * c, c2e = GSA_FMA(c, c, -c2);        // c^2 exactly
+        double m1 = dn * c2, m1e = GSA_FMA(dn, c2, -m1);    // n*c^2 (hi part) ...
+        m1e = GSA_FMA(dn, c2e, m1e);                        // ... plus n * (low part of c^2)
+        double m2 = 2.0 * c * sp.hi, m2e = GSA_FMA(2.0 * c, sp.hi, -m2);
+        m2e = GSA_FMA(2.0 * c, sp.lo, m2e);
+        Q = qp;
+        dd_add_dd(Q, quick_two_sum(m1, m1e));
+        dd_add_dd(Q, quick_two_sum(m2, m2e));
+#undef GSA_FMA
+    }
+};
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------
 // warp / block reductions in a FIXED order (xor butterflies), for run-to-run reproducibility

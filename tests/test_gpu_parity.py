@@ -596,3 +596,19 @@ def test_analyze_y_mid_d_first_order(d):
         ref = gsa_ref.analyze_y(Y, d, N // nboot, nboot=nboot, Ei_estimator=est)
         res = g.gsa_sobol_all_y_analysis(g.Sobol(nboot=nboot), Y, d, N // nboot, est)
         assert_parity(res, ref, what=(d, est))
+
+
+@pytest.mark.parametrize("d,second", [(4, True), (6, False), (30, False)])
+def test_variance_robust_when_mean_dominates(d, second):
+    """mean^2 / var ~ 1e16: a one-pass variance in plain fp64 would return noise; the kernels' shifted, compensated sums
+    (un-shifted exactly in double-double) must reproduce the reference's two-pass var (:183).  ST (Jansen) isolates Var."""
+    N, nboot = 40000, 2
+    a = np.linspace(0.0, 9.0, d)
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    order = (0, 1, 2) if second else (0, 1)
+    P = gsa_ref.all_points(A, B, nboot, second)
+    Y = 1.0e5 + 1.0e-3 * gsa_ref.model_batch("sobol_g", a, P)
+    ref = gsa_ref.analyze_y(Y, d, N // nboot, order=order, nboot=nboot)
+    res = g.gsa_sobol_all_y_analysis(g.Sobol(order=order, nboot=nboot), Y, d, N // nboot)
+    assert parity_err(res.ST, ref.ST) < 1e-10, parity_err(res.ST, ref.ST)
+    assert parity_err(res.ST_Conf_Int, ref.ST_Conf_Int) < 1e-10
