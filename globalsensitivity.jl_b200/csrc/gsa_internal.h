@@ -64,7 +64,6 @@ struct gsa_handle {
     int aux_kind = -1;                  // what h->aux holds for params_cache (plan kind), -1 = nothing
     std::vector<uint32_t> vhost;  // cached direction numbers [vdims][32]
     int vdims = 0;
-    float last_ms = 0.f;
     bool kernel_timed = false;   // evk0/evk1 bracket the dominant kernel of the last call
     int last_launches = 0;
 };
