@@ -612,3 +612,20 @@ def test_variance_robust_when_mean_dominates(d, second):
     res = g.gsa_sobol_all_y_analysis(g.Sobol(order=order, nboot=nboot), Y, d, N // nboot)
     assert parity_err(res.ST, ref.ST) < 1e-10, parity_err(res.ST, ref.ST)
     assert parity_err(res.ST_Conf_Int, ref.ST_Conf_Int) < 1e-10
+
+
+def test_empty_and_degenerate_inputs():
+    """Empty designs and one-column designs do not crash: the reference returns NaN (0/0) there, and so do we."""
+    ishi = g.DeviceModel("ishigami", [7.0, 0.1])
+    A = np.zeros((3, 0), order="F")
+    res = g.gsa(ishi, g.Sobol(order=[0, 1, 2]), A, A.copy(order="F"), batch=True)
+    assert res.S1.shape == (3,) and np.all(np.isnan(res.S1)) and res.S2.shape == (3, 3)
+    A, B = gsa_ref.sobol_design(1, -np.pi * np.ones(3), np.pi * np.ones(3))
+    res = g.gsa(ishi, g.Sobol(), A, B, batch=True)
+    assert np.all(np.isnan(res.S1)) or np.all(np.isinf(res.S1))          # Var of two values / zero spread: not finite
+    res = g.gsa_sobol_all_y_analysis(g.Sobol(), np.zeros(0), 3, 0)
+    assert np.all(np.isnan(res.S1))
+    W = np.ones((2, 3))
+    res = g.gsa(g.DeviceModel("linear", W), g.Sobol(), np.zeros((3, 0), order="F"), np.zeros((3, 0), order="F"), batch=True)
+    assert res.S1.shape == (2, 3) and np.all(np.isnan(res.S1))
+    assert g.generate_design_matrices(1, np.zeros(2), np.ones(2))[0].shape == (2, 1)
