@@ -31,7 +31,9 @@ struct FusedPlan {
     uint64_t gen_first = 0;
     int gen_nboot = 1, gen_unit_box = 0;
     double pa = 0.0, pb = 0.0;   // Ishigami parameters (small kernel)
-    int lin_DP = 0;              // padded d+1 of the linear (Gram) kernel
+    int lin_NB = 0;              // 8-coordinate blocks of the stacked [a; b] vector (linear Gram kernel)
+    bool writes_partials() const { return kind == PLAN_LINEAR; }   // the plan adds its records to `out_partials` itself
+    double* out_partials = nullptr;
 
     int prepare(gsa_handle* h, const double* params, int np);
     int launch(gsa_handle* h, const double* A, const double* B, const TileGeom& g, int t0, int t1);
@@ -164,27 +166,25 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
     if (gen)
         return fail(GSA_ERR_UNSUPPORTED, "fused design generation is implemented for product-form models (sobol_g), S1/ST, Jansen1999, d <= 416; "
                                          "use gsa_sobol_design + gsa_sobol_run for this request");
-    if (!generic_only && model == GSA_MODEL_LINEAR && !second && est == GSA_EI_JANSEN1999 && d + 1 <= LIN_DPMAX) {
+    if (!generic_only && model == GSA_MODEL_LINEAR && !second && est == GSA_EI_JANSEN1999 && d <= LIN_DMAX) {
         p->kind = PLAN_LINEAR;
-        p->lin_DP = (d + 1 + 7) / 8 * 8;
         p->threads = LIN_THREADS;
-        const int NB = p->lin_DP / 8, NBD = (d + 7) / 8, np_ = lin_num_pairs(NB, NBD);
-        int lps = 4;
-        while (lps < np_) lps <<= 1;
-        p->lin_smem = lin_smem_bytes(NB, d);
+        const int NB = (2 * d + 7) / 8;
+        int un = NB <= 3 ? 4 : 2;            // NB = 5 (d = 20): 164 registers with 2 steps per group, spills with 4
+        if (const char* e = getenv("GSA_LIN_UN")) un = (atoi(e) == 4 && NB <= 5) ? 4 : 2;   // tuning knob: warp steps per load group
         const void* kern = nullptr;
-#define GSA_LIN_CASE(NBV, LPSV) if (NB == NBV && lps == LPSV) kern = (const void*)linear_gram_kernel<NBV, LPSV>;
-        GSA_LIN_CASE(1, 4) GSA_LIN_CASE(2, 16) GSA_LIN_CASE(3, 32) GSA_LIN_CASE(4, 64)
-        GSA_LIN_CASE(2, 8) GSA_LIN_CASE(3, 16) GSA_LIN_CASE(4, 32)     // d = 8 / 16 / 24: the delta vector has one block fewer
+#define GSA_LIN_CASE(NBV) if (NB == NBV) kern = un == 4 ? (const void*)linear_gram_kernel<NBV, (NBV <= 5 ? 4 : 2)> : (const void*)linear_gram_kernel<NBV, 2>;
+        GSA_LIN_CASE(1) GSA_LIN_CASE(2) GSA_LIN_CASE(3) GSA_LIN_CASE(4) GSA_LIN_CASE(5) GSA_LIN_CASE(6) GSA_LIN_CASE(7) GSA_LIN_CASE(8)
 #undef GSA_LIN_CASE
-        if (!kern) return fail(GSA_ERR_UNSUPPORTED, "linear kernel: no instantiation for %d blocks / %d pairs", NB, np_);
-        if (p->lin_smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lin_smem));
+        if (!kern) return fail(GSA_ERR_UNSUPPORTED, "linear kernel: no instantiation for %d blocks", NB);
+        p->lin_NB = NB;
+        p->lin_smem = sizeof(double) * (64 * (size_t)NB * NB + 8 * NB);
         int nbl = 0;
         GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbl, kern, LIN_THREADS, p->lin_smem));
         p->lin_kernel = kern;
         p->resident = h->sm_count * std::max(1, nbl);
-        p->tiles_per_cta = 1;               // few, large tiles: every tile costs one moments->records conversion per output
-        p->ts_min = p->ts_gran = LIN_S;
+        p->tiles_per_cta = 1;               // few, large tiles: every tile ends with a cross-warp combine and a moments write-out
+        p->ts_min = p->ts_gran = 4 * un * LIN_NW;
         return GSA_OK;
     }
     {
@@ -251,25 +251,24 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
     else if (kind == PLAN_SMALL_SOBOLG)
         return launch_small_sobolg(h, d, second, est, A, B, h->aux.as<double2>(), g, t0, t1, nstat, h->tile_rec.as<double>());
     else if (kind == PLAN_LINEAR) {
-        const int gs = lin_gram_size(lin_DP);
-        int rc = h->gram.reserve(sizeof(double) * (size_t)g.ntiles * gs);
+        // moments per tile -> moments per replicate of this launch -> records added to `partials` (no tile records, no stage 2)
+        const int gs = lin_gram_size(lin_NB);
+        const int rl0 = t0 / g.tpr, nrl = (t1 - 1) / g.tpr - rl0 + 1;
+        int rc = h->gram.reserve(sizeof(double) * ((size_t)g.ntiles + g.ntiles / g.tpr) * gs);
         if (rc) return rc;
+        double* red = h->gram.as<double>() + (size_t)g.ntiles * gs;
         LinearArgs a;
         a.A = A; a.B = B; a.gram = h->gram.as<double>(); a.g = g; a.d = d; a.t_begin = t0; a.t_end = t1;
-        const int grid_l = std::min(t1 - t0, resident);
-        const void* kern = lin_kernel;
-        const size_t smem_l = lin_smem;
         void* kargs[] = {&a};
-        GSA_CUDA(cudaLaunchKernel(kern, dim3(grid_l), dim3(LIN_THREADS), kargs, smem_l, h->stream));
+        GSA_CUDA(cudaLaunchKernel(lin_kernel, dim3(grid), dim3(LIN_THREADS), kargs, lin_smem, h->stream));
         GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
         h->kernel_timed = true;
-        h->last_launches++;
-        GSA_CUDA(cudaGetLastError());
+        linear_gram_reduce_kernel<<<dim3((gs + LGR_X - 1) / LGR_X, nrl), dim3(LGR_X, LGR_Y), 0, h->stream>>>(a.gram, red, gs, g.tpr, t0, t1, rl0);
         LinearRecArgs r;
-        r.gram = h->gram.as<double>(); r.W = h->params.as<double>(); r.tile_rec = h->tile_rec.as<double>();
-        r.d = d; r.DP = lin_DP; r.nout = nout; r.nstat = nstat; r.t_begin = t0; r.t_end = t1;
-        linear_records_kernel<<<t1 - t0, 256, sizeof(double) * gs, h->stream>>>(r);
-        h->last_launches++;
+        r.red = red; r.A = A; r.W = h->params.as<double>(); r.partials = out_partials;
+        r.g = g; r.d = d; r.NB = lin_NB; r.nout = nout; r.nstat = nstat; r.rl_first = rl0;
+        linear_records_kernel<<<nrl, 256, sizeof(double) * (2 * (size_t)d * d + 4 * d), h->stream>>>(r);
+        h->last_launches += 3;
         GSA_CUDA(cudaGetLastError());
         return GSA_OK;
     }

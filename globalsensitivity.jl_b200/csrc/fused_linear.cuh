@@ -1,221 +1,212 @@
 // fused_linear.cuh -- K2+K3 for LINEAR multi-output models  y = W x  (BASELINE config 4: d = 20, 256 outputs), S1/ST.
 //
 // For a linear model every quantity the estimators need is a quadratic form of INPUT moments, so the kernel never
-// evaluates the nout outputs per sample.  With a = A_s - c, b = B_s - c (c = first row of the tile, a numerical
-// shift only), delta = b - a and w = W[o, :]:
-//     yA = y0 + w.a,  yB = y0 + w.b,  y0 = w.c,      yAB_k - yA = W_ok * delta_k            (rank-1 update)
-//     sum (yA-y0)^2 + (yB-y0)^2   = w' G w,          G  = sum a a' + b b'                    -> Var   (:183)
-//     sum yB (yAB_k - yA)         = W_ok (y0 sum delta_k + sum_l w_l H[l][k]),  H = sum b delta'   -> V_k   (:192)
-//     sum (yA - yAB_k)^2          = W_ok^2 D[k],     D  = sum delta_k^2                      -> E_k   (:213)
-// Cost per sample: O(d^2) FMAs, independent of nout (the reference's path is O(d * nout * (d+2))): the 189 GB
-// `all_y` of config 4 is never formed, and neither is any per-output intermediate.
+// evaluates the nout outputs per sample.  With a = A_s - c, b = B_s - c (c = the first row of the replicate that this
+// launch sees: a numerical shift only), u = [a; b] (2d coordinates) and w = W[o, :]:
+//     yA = y0 + w.a,  yB = y0 + w.b,  y0 = w.c,      yAB_k - yA = W_ok (b_k - a_k)            (rank-1 update)
+//     sum (yA-y0)^2 + (yB-y0)^2   = w' (Uaa + Ubb) w                                          -> Var   (:183)
+//     sum yB (yAB_k - yA)         = W_ok (y0 (sb_k - sa_k) + sum_l w_l (Ubb - Uba)[l][k])     -> V_k   (:192)
+//     sum (yA - yAB_k)^2          = W_ok^2 (Ubb - 2 Uab + Uaa)[k][k]                          -> E_k   (:213)
+// where U = sum_s u u' (the 2d x 2d Gram matrix of the stacked rows) and sa, sb the first moments.  Cost per sample:
+// O(d^2) FMAs, independent of nout (the reference's path is O(d * nout * (d+2))): the 189 GB `all_y` of config 4 is
+// never formed, and neither is any per-output intermediate.
 //
-// Kernel 1 (gram): the vectors are extended with a constant-1 coordinate at index d (first moments come out of the same
-// products) and cut into 8-double blocks; every LANE owns one 8x8 block pair -- (a,a) and (b,b) upper triangle, (b,delta),
-// (delta,delta) diagonal -- i.e. 64 register accumulators fed by 16 operands per sample (4 FMA per operand delivered from
-// shared memory; a row-per-lane layout with broadcast loads delivered 1 and ran 3.5x slower, profiles/r1_notes.md).
-// Blocks are stored with a 10-double stride so the per-lane 16-byte loads of a quarter-warp fall in distinct banks.
-// Kernel 2 (records): per (tile, output) turns the tile's moments into the library's standard sufficient-
-// statistics record (double-double sums of y and y^2 recentred exactly), so tiles, replicates and GPUs combine
-// through the same reduce / all-reduce / finalize path as every other model.
+// Kernel 1 (gram) -- the one real dense contraction of this library (U = X'X with the SAMPLES as the contraction index), so it
+// runs on the FP64 tensor-core path: `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4; tcgen05 has no FP64 kind).  tools/fp64_peak.cu
+// measured DMMA = 37.0 and DFMA = 36.6 TFLOP/s on this B200: the same peak, but a DMMA carries 256 FMAs per issue slot and takes
+// its operands from registers.  The previous DFMA version (8x8 register blocks fed from shared memory) sat at 42 % of that peak
+// on operand delivery.  u is cut into NB = ceil(2d/8) blocks of 8 coordinates; a warp step covers 4 consecutive samples: thread
+// (g = lane/4, t = lane%4) loads coordinate 8*blk+g of sample t straight from global memory (the 8 lanes of a sample read
+// 64 contiguous bytes), which is at once the A fragment (row g, k = t) and the B fragment (k = t, column g) of every block pair
+// -- no shared memory, no transposition.  NB(NB+1)/2 DMMAs per step accumulate the upper block triangle of U.  Loads of the
+// next group of steps are issued before the DMMAs of the current one.
+// Kernel 2 sums the per-tile moments of a replicate (fixed order).  Kernel 3 turns them into the library's standard sufficient-
+// statistics record per (replicate, output) -- double-double sums of y and y^2 recentred exactly -- and adds it to `partials`.
 #pragma once
 #include "gsa_common.cuh"
 
 namespace gsa {
 
-constexpr int LIN_THREADS = 128;  // ~190 registers/thread: two or three CTAs per SM overlap staging and accumulation
-constexpr int LIN_S = 48;         // samples staged per pass (tile granule)
-constexpr int LIN_DPMAX = 32;     // d + 1 <= 32
-constexpr int LIN_BS = 10;        // shared-memory stride of an 8-double block (padded: conflict-free 16-byte lane loads)
+constexpr int LIN_THREADS = 128;
+constexpr int LIN_NW = LIN_THREADS / 32;
+constexpr int LIN_DMAX = 32;      // 2d <= 64: at most 8 blocks, 36 accumulator pairs per thread
+
+// per-tile / per-replicate moments: U[DU][DU] (row-major, only block-upper-triangular entries are written), S[DU], count
+__host__ __device__ inline int lin_gram_size(int NB) { return 64 * NB * NB + 8 * NB + 8; }
 
 struct LinearArgs {
     const double* A;
     const double* B;
-    double* gram;  // [ntiles][lin_gram_size(DP)]: G (DP x DP, row-major, full), H (DP x DP), D (DP), c (DP; c[d] = #samples)
+    double* gram;   // [ntiles][lin_gram_size(NB)]
     TileGeom g;
     int d, t_begin, t_end;
 };
 
+// first global column of replicate r that this launch holds: the row used as shift for all of the replicate's tiles
+__host__ __device__ inline int64_t lin_shift_col(const TileGeom& g, int r) {
+    int64_t c = (int64_t)r * g.n;
+    if (c < g.col_lo) c = g.col_lo;
+    if (c < g.buf_col0) c = g.buf_col0;
+    return c;
+}
+
 #ifdef __CUDACC__
-__device__ __forceinline__ void cp_async8_l(double* smem_dst, const double* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async16_l(double* smem_dst, const double* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-#endif
-// dynamic shared memory of linear_gram_kernel (bytes)
-__host__ __device__ inline size_t lin_smem_bytes(int NB, int d) {
-    return sizeof(double) * ((size_t)LIN_S * 3 * NB * 10 + 8 * NB + 4 * (size_t)LIN_S * d);
-}
-__host__ __device__ inline int lin_gram_size(int DP) { return 2 * DP * DP + 2 * DP; }
-// 8x8 block pairs of the extended vectors X = [a_ext | b_ext | delta_ext] (NB blocks each):
-//   a x a and b x b upper-triangular block pairs, b x delta (all), delta x delta (diagonal blocks)
-__host__ __device__ inline int lin_num_pairs(int NB, int NBD) { return NB * (NB + 1) + NB * NBD + NBD; }
-
-// decode pair p -> (row vector, row block, col vector, col block); vectors: 0 = a, 1 = b, 2 = delta
-__host__ __device__ inline void lin_pair(int p, int NB, int NBD, int& rv, int& rb, int& cv, int& cb) {
-    const int tri = NB * (NB + 1) / 2;
-    if (p < 2 * tri) {
-        rv = cv = p / tri;
-        int q = p % tri;
-        rb = 0;
-        while (q >= NB - rb) { q -= NB - rb; ++rb; }
-        cb = rb + q;
-    } else if (p < 2 * tri + NB * NBD) {
-        const int q = p - 2 * tri;
-        rv = 1; rb = q / NBD; cv = 2; cb = q % NBD;
-    } else {
-        rv = cv = 2;
-        rb = cb = p - 2 * tri - NB * NBD;
-    }
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// NB = number of 8-blocks of the extended (d+1)-vector; LPS = lanes per sample (power of two >= number of pairs)
-template <int NB, int LPS>
+// NB = blocks of the stacked vector; UN = warp steps (of 4 samples) per load group
+template <int NB, int UN>
 __global__ void __launch_bounds__(LIN_THREADS) linear_gram_kernel(LinearArgs a) {
-    constexpr int DP = 8 * NB;
-    constexpr int REC = 3 * NB * LIN_BS;            // doubles per staged sample
-    constexpr int SPW = LPS >= 32 ? 1 : 32 / LPS;   // samples per warp step
-    constexpr int WPS = LPS >= 32 ? LPS / 32 : 1;   // warps per sample
-    constexpr int NW = LIN_THREADS / 32;
-    constexpr int SLOTS = NW * SPW / WPS;           // samples processed concurrently by the CTA
-    extern __shared__ __align__(16) double lin_sm[];
-    double* stage = lin_sm;                          // [LIN_S][REC]   shifted / differenced, block-padded records
-    double* cshift = lin_sm + LIN_S * REC;           // [DP]
-    double* raw = cshift + DP;                       // [2][2][LIN_S * d]  raw A and B rows of the next pass (cp.async ring)
-    const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rawsz = LIN_S * d;
-    const int NBD = (d + 7) / 8, npairs = lin_num_pairs(NB, NBD);
-    // this lane's pair and sample slot
-    const int pair = LPS >= 32 ? (warp % WPS) * 32 + lane : lane % LPS;
-    const int slot = LPS >= 32 ? warp / WPS : warp * SPW + lane / LPS;
-    const bool active = pair < npairs;
-    int rv = 0, rb = 0, cv = 0, cb = 0;
-    if (active) lin_pair(pair, NB, NBD, rv, rb, cv, cb);
-    const int roff = (rv * NB + rb) * LIN_BS, coff = (cv * NB + cb) * LIN_BS;
+    constexpr int DU = 8 * NB, NP = NB * (NB + 1) / 2, GS = 64 * NB * NB + 8 * NB + 8;
+    extern __shared__ __align__(16) double lin_sm[];   // U[DU*DU], S[DU]
+    const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g8 = lane >> 2, t4 = lane & 3;
+    // this thread's coordinate of every block: offset inside a row of A (i < d) or of B (d <= i < 2d)
+    const double* src[NB];
+    bool ok[NB];
+    int coff[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        const int i = 8 * k + g8;
+        ok[k] = i < 2 * d;
+        coff[k] = i < d ? i : i - d;
+        src[k] = (i < d ? a.A : a.B) + (ok[k] ? coff[k] : 0);
+    }
 
     for (int tile = a.t_begin + blockIdx.x; tile < a.t_end; tile += gridDim.x) {
         int64_t c0, c1;
         tile_range(a.g, tile, c0, c1);
-        double* out = a.gram + (size_t)tile * lin_gram_size(DP);
+        double* out = a.gram + (size_t)tile * GS;
         if (c1 <= c0) {
-            for (int i = threadIdx.x; i < lin_gram_size(DP); i += LIN_THREADS) out[i] = 0.0;
+            for (int i = threadIdx.x; i < GS; i += LIN_THREADS) out[i] = 0.0;
             continue;
         }
-        if (threadIdx.x < DP) cshift[threadIdx.x] = threadIdx.x < d ? __ldg(a.A + (size_t)(c0 - a.g.buf_col0) * d + threadIdx.x) : 0.0;
-        double acc[64];
+        const int64_t cs = lin_shift_col(a.g, a.g.rep_first + tile / a.g.tpr);
+        double sh[NB], s1[NB], acc[NP][2];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) acc[i] = 0.0;
+        for (int k = 0; k < NB; ++k) {
+            sh[k] = ok[k] ? __ldg(a.A + (size_t)(cs - a.g.buf_col0) * d + coff[k]) : 0.0;
+            s1[k] = 0.0;
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) acc[p][0] = acc[p][1] = 0.0;
 
-        // asynchronous copy of the raw rows of one pass (contiguous ns*d doubles of A and of B) into ring slot `buf`
-        auto prefetch = [&](int64_t p0, int buf) {
-            if (p0 < c1) {
-                const int cnt = (int)min((int64_t)LIN_S, c1 - p0) * d;
-                const double* ga = a.A + (size_t)(p0 - a.g.buf_col0) * d;
-                const double* gb = a.B + (size_t)(p0 - a.g.buf_col0) * d;
-                double* ra = raw + (size_t)buf * 2 * rawsz;
-                double* rbuf = ra + rawsz;
-                const bool al16 = ((reinterpret_cast<uintptr_t>(ga) | reinterpret_cast<uintptr_t>(gb)) & 15) == 0 && (rawsz % 2 == 0);
-                if (al16) {
-                    for (int e = 2 * threadIdx.x; e < cnt; e += 2 * LIN_THREADS) {
-                        if (e + 1 < cnt) { cp_async16_l(ra + e, ga + e); cp_async16_l(rbuf + e, gb + e); }
-                        else { cp_async8_l(ra + e, ga + e); cp_async8_l(rbuf + e, gb + e); }
-                    }
-                } else {
-                    for (int e = threadIdx.x; e < cnt; e += LIN_THREADS) { cp_async8_l(ra + e, ga + e); cp_async8_l(rbuf + e, gb + e); }
-                }
+        const int64_t cnt = c1 - c0, row0 = c0 - a.g.buf_col0;
+        const int64_t ngroups = (cnt + 4 * UN - 1) / (4 * UN);
+        // group G = steps [G*UN, (G+1)*UN), step q = samples [4q, 4q+4) of the tile; the warps take groups round-robin
+        auto load = [&](double (&v)[UN][NB], int64_t G) {
+            const int64_t s0 = G * (4 * UN) + t4;
+            if ((G + 1) * (4 * UN) <= cnt) {
+#pragma unroll
+                for (int j = 0; j < UN; ++j)
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) v[j][k] = ok[k] ? ldg_stream(src[k] + (size_t)(row0 + s0 + 4 * j) * d) : 0.0;
+#pragma unroll
+                for (int j = 0; j < UN; ++j)
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) v[j][k] -= sh[k];
+            } else {
+#pragma unroll
+                for (int j = 0; j < UN; ++j)
+#pragma unroll
+                    for (int k = 0; k < NB; ++k)
+                        v[j][k] = (ok[k] && s0 + 4 * j < cnt) ? ldg_stream(src[k] + (size_t)(row0 + s0 + 4 * j) * d) - sh[k] : 0.0;
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        prefetch(c0, 0);
-        int buf = 0;
-        for (int64_t p0 = c0; p0 < c1; p0 += LIN_S, buf ^= 1) {
-            const int ns = (int)min((int64_t)LIN_S, c1 - p0);
-            prefetch(p0 + LIN_S, buf ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            __syncthreads();   // every thread's copies of this pass are visible; the previous accumulate is finished
-            // ---- transform: raw rows -> shifted / differenced, block-padded records ----
-            const double* ra = raw + (size_t)buf * 2 * rawsz;
-            const double* rbuf = ra + rawsz;
-            for (int e = threadIdx.x; e < ns * DP; e += LIN_THREADS) {
-                const int s = e / DP, k = e - s * DP;
-                double va = 0.0, vb = 0.0, vd = 0.0;
-                if (k < d) {
-                    const double xa = ra[s * d + k], xb = rbuf[s * d + k], c = cshift[k];
-                    va = xa - c;
-                    vb = xb - c;
-                    vd = xb - xa;
-                } else if (k == d) {
-                    va = vb = 1.0;  // constant coordinate: row/column d of G and H carry the first moments
-                }
-                double* r = stage + s * REC + (k >> 3) * LIN_BS + (k & 7);
-                r[0] = va;
-                r[NB * LIN_BS] = vb;
-                r[2 * NB * LIN_BS] = vd;
+        auto accumulate = [&](const double (&v)[UN][NB]) {
+#pragma unroll
+            for (int j = 0; j < UN; ++j) {
+                int p = 0;
+#pragma unroll
+                for (int rb = 0; rb < NB; ++rb)
+#pragma unroll
+                    for (int cb = rb; cb < NB; ++cb, ++p) dmma_8x8x4(acc[p][0], acc[p][1], v[j][rb], v[j][cb]);
+#pragma unroll
+                for (int k = 0; k < NB; ++k) s1[k] += v[j][k];
             }
-            __syncthreads();
-            // ---- accumulate: every lane adds the 8x8 outer product of its (row block, column block) ----
-            for (int s = slot; s < ns; s += SLOTS) {
-                if (active) {
-                    const double* r = stage + s * REC;
-                    double rr[8], cc[8];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double2 x = *reinterpret_cast<const double2*>(r + roff + 2 * j);
-                        const double2 y = *reinterpret_cast<const double2*>(r + coff + 2 * j);
-                        rr[2 * j] = x.x; rr[2 * j + 1] = x.y; cc[2 * j] = y.x; cc[2 * j + 1] = y.y;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[8 * i + j] = fma(rr[i], cc[j], acc[8 * i + j]);
-                }
-            }
+        };
+        double v0[UN][NB], v1[UN][NB];
+        int64_t G = warp;
+        if (G < ngroups) load(v0, G);
+        while (G < ngroups) {
+            if (G + LIN_NW < ngroups) load(v1, G + LIN_NW);
+            accumulate(v0);
+            G += LIN_NW;
+            if (G >= ngroups) break;
+            if (G + LIN_NW < ngroups) load(v0, G + LIN_NW);
+            accumulate(v1);
+            G += LIN_NW;
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+        // ---- combine the warps in a fixed order (shared memory), write the tile's moments ----
+        double* U = lin_sm;
+        double* S = lin_sm + DU * DU;
+        __syncthreads();   // the previous tile's write-out has finished reading lin_sm
+        for (int i = threadIdx.x; i < DU * DU + DU; i += LIN_THREADS) lin_sm[i] = 0.0;
         __syncthreads();
-        // ---- combine: dense G (a x a + b x b, both triangles), H, D in shared memory; sample slots take turns (fixed order) ----
-        double* G = stage;               // [DP][DP]
-        double* H = stage + DP * DP;     // [DP][DP]
-        double* Dv = H + DP * DP;        // [DP]
-        static_assert(2 * DP * DP + DP <= LIN_S * REC, "staging buffer too small for the combine");
-        for (int i = threadIdx.x; i < 2 * DP * DP + DP; i += LIN_THREADS) stage[i] = 0.0;
-        __syncthreads();
-        for (int turn = 0; turn < SLOTS * 2; ++turn) {
-            // a x a pairs and b x b pairs hit the same G entries: give them separate turns (rv = 0 first, then the rest)
-            const int tslot = turn >> 1, phase = turn & 1;
-            if (active && slot == tslot && ((rv == 0) == (phase == 0))) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+        for (int k = 0; k < NB; ++k) {   // first moments: sum over the 4 sample lanes of a coordinate
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 1);
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 2);
+        }
+        for (int w = 0; w < LIN_NW; ++w) {
+            if (warp == w) {
+                int p = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int l = 8 * rb + i, k = 8 * cb + j;
-                        const double v = acc[8 * i + j];
-                        if (rv == cv && rv < 2) {
-                            G[l * DP + k] += v;
-                            if (rb != cb) G[k * DP + l] += v;   // mirror the off-diagonal blocks
-                        } else if (rv == 1) {
-                            H[l * DP + k] += v;
-                        } else if (i == j) {
-                            Dv[k] += v;
-                        }
+                for (int rb = 0; rb < NB; ++rb)
+#pragma unroll
+                    for (int cb = rb; cb < NB; ++cb, ++p) {
+                        double* e = U + (8 * rb + g8) * DU + 8 * cb + 2 * t4;   // C fragment: row g, columns 2t, 2t+1
+                        e[0] += acc[p][0];
+                        e[1] += acc[p][1];
                     }
+                if (t4 == 0) {
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) S[8 * k + g8] += s1[k];
+                }
             }
             __syncthreads();
         }
-        for (int i = threadIdx.x; i < 2 * DP * DP + DP; i += LIN_THREADS) out[i] = stage[i];
-        if (threadIdx.x < DP) out[2 * DP * DP + DP + threadIdx.x] = threadIdx.x < d ? cshift[threadIdx.x] : (threadIdx.x == d ? (double)(c1 - c0) : 0.0);
-        __syncthreads();
+        for (int i = threadIdx.x; i < DU * DU + DU; i += LIN_THREADS) out[i] = lin_sm[i];
+        if (threadIdx.x < 8) out[DU * DU + DU + threadIdx.x] = threadIdx.x == 0 ? (double)cnt : 0.0;
     }
 }
 
-// moments of a tile -> standard record of output o.  One thread per output.
+// moments of the tiles [t_begin, t_end) of each replicate -> one moment set per replicate of the launch (fixed order)
+constexpr int LGR_X = 64, LGR_Y = 16;
+__global__ void __launch_bounds__(LGR_X* LGR_Y) linear_gram_reduce_kernel(const double* __restrict__ gram, double* __restrict__ red, int gs, int tpr,
+                                                                         int t_begin, int t_end, int rl_first) {
+    __shared__ double sh[LGR_Y][LGR_X];
+    const int i = blockIdx.x * LGR_X + threadIdx.x, rl = rl_first + blockIdx.y;
+    const int j0 = max(t_begin, rl * tpr), j1 = min(t_end, (rl + 1) * tpr);
+    double s = 0.0;
+    if (i < gs) {
+        int j = j0 + threadIdx.y;
+        for (; j + 3 * LGR_Y < j1; j += 4 * LGR_Y) {
+            const double v0 = gram[(size_t)j * gs + i], v1 = gram[(size_t)(j + LGR_Y) * gs + i];
+            const double v2 = gram[(size_t)(j + 2 * LGR_Y) * gs + i], v3 = gram[(size_t)(j + 3 * LGR_Y) * gs + i];
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; j < j1; j += LGR_Y) s += gram[(size_t)j * gs + i];
+    }
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < gs) {
+        double t = 0.0;
+        for (int y = 0; y < LGR_Y; ++y) t += sh[y][threadIdx.x];
+        red[(size_t)blockIdx.y * gs + i] = t;
+    }
+}
+
+// moments of a replicate -> standard record of every output, ADDED to partials[replicate][output].  One CTA per replicate of the
+// launch, one thread per output.  Launches are serialised on the handle's stream, so the read-modify-write is race-free.
 struct LinearRecArgs {
-    const double* gram;
-    const double* W;   // nout x d column-major
-    double* tile_rec;  // [ntiles][nout][nstat]
-    int d, DP, nout, nstat, t_begin, t_end;
+    const double* red;   // [nrep_launch][gs]
+    const double* A;     // the launch's A buffer (shift rows)
+    const double* W;     // nout x d column-major
+    double* partials;    // [nboot][nout][nstat]
+    TileGeom g;
+    int d, NB, nout, nstat, rl_first;
 };
 
 __device__ __forceinline__ dd dd_from(double x) { return dd{x, 0.0}; }
@@ -227,50 +218,68 @@ __device__ __forceinline__ dd dd_mul_d(dd a, double b) {  // a * b
 }
 
 __global__ void __launch_bounds__(256) linear_records_kernel(LinearRecArgs a) {
-    extern __shared__ double sg[];  // the tile's moments
-    const int d = a.d, DP = a.DP, gs = lin_gram_size(DP);
-    for (int tile = a.t_begin + blockIdx.x; tile < a.t_end; tile += gridDim.x) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < gs; i += blockDim.x) sg[i] = a.gram[(size_t)tile * gs + i];
-        __syncthreads();
-        const double* G = sg;
-        const double* H = sg + DP * DP;
-        const double* D = sg + 2 * DP * DP;
-        const double* c = D + DP;
-        const double m = c[d];  // samples in the tile
-        for (int o = threadIdx.x; o < a.nout; o += blockDim.x) {
-            double* rec = a.tile_rec + ((size_t)tile * a.nout + o) * a.nstat;
-            for (int i = 0; i < a.nstat; ++i) rec[i] = 0.0;
-            if (m == 0.0) continue;
-            double w[LIN_DPMAX];                           // this output's row of W (coalesced loads across outputs)
-            for (int l = 0; l < d; ++l) w[l] = __ldg(a.W + o + (size_t)a.nout * l);
-            // y0 = w.c ; S' = sum_l w_l G[l][d] ; Q' = w' G w (l,k < d)
-            double y0 = 0.0, S1 = 0.0, Q = 0.0;
-            for (int l = 0; l < d; ++l) {
-                const double wl = w[l];
-                y0 = fma(wl, c[l], y0);
-                S1 = fma(wl, G[l * DP + d], S1);
-                double row = 0.0;
-                for (int k = 0; k < d; ++k) row = fma(w[k], G[l * DP + k], row);
-                Q = fma(wl, row, Q);
-            }
-            // un-shift exactly: sum y = S' + 2m y0 ; sum y^2 = Q' + 2 y0 S' + 2m y0^2   (double-double)
-            dd sy = dd_from(S1);
-            dd_add_dd(sy, dd_mul_d(dd_from(2.0 * m), y0));
-            dd t = dd_mul_d(dd_from(y0), y0);              // y0^2
-            dd syy = dd_from(Q);
-            dd_add_dd(syy, dd_mul_d(dd_mul_d(dd_from(2.0 * y0), S1), 1.0));
-            dd_add_dd(syy, dd_mul_d(t, 2.0 * m));
-            rec[0] = sy.hi; rec[1] = sy.lo; rec[2] = syy.hi; rec[3] = syy.lo;
-            for (int k = 0; k < d; ++k) {
-                const double wk = w[k];
-                double hv = y0 * H[d * DP + k];            // y0 * sum delta_k   (row d of H: b_ext[d] = 1)
-                for (int l = 0; l < d; ++l) hv = fma(w[l], H[l * DP + k], hv);
-                rec[stat_v(k)] = wk * hv;                  // sum yB (yAB_k - yA)       (:192)
-                rec[stat_e(d, 0, k)] = wk * wk * D[k];     // sum (yA - yAB_k)^2        (:213)
-            }
+    extern __shared__ double sg[];  // G[d*d] (Uaa + Ubb), H[d*d] (Ubb - Uba), g1[d] (sa + sb), h1[d] (sb - sa), D[d], c[d]
+    const int d = a.d, DU = 8 * a.NB, gs = lin_gram_size(a.NB);
+    const int rl = a.rl_first + blockIdx.x, r = a.g.rep_first + rl;
+    const double* red = a.red + (size_t)blockIdx.x * gs;
+    const double* S = red + DU * DU;
+    const double m = red[DU * DU + DU];   // samples of the replicate in this launch
+    if (m == 0.0) return;
+    double* G = sg;
+    double* H = G + d * d;
+    double* g1 = H + d * d;
+    double* h1 = g1 + d;
+    double* D = h1 + d;
+    double* c = D + d;
+    // U is stored block-upper-triangular: entry (l, k) lives at [l][k] when block(l) <= block(k), else at [k][l]
+    auto Us = [&](int l, int k) { return (l >> 3) <= (k >> 3) ? red[l * DU + k] : red[k * DU + l]; };
+    const int64_t cs = lin_shift_col(a.g, r);
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+        const int l = e / d, k = e - l * d;
+        G[e] = Us(l, k) + Us(d + l, d + k);
+        H[e] = Us(d + l, d + k) - Us(d + l, k);
+    }
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+        g1[k] = S[k] + S[d + k];
+        h1[k] = S[d + k] - S[k];
+        D[k] = (Us(d + k, d + k) - 2.0 * Us(k, d + k)) + Us(k, k);
+        c[k] = __ldg(a.A + (size_t)(cs - a.g.buf_col0) * d + k);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < a.nout; o += blockDim.x) {
+        double* rec = a.partials + ((size_t)r * a.nout + o) * a.nstat;
+        double w[LIN_DMAX];                           // this output's row of W (coalesced loads across outputs)
+        for (int l = 0; l < d; ++l) w[l] = __ldg(a.W + o + (size_t)a.nout * l);
+        // y0 = w.c ; S' = w.g1 ; Q' = w' G w
+        double y0 = 0.0, S1 = 0.0, Q = 0.0;
+        for (int l = 0; l < d; ++l) {
+            const double wl = w[l];
+            y0 = fma(wl, c[l], y0);
+            S1 = fma(wl, g1[l], S1);
+            double row = 0.0;
+            for (int k = 0; k < d; ++k) row = fma(w[k], G[l * d + k], row);
+            Q = fma(wl, row, Q);
+        }
+        // un-shift exactly: sum y = S' + 2m y0 ; sum y^2 = Q' + 2 y0 S' + 2m y0^2   (double-double)
+        dd sy = dd_from(S1);
+        dd_add_dd(sy, dd_mul_d(dd_from(2.0 * m), y0));
+        dd t = dd_mul_d(dd_from(y0), y0);              // y0^2
+        dd syy = dd_from(Q);
+        dd_add_dd(syy, dd_mul_d(dd_from(2.0 * y0), S1));
+        dd_add_dd(syy, dd_mul_d(t, 2.0 * m));
+        dd p0{rec[0], rec[1]}, p1{rec[2], rec[3]};
+        dd_add_dd(p0, sy);
+        dd_add_dd(p1, syy);
+        rec[0] = p0.hi; rec[1] = p0.lo; rec[2] = p1.hi; rec[3] = p1.lo;
+        for (int k = 0; k < d; ++k) {
+            const double wk = w[k];
+            double hv = y0 * h1[k];
+            for (int l = 0; l < d; ++l) hv = fma(w[l], H[l * d + k], hv);
+            rec[stat_v(k)] += wk * hv;                  // sum yB (yAB_k - yA)       (:192)
+            rec[stat_e(d, 0, k)] += wk * wk * D[k];     // sum (yA - yAB_k)^2        (:213)
         }
     }
 }
+#endif  // __CUDACC__
 
 }  // namespace gsa

@@ -332,12 +332,14 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         }
         g.ntiles = nrep * g.tpr;
         if ((int64_t)nrep * g.tpr > (int64_t)INT32_MAX / 2) return fail(GSA_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)nrep * g.tpr);
-        if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)g.ntiles * recsz))) return rc;
+        const bool direct = plan.writes_partials();   // the plan's own kernels add per-replicate records to `partials`
+        plan.out_partials = partials;
+        if (!direct && (rc = h->tile_rec.reserve(sizeof(double) * (size_t)g.ntiles * recsz))) return rc;
         // tiles that intersect the shard form one contiguous index range [t_lo, t_hi); the others are all-zero records
         const int t_lo = (int)((col0 - (int64_t)g.rep_first * n) / g.ts);
         const int t_hi = (rep_last - g.rep_first) * g.tpr + (int)((valid_hi - 1 - (int64_t)rep_last * n) / g.ts) + 1;
-        if (t_lo > 0) GSA_CUDA(cudaMemsetAsync(h->tile_rec.p, 0, sizeof(double) * (size_t)t_lo * recsz, h->stream));
-        if (t_hi < g.ntiles)
+        if (!direct && t_lo > 0) GSA_CUDA(cudaMemsetAsync(h->tile_rec.p, 0, sizeof(double) * (size_t)t_lo * recsz, h->stream));
+        if (!direct && t_hi < g.ntiles)
             GSA_CUDA(cudaMemsetAsync(h->tile_rec.as<double>() + (size_t)t_hi * recsz, 0, sizeof(double) * (size_t)(g.ntiles - t_hi) * recsz, h->stream));
 
         if (!host_in) {
@@ -369,7 +371,7 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
                     if (a1 > a0) { c0 = std::min(c0, a0); c1 = std::max(c1, a1); }
                 }
                 if (c1 <= c0) {   // nothing of this chunk lies in the shard: its tile records are all-zero
-                    GSA_CUDA(cudaMemsetAsync(h->tile_rec.as<double>() + (size_t)t0 * recsz, 0, sizeof(double) * (size_t)(t1 - t0) * recsz, h->stream));
+                    if (!direct) GSA_CUDA(cudaMemsetAsync(h->tile_rec.as<double>() + (size_t)t0 * recsz, 0, sizeof(double) * (size_t)(t1 - t0) * recsz, h->stream));
                     --ci;         // keep the buffer parity in step with the chunks that really use a buffer
                     continue;
                 }
@@ -401,7 +403,7 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
                 GSA_CUDA(cudaEventRecord(h->ev_done[b], h->stream));
             }
         }
-        if ((rc = run_reduce(h, recsz, nstat, g.tpr, g.rep_first, nrep, partials))) return rc;
+        if (!direct && (rc = run_reduce(h, recsz, nstat, g.tpr, g.rep_first, nrep, partials))) return rc;
     }
     GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
     return GSA_OK;

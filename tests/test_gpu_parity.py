@@ -321,9 +321,11 @@ def test_small_kernels_match_generic(monkeypatch):
         assert_parity(res, ref, what=("y", force))
 
 
-@pytest.mark.parametrize("d,nout,N,nboot", [(20, 256, 1 << 15, 1), (5, 3, 20000, 4), (31, 7, 5000, 1), (3, 1, 4097, 2), (12, 40, 30011, 3)])
+@pytest.mark.parametrize("d,nout,N,nboot", [(20, 256, 1 << 15, 1), (5, 3, 20000, 4), (31, 7, 5000, 1), (3, 1, 4097, 2), (12, 40, 30011, 3),
+                                            (32, 4, 9001, 2), (1, 2, 3001, 1), (4, 1, 1000, 5), (17, 3, 1 << 16, 1), (8, 300, 777, 37), (20, 2, 3, 1)])
 def test_linear_gram_kernel(d, nout, N, nboot):
-    """BASELINE config 4 shape (d=20, 256 outputs; smaller N) and odd shapes through the input-moment (Gram) kernel."""
+    """BASELINE config 4 shape (d=20, 256 outputs; smaller N) and odd shapes through the input-moment (Gram, FP64 mma) kernel:
+    every block count 1..8 of the stacked [a; b] vector, tiles that are not a multiple of 4 samples, many short replicates."""
     rng = np.random.default_rng(d * 1000 + nout)
     W = rng.normal(size=(nout, d)) * (1.0 + np.arange(d))[None, :] / d
     lb, ub = -rng.random(d) - 0.5, rng.random(d) + 2.0            # a box with non-zero mean: exercises the shift
@@ -351,6 +353,30 @@ def test_linear_large_offset_inputs():
     ref = gsa_ref.gsa_sobol("linear", W, A, B)
     res = g.gsa(g.DeviceModel("linear", W), g.Sobol(), A, B, batch=True)
     assert parity_err(res.S1, ref.S1) < 1e-9 and parity_err(res.ST, ref.ST) < 1e-9      # the oracle's own fB*(fAB-fA) cancels here
+
+
+def test_linear_streamed_shards():
+    """Linear model on HOST shards that start mid-replicate and span several streaming chunks: the per-launch shift row and the
+    records added to the partial sums chunk by chunk must give the same result as one resident launch."""
+    import torch
+    d, nout, N, nboot, world = 24, 3, 900000, 2, 3            # 172.8 MB per matrix: 3 pageable chunks per shard
+    rng = np.random.default_rng(7)
+    W = rng.normal(size=(nout, d))
+    model, method = g.DeviceModel("linear", W), g.Sobol(nboot=nboot)
+    A, B = g.generate_design_matrices(N, -np.ones(d), 3.0 * np.ones(d), 2, device=True)
+    whole = g.gsa(model, method, A, B, batch=True)
+    An, Bn = A.cpu().numpy(), B.cpu().numpy()
+    total = None
+    for rank in range(world):
+        c0, nc = g.shard_columns(N, rank, world)
+        Al, Bl = np.asfortranarray(An[:, c0:c0 + nc]), np.asfortranarray(Bn[:, c0:c0 + nc])
+        p = g.sobol_partials(model, method, Al, Bl, N, c0)
+        total = p.clone() if total is None else total + p
+    torch.cuda.synchronize()
+    assert_parity(g.sobol_finalize(method, total, d, N), whole)
+    ref = gsa_ref.gsa_sobol("linear", W, An[:, :200000], Bn[:, :200000], nboot=nboot)
+    res = g.gsa(model, method, np.asfortranarray(An[:, :200000]), np.asfortranarray(Bn[:, :200000]), batch=True)
+    assert_parity(res, ref, what="host prefix vs oracle")
 
 
 USER_MODEL_CU = r'''
