@@ -7,13 +7,13 @@
 #include "gsa_internal.h"
 #include "fused_generic.cuh"
 #include "fused_product.cuh"
-#include "fused_product2.cuh"
 #include "small_launch.cuh"
 #include "fused_linear.cuh"
+#include "fused_pairs_mma.cuh"
 
 namespace gsa {
 
-enum { PLAN_GENERIC = 0, PLAN_PRODUCT = 1, PLAN_SMALL_ISHIGAMI = 2, PLAN_SMALL_SOBOLG = 3, PLAN_LINEAR = 4, PLAN_PRODUCT2 = 5 };
+enum { PLAN_GENERIC = 0, PLAN_PRODUCT = 1, PLAN_SMALL_ISHIGAMI = 2, PLAN_SMALL_SOBOLG = 3, PLAN_LINEAR = 4, PLAN_PAIRS_MMA = 5 };
 
 struct FusedPlan {
     int kind = PLAN_GENERIC;
@@ -155,6 +155,18 @@ static int plan_product(gsa_handle* h, FusedPlan* p) {
     return GSA_OK;
 }
 
+// ---- second-order pair sums on the FP64 tensor-core path (fused_pairs_mma.cuh) ----------------------
+constexpr int PMMA_UN = 2, PMMA_ST = 4;
+template <bool YSRC, bool VEC = false>
+static const void* pairs_mma_kernel_for(int NB, size_t* smem) {
+    switch (NB) {
+#define GSA_PM(NBV) case NBV: *smem = pm_smem_bytes<YSRC, NBV, PMMA_UN, PMMA_ST>(); return (const void*)pairs_mma_kernel<YSRC, NBV, PMMA_UN, PMMA_ST, VEC>;
+        GSA_PM(1) GSA_PM(2) GSA_PM(3) GSA_PM(4)
+#undef GSA_PM
+        default: return nullptr;
+    }
+}
+
 static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool second, int est, FusedPlan* p, bool gen = false) {
     p->gen = gen;
     p->model = model; p->d = d; p->nout = nout; p->np = np; p->second = second; p->est = est;
@@ -170,15 +182,17 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
         p->kind = PLAN_LINEAR;
         p->threads = LIN_THREADS;
         const int NB = (2 * d + 7) / 8;
-        int un = NB <= 3 ? 4 : 2;            // NB = 5 (d = 20): 164 registers with 2 steps per group, spills with 4
-        if (const char* e = getenv("GSA_LIN_UN")) un = (atoi(e) == 4 && NB <= 5) ? 4 : 2;   // tuning knob: warp steps per load group
+        const int un = 2;
+        int st = NB <= 5 ? 6 : 4;            // groups in flight per thread (ring stages)
+        if (const char* e = getenv("GSA_LIN_ST")) st = atoi(e) == 3 ? 3 : (atoi(e) == 4 ? 4 : 6);   // tuning knob
         const void* kern = nullptr;
-#define GSA_LIN_CASE(NBV) if (NB == NBV) kern = un == 4 ? (const void*)linear_gram_kernel<NBV, (NBV <= 5 ? 4 : 2)> : (const void*)linear_gram_kernel<NBV, 2>;
+#define GSA_LIN_CASE(NBV) if (NB == NBV) kern = st == 6 ? (const void*)linear_gram_kernel<NBV, 2, 6> : st == 4 ? (const void*)linear_gram_kernel<NBV, 2, 4> : (const void*)linear_gram_kernel<NBV, 2, 3>;
         GSA_LIN_CASE(1) GSA_LIN_CASE(2) GSA_LIN_CASE(3) GSA_LIN_CASE(4) GSA_LIN_CASE(5) GSA_LIN_CASE(6) GSA_LIN_CASE(7) GSA_LIN_CASE(8)
 #undef GSA_LIN_CASE
         if (!kern) return fail(GSA_ERR_UNSUPPORTED, "linear kernel: no instantiation for %d blocks", NB);
         p->lin_NB = NB;
-        p->lin_smem = sizeof(double) * (64 * (size_t)NB * NB + 8 * NB);
+        p->lin_smem = lin_smem_bytes(NB, un, st);
+        if (p->lin_smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lin_smem));
         int nbl = 0;
         GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbl, kern, LIN_THREADS, p->lin_smem));
         p->lin_kernel = kern;
@@ -188,31 +202,21 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
         return GSA_OK;
     }
     {
-        const char* e2 = getenv("GSA_PRODUCT2");   // tuning knob: 0 / 1 forces the lane-per-coordinate second-order kernel off / on
-        // (d <= 8 stays on the thread-per-sample register kernel: 0.14 vs 0.30 ms on config 3 -- with one coordinate per lane the
-        // shuffles and the per-lane double-double sums dominate; for 8 < d <= 32 it is 3x faster than the generic kernel)
-        const bool want2 = e2 ? atoi(e2) != 0 : d > SMALL_DMAX2;
-        if (!generic_only && model == GSA_MODEL_SOBOL_G && second && est == GSA_EI_JANSEN1999 && d >= 2 && d <= 32 && want2) {
-            int T = 2;
-            while (T < d) T <<= 1;
-            p->kind = PLAN_PRODUCT2;
-            p->prod_T = T;
-            p->threads = PROD2_THREADS;
-            const void* k = nullptr;
-            size_t sm = 0;
-            switch (T) {
-#define GSA_P2(TV) case TV: k = (const void*)fused_product2_kernel<TV>; sm = product2_smem_bytes<TV>(); break;
-                GSA_P2(2) GSA_P2(4) GSA_P2(8) GSA_P2(16) GSA_P2(32)
-#undef GSA_P2
-            }
-            p->kernel = k;
-            p->smem = sm;
-            if (sm > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        // d <= 8 stays on the thread-per-sample register kernel (config 3: 0.133 vs 0.158 ms: with one 8-coordinate block the
+        // per-step butterfly dominates); 8 < d <= 32: 7x faster than the
+        // lane-per-coordinate kernel with shuffled pair sums it replaced (d = 20, N = 2^21: 1.30 -> 0.19 ms).
+        const char* em = getenv("GSA_PAIRS_MMA");   // tuning knob: 0 = never, 1 = whenever possible
+        const bool want_mma = em ? atoi(em) != 0 : d > SMALL_DMAX2;
+        if (!generic_only && model == GSA_MODEL_SOBOL_G && second && est == GSA_EI_JANSEN1999 && d <= PMMA_DMAX && want_mma) {
+            p->kind = PLAN_PAIRS_MMA;
+            p->threads = PMMA_THREADS;
+            p->kernel = pairs_mma_kernel_for<false>((d + 7) / 8, &p->smem);
+            if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
             int nb = 0;
-            GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, PROD2_THREADS, sm));
+            GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));
             p->resident = std::max(1, nb) * h->sm_count;
-            p->tiles_per_cta = 2;
-            p->ts_min = p->ts_gran = PROD2_THREADS / T;
+            p->tiles_per_cta = 1;
+            p->ts_min = p->ts_gran = 4 * PMMA_UN * PMMA_NW;
             return GSA_OK;
         }
     }
@@ -272,9 +276,9 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         GSA_CUDA(cudaGetLastError());
         return GSA_OK;
     }
-    else if (kind == PLAN_PRODUCT2) {
-        Product2Args a;
-        a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = h->tile_rec.as<double>();
+    else if (kind == PLAN_PAIRS_MMA) {
+        PairsArgs a{};
+        a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = h->tile_rec.as<double>(); a.nout = 1;
         a.g = g; a.d = d; a.nstat = nstat; a.est = est; a.t_begin = t0; a.t_end = t1;
         void* kargs[] = {&a};
         GSA_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, h->stream));
@@ -298,7 +302,7 @@ inline int FusedPlan::prepare(gsa_handle* h, const double* params, int np_) {
         pa = params[0];
         pb = params[1];
     }
-    if ((kind == PLAN_PRODUCT || kind == PLAN_PRODUCT2 || kind == PLAN_SMALL_SOBOLG) && h->aux_kind != PLAN_PRODUCT) {
+    if ((kind == PLAN_PRODUCT || kind == PLAN_SMALL_SOBOLG || kind == PLAN_PAIRS_MMA) && h->aux_kind != PLAN_PRODUCT) {
         // (upload_params resets aux_kind whenever the parameters change)
         // g_k(x) = (|4x-2| + a_k)/(1 + a_k) = |x - 0.5| * 4/(1+a_k) + a_k/(1+a_k)
         std::vector<double> c(2 * (size_t)d);

@@ -18,8 +18,8 @@
 // on operand delivery.  u is cut into NB = ceil(2d/8) blocks of 8 coordinates; a warp step covers 4 consecutive samples: thread
 // (g = lane/4, t = lane%4) loads coordinate 8*blk+g of sample t straight from global memory (the 8 lanes of a sample read
 // 64 contiguous bytes), which is at once the A fragment (row g, k = t) and the B fragment (k = t, column g) of every block pair
-// -- no shared memory, no transposition.  NB(NB+1)/2 DMMAs per step accumulate the upper block triangle of U.  Loads of the
-// next group of steps are issued before the DMMAs of the current one.
+// -- no transposition.  NB(NB+1)/2 DMMAs per step accumulate the upper block triangle of U.  The operands of the next groups of
+// steps are in flight as per-thread cp.async copies into a private shared-memory ring while the DMMAs of the current group run.
 // Kernel 2 sums the per-tile moments of a replicate (fixed order).  Kernel 3 turns them into the library's standard sufficient-
 // statistics record per (replicate, output) -- double-double sums of y and y^2 recentred exactly -- and adds it to `partials`.
 #pragma once
@@ -51,15 +51,25 @@ __host__ __device__ inline int64_t lin_shift_col(const TileGeom& g, int r) {
 }
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void lin_cp_async8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// NB = blocks of the stacked vector; UN = warp steps (of 4 samples) per load group
-template <int NB, int UN>
+// NB = blocks of the stacked vector; UN = warp steps (of 4 samples) per load group; ST = groups in flight per thread.
+// Every thread stages its own future operands in a private shared-memory ring with cp.async (no barrier: a thread only ever
+// reads what it copied itself), so ST groups = ST*UN*NB 8-byte loads are in flight per thread without holding registers.
+__host__ __device__ inline size_t lin_smem_bytes(int NB, int UN, int ST) {
+    return sizeof(double) * (64 * (size_t)NB * NB + 8 * NB + (size_t)ST * UN * NB * LIN_THREADS);
+}
+
+template <int NB, int UN, int ST>
 __global__ void __launch_bounds__(LIN_THREADS) linear_gram_kernel(LinearArgs a) {
     constexpr int DU = 8 * NB, NP = NB * (NB + 1) / 2, GS = 64 * NB * NB + 8 * NB + 8;
-    extern __shared__ __align__(16) double lin_sm[];   // U[DU*DU], S[DU]
+    extern __shared__ __align__(16) double lin_sm[];   // U[DU*DU], S[DU], ring[ST][UN][NB][LIN_THREADS]
+    double* ring = lin_sm + DU * DU + DU + threadIdx.x;
     const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g8 = lane >> 2, t4 = lane & 3;
     // this thread's coordinate of every block: offset inside a row of A (i < d) or of B (d <= i < 2d)
     const double* src[NB];
@@ -94,26 +104,28 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_gram_kernel(LinearArgs a) 
         const int64_t cnt = c1 - c0, row0 = c0 - a.g.buf_col0;
         const int64_t ngroups = (cnt + 4 * UN - 1) / (4 * UN);
         // group G = steps [G*UN, (G+1)*UN), step q = samples [4q, 4q+4) of the tile; the warps take groups round-robin
-        auto load = [&](double (&v)[UN][NB], int64_t G) {
-            const int64_t s0 = G * (4 * UN) + t4;
-            if ((G + 1) * (4 * UN) <= cnt) {
-#pragma unroll
-                for (int j = 0; j < UN; ++j)
-#pragma unroll
-                    for (int k = 0; k < NB; ++k) v[j][k] = ok[k] ? ldg_stream(src[k] + (size_t)(row0 + s0 + 4 * j) * d) : 0.0;
-#pragma unroll
-                for (int j = 0; j < UN; ++j)
-#pragma unroll
-                    for (int k = 0; k < NB; ++k) v[j][k] -= sh[k];
-            } else {
+        auto issue = [&](int64_t G, int st) {   // asynchronous copies of group G into ring stage st (always commits a group)
+            if (G < ngroups) {
+                const int64_t s0 = G * (4 * UN) + t4;
+                const bool full = (G + 1) * (4 * UN) <= cnt;
 #pragma unroll
                 for (int j = 0; j < UN; ++j)
 #pragma unroll
                     for (int k = 0; k < NB; ++k)
-                        v[j][k] = (ok[k] && s0 + 4 * j < cnt) ? ldg_stream(src[k] + (size_t)(row0 + s0 + 4 * j) * d) - sh[k] : 0.0;
+                        if (ok[k] && (full || s0 + 4 * j < cnt))
+                            lin_cp_async8(ring + ((st * UN + j) * NB + k) * LIN_THREADS, src[k] + (size_t)(row0 + s0 + 4 * j) * d);
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        auto accumulate = [&](const double (&v)[UN][NB]) {
+        auto consume = [&](int64_t G, int st) {
+            const int64_t s0 = G * (4 * UN) + t4;
+            const bool full = (G + 1) * (4 * UN) <= cnt;
+            double v[UN][NB];
+#pragma unroll
+            for (int j = 0; j < UN; ++j)
+#pragma unroll
+                for (int k = 0; k < NB; ++k)
+                    v[j][k] = (ok[k] && (full || s0 + 4 * j < cnt)) ? ring[((st * UN + j) * NB + k) * LIN_THREADS] - sh[k] : 0.0;
 #pragma unroll
             for (int j = 0; j < UN; ++j) {
                 int p = 0;
@@ -125,18 +137,16 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_gram_kernel(LinearArgs a) 
                 for (int k = 0; k < NB; ++k) s1[k] += v[j][k];
             }
         };
-        double v0[UN][NB], v1[UN][NB];
-        int64_t G = warp;
-        if (G < ngroups) load(v0, G);
-        while (G < ngroups) {
-            if (G + LIN_NW < ngroups) load(v1, G + LIN_NW);
-            accumulate(v0);
-            G += LIN_NW;
-            if (G >= ngroups) break;
-            if (G + LIN_NW < ngroups) load(v0, G + LIN_NW);
-            accumulate(v1);
-            G += LIN_NW;
+#pragma unroll
+        for (int st = 0; st < ST - 1; ++st) issue(warp + (int64_t)st * LIN_NW, st);
+        int st = 0;
+        for (int64_t G = warp; G < ngroups; G += LIN_NW) {
+            issue(G + (int64_t)(ST - 1) * LIN_NW, st == 0 ? ST - 1 : st - 1);   // refills the stage consumed one iteration ago
+            asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
+            consume(G, st);
+            st = st + 1 == ST ? 0 : st + 1;
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
 
         // ---- combine the warps in a fixed order (shared memory), write the tile's moments ----
         double* U = lin_sm;

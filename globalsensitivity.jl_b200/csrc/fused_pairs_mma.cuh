@@ -1,0 +1,359 @@
+// fused_pairs_mma.cuh -- SECOND-order Sobol sums with the pair terms on the FP64 tensor-core path, d <= 32.
+//
+// The second-order estimator needs, for every pair k < j,  sum_s (yBA_k(s) * yAB_j(s) - yA(s) yB(s))  (reference
+// src/sobol_sensitivity.jl:197): d(d-1)/2 running sums per sample.  Over the samples this is a dense contraction,
+//     P[k][j] = sum_s yBA_k(s) * yAB_j(s)        (a d x d matrix product with the SAMPLES as the contraction index),
+// so it runs as `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4): a warp step covers 4 samples, thread (g = lane/4, t = lane%4) owns
+// coordinate 8*blk+g of sample t for every 8-coordinate block blk < NB; its yBA value is the A fragment (row g, k = t) and its
+// yAB value the B fragment (k = t, column g) of the block pairs rb <= cb.  One DMMA replaces 64 (diagonal blocks: 28 useful)
+// multiply-adds AND the shuffles that a lane-per-coordinate layout would need to bring yBA_k to the lane of yAB_j.
+//
+// Values enter the products shifted by c = yA of the tile's first sample (p = yBA - c, q = yAB - c), so the sums stay of the
+// order of the output's spread, not its mean:
+//     sum (yBA_k yAB_j - yA yB) = [P'_kj - sum fa' fb'] + c [(sum p_k + sum q_j) - (sum fa' + sum fb')],   fa' = yA - c, fb' = yB - c.
+// The first- and total-order terms are formed per sample exactly as the reference forms them (difference first, :192, :213).
+//
+// Two sources feed the same engine:
+//   * product-form models (Sobol G, BASELINE config 3): lane (g, t) loads coordinate 8*blk+g of rows A_s, B_s (the 8 lanes of a
+//     sample read 64 contiguous bytes), evaluates its factors, and one xor butterfly over the 8 lanes of the sample gives it the
+//     product of all OTHER factors (no division: a factor may be 0), hence yAB_i = gB_i * othersA_i, yBA_i = gA_i * othersB_i;
+//   * a precomputed Y = f(all_points) (estimator-only entry): lane (g, t) loads yAB_i(s+t), yBA_i(s+t) -- for a fixed block the
+//     4 lanes t read one 32-byte sector.
+// Operands of future steps are in flight as per-thread cp.async copies into a private shared-memory ring (no barriers).
+#pragma once
+#include "gsa_common.cuh"
+
+namespace gsa {
+
+constexpr int PMMA_THREADS = 128;
+constexpr int PMMA_NW = PMMA_THREADS / 32;
+constexpr int PMMA_DMAX = 32;
+
+struct PairsArgs {
+    // product source
+    const double* A;
+    const double* B;
+    const double2* coef;  // [d] (c1_k, c0_k): g_k(x) = |x - 0.5| * c1_k + c0_k
+    // Y source: element (o, col) at Y[o + nout*col], blocks [A | B | AB_1..AB_d | BA_1..BA_d] of n columns per replicate
+    const double* Y;
+    int64_t n;
+    int nout;
+    double* tile_rec;     // [ntiles][nout][nstat]
+    TileGeom g;
+    int d, nstat, est, t_begin, t_end;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pm_cp_async8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void pm_cp_async16(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void pm_dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// doubles staged per thread and step: product source 2*NB (xa, xb per block); Y source 2*NB + 2 (yAB, yBA per block, yA, yB)
+template <bool YSRC, int NB>
+__host__ __device__ constexpr int pm_step_doubles() { return YSRC ? 2 * NB + 2 : 2 * NB; }
+template <bool YSRC, int NB, int UN, int ST>
+constexpr size_t pm_smem_bytes() {
+    return sizeof(double) * ((size_t)ST * UN * pm_step_doubles<YSRC, NB>() * PMMA_THREADS + 64 * NB * NB + 4 * 8 * NB + 8);
+}
+
+// NB = 8-coordinate blocks (d <= 8*NB); UN = warp steps per load group; ST = groups in flight per thread.
+// Sample -> (step j, lane t) assignment inside a group of 4*UN samples (any assignment is valid: the contraction runs over all
+// samples): product source 4j + t (the 4 lanes t read 4 consecutive rows); Y source UN*t + j (a lane reads UN consecutive
+// samples of each block: VEC = one 16-byte copy per block when nout == 1 and the block starts are 16-byte aligned, UN == 2).
+template <bool YSRC, int NB, int UN, int ST, bool VEC = false>
+__global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
+    static_assert(!VEC || (YSRC && UN == 2), "16-byte copies: Y source, two samples per lane");
+    constexpr int DU = 8 * NB, NP = NB * (NB + 1) / 2, SD = pm_step_doubles<YSRC, NB>();
+    extern __shared__ __align__(16) double pm_sm[];
+    double* ring = pm_sm + (YSRC ? UN * threadIdx.x : threadIdx.x);   // product: [ST][UN][SD][THREADS]; Y: [ST][SD][THREADS][UN]
+    double* Csm = pm_sm + (size_t)ST * UN * SD * PMMA_THREADS;  // [DU][DU]
+    double* Vsm = Csm + DU * DU;                                // V[DU], E[DU], SP[DU], SQ[DU], sums[8]
+    const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g8 = lane >> 2, t4 = lane & 3;
+    bool ok[NB];
+    double2 cf[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+        ok[k] = 8 * k + g8 < d;
+        cf[k] = (!YSRC && ok[k]) ? __ldg(a.coef + 8 * k + g8) : make_double2(0.0, 1.0);   // padded coordinates: factor 1
+    }
+    const int units = (a.t_end - a.t_begin) * (YSRC ? a.nout : 1);
+
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int tile = a.t_begin + (YSRC ? u / a.nout : u), o = YSRC ? u % a.nout : 0;
+        int64_t c0, c1;
+        tile_range(a.g, tile, c0, c1);
+        double* rec = a.tile_rec + ((size_t)tile * (YSRC ? a.nout : 1) + o) * a.nstat;
+        if (c1 <= c0) {
+            for (int i = threadIdx.x; i < a.nstat; i += PMMA_THREADS) rec[i] = 0.0;
+            continue;
+        }
+        const int r = a.g.rep_first + tile / a.g.tpr;
+        const int64_t cnt = c1 - c0;
+        // source geometry: product -> row index inside the A/B buffers; Y -> column of block 0 (yA) of this replicate
+        const int64_t row0 = c0 - a.g.buf_col0;
+        const int64_t ycol0 = (int64_t)r * (2 * d + 2) * a.n + (c0 - (int64_t)r * a.g.n);
+        const double* ybase = YSRC ? a.Y + o + (size_t)a.nout * ycol0 : nullptr;
+        const int64_t ybs = (int64_t)a.nout * a.n;   // Y block stride (doubles)
+
+        // ---- the shift: yA of the tile's first sample, bit-identical in every thread ----
+        double c;
+        if constexpr (YSRC) {
+            c = __ldg(ybase);
+        } else {
+            double la = 1.0;
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                const double x = ok[k] ? __ldg(a.A + (size_t)row0 * d + 8 * k + g8) : 0.5;
+                la *= fma(fabs(x - 0.5), cf[k].x, cf[k].y);
+            }
+            la *= __shfl_xor_sync(0xffffffffu, la, 4);
+            la *= __shfl_xor_sync(0xffffffffu, la, 8);
+            la *= __shfl_xor_sync(0xffffffffu, la, 16);
+            c = la;
+        }
+
+        double V[NB], E[NB], SP[NB], SQ[NB], acc[NP][2];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) V[k] = E[k] = SP[k] = SQ[k] = 0.0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) acc[p][0] = acc[p][1] = 0.0;
+        double sfa = 0.0, sfb = 0.0, qfa = 0.0, qfb = 0.0, sab = 0.0;   // sums of fa', fb', fa'^2, fb'^2, fa' fb' (this lane's samples)
+
+        const int64_t ngroups = (cnt + 4 * UN - 1) / (4 * UN);
+        // slot of (stage st, step j, staged value v) in this thread's ring
+        auto slot_of = [&](int st, int j, int v) -> double* {
+            if constexpr (YSRC) return ring + ((size_t)(st * SD + v) * PMMA_THREADS) * UN + j;
+            else return ring + (size_t)((st * UN + j) * SD + v) * PMMA_THREADS;
+        };
+        auto issue = [&](int64_t G, int st) {
+            if (G < ngroups) {
+                if constexpr (YSRC) {
+                    const int64_t s0 = G * (4 * UN) + UN * t4;
+                    if (VEC && s0 + 1 < cnt) {   // both samples of the lane exist: one 16-byte copy per block
+                        const double* yp = ybase + s0;
+                        pm_cp_async16(slot_of(st, 0, 0), yp);
+                        pm_cp_async16(slot_of(st, 0, 1), yp + ybs);
+#pragma unroll
+                        for (int k = 0; k < NB; ++k)
+                            if (ok[k]) {
+                                const int i = 8 * k + g8;
+                                pm_cp_async16(slot_of(st, 0, 2 + 2 * k), yp + ybs * (2 + i));
+                                pm_cp_async16(slot_of(st, 0, 3 + 2 * k), yp + ybs * (2 + d + i));
+                            }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < UN; ++j) {
+                            const int64_t s = s0 + j;
+                            if (s < cnt) {
+                                const double* yp = ybase + (size_t)a.nout * s;
+                                pm_cp_async8(slot_of(st, j, 0), yp);
+                                pm_cp_async8(slot_of(st, j, 1), yp + ybs);
+#pragma unroll
+                                for (int k = 0; k < NB; ++k)
+                                    if (ok[k]) {
+                                        const int i = 8 * k + g8;
+                                        pm_cp_async8(slot_of(st, j, 2 + 2 * k), yp + ybs * (2 + i));
+                                        pm_cp_async8(slot_of(st, j, 3 + 2 * k), yp + ybs * (2 + d + i));
+                                    }
+                            }
+                        }
+                    }
+                } else {
+                    const int64_t s0 = G * (4 * UN) + t4;
+#pragma unroll
+                    for (int j = 0; j < UN; ++j) {
+                        const int64_t s = s0 + 4 * j;
+                        if (s < cnt) {
+#pragma unroll
+                            for (int k = 0; k < NB; ++k)
+                                if (ok[k]) {
+                                    const size_t e = (size_t)(row0 + s) * d + 8 * k + g8;
+                                    pm_cp_async8(slot_of(st, j, 2 * k), a.A + e);
+                                    pm_cp_async8(slot_of(st, j, 2 * k + 1), a.B + e);
+                                }
+                        }
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto consume = [&](int64_t G, int st) {
+#pragma unroll
+            for (int j = 0; j < UN; ++j) {
+                const bool valid = (YSRC ? G * (4 * UN) + UN * t4 + j : G * (4 * UN) + t4 + 4 * j) < cnt;
+                double yA, yB, yab[NB], yba[NB];
+                if constexpr (YSRC) {
+                    yA = valid ? *slot_of(st, j, 0) : c;
+                    yB = valid ? *slot_of(st, j, 1) : c;
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        const bool lv = valid && ok[k];
+                        yab[k] = lv ? *slot_of(st, j, 2 + 2 * k) : yA;
+                        yba[k] = lv ? *slot_of(st, j, 3 + 2 * k) : c;
+                    }
+                } else {
+                    double ga[NB], gb[NB];
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        const bool lv = valid && ok[k];
+                        const double xa = lv ? *slot_of(st, j, 2 * k) : 0.5, xb = lv ? *slot_of(st, j, 2 * k + 1) : 0.5;
+                        ga[k] = fma(fabs(xa - 0.5), cf[k].x, cf[k].y);
+                        gb[k] = fma(fabs(xb - 0.5), cf[k].x, cf[k].y);
+                    }
+                    // products of this thread's OTHER factors (prefix * suffix), then of the other 7 lanes of the sample (xor butterfly)
+                    double ea[NB], eb[NB];
+                    double pa = 1.0, pb = 1.0;
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) { ea[k] = pa; eb[k] = pb; pa *= ga[k]; pb *= gb[k]; }
+                    double sa = 1.0, sb = 1.0;
+#pragma unroll
+                    for (int k = NB - 1; k >= 0; --k) { ea[k] *= sa; eb[k] *= sb; sa *= ga[k]; sb *= gb[k]; }
+                    double oa = 1.0, ob = 1.0;   // pa, pb = this lane's full product; oa, ob = product over the other lanes
+#pragma unroll
+                    for (int x = 4; x < 32; x <<= 1) {
+                        const double ta = __shfl_xor_sync(0xffffffffu, pa, x), tb = __shfl_xor_sync(0xffffffffu, pb, x);
+                        oa *= ta; pa *= ta;
+                        ob *= tb; pb *= tb;
+                    }
+                    yA = pa;
+                    yB = pb;
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        yab[k] = gb[k] * (ea[k] * oa);   // A with coordinate i from B (:96-99)
+                        yba[k] = ga[k] * (eb[k] * ob);   // B with coordinate i from A (:100-104)
+                    }
+                }
+                const double fa = valid ? yA - c : 0.0, fb = valid ? yB - c : 0.0;
+                sfa += fa; sfb += fb;
+                qfa = fma(fa, fa, qfa); qfb = fma(fb, fb, qfb); sab = fma(fa, fb, sab);
+                double pv[NB], qv[NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                    const bool lv = valid && ok[k];
+                    const double df = lv ? yab[k] - yA : 0.0;
+                    V[k] = fma(yB, df, V[k]);            // :192
+                    E[k] = fma(df, df, E[k]);            // :213
+                    pv[k] = lv ? yba[k] - c : 0.0;
+                    qv[k] = lv ? yab[k] - c : 0.0;
+                    SP[k] += pv[k];
+                    SQ[k] += qv[k];
+                }
+                int p = 0;
+#pragma unroll
+                for (int rb = 0; rb < NB; ++rb)
+#pragma unroll
+                    for (int cb = rb; cb < NB; ++cb, ++p) pm_dmma(acc[p][0], acc[p][1], pv[rb], qv[cb]);   // :197
+            }
+        };
+#pragma unroll
+        for (int st = 0; st < ST - 1; ++st) issue(warp + (int64_t)st * PMMA_NW, st);
+        int st = 0;
+        for (int64_t G = warp; G < ngroups; G += PMMA_NW) {
+            issue(G + (int64_t)(ST - 1) * PMMA_NW, st == 0 ? ST - 1 : st - 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
+            consume(G, st);
+            st = st + 1 == ST ? 0 : st + 1;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+        // ---- flush: lanes of a coordinate (xor 1, 2), then the warps in a fixed order through shared memory ----
+#pragma unroll
+        for (int x = 1; x < 4; x <<= 1) {
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                V[k] += __shfl_xor_sync(0xffffffffu, V[k], x);
+                E[k] += __shfl_xor_sync(0xffffffffu, E[k], x);
+                SP[k] += __shfl_xor_sync(0xffffffffu, SP[k], x);
+                SQ[k] += __shfl_xor_sync(0xffffffffu, SQ[k], x);
+            }
+            sfa += __shfl_xor_sync(0xffffffffu, sfa, x); sfb += __shfl_xor_sync(0xffffffffu, sfb, x);
+            qfa += __shfl_xor_sync(0xffffffffu, qfa, x); qfb += __shfl_xor_sync(0xffffffffu, qfb, x);
+            sab += __shfl_xor_sync(0xffffffffu, sab, x);
+        }
+        __syncthreads();   // nobody still reads the shared arrays of the previous tile
+        for (int i = threadIdx.x; i < DU * DU + 4 * DU + 8; i += PMMA_THREADS) Csm[i] = 0.0;
+        __syncthreads();
+        for (int w = 0; w < PMMA_NW; ++w) {
+            if (warp == w) {
+                int p = 0;
+#pragma unroll
+                for (int rb = 0; rb < NB; ++rb)
+#pragma unroll
+                    for (int cb = rb; cb < NB; ++cb, ++p) {
+                        double* e = Csm + (8 * rb + g8) * DU + 8 * cb + 2 * t4;   // C fragment: row g, columns 2t, 2t+1
+                        e[0] += acc[p][0];
+                        e[1] += acc[p][1];
+                    }
+                if (t4 == 0) {
+#pragma unroll
+                    for (int k = 0; k < NB; ++k) {
+                        const int i = 8 * k + g8;
+                        Vsm[i] += V[k]; Vsm[DU + i] += E[k]; Vsm[2 * DU + i] += SP[k]; Vsm[3 * DU + i] += SQ[k];
+                    }
+                }
+                if (lane == 0) {
+                    double* q = Vsm + 4 * DU;
+                    q[0] += sfa; q[1] += sfb; q[2] += qfa; q[3] += qfb; q[4] += sab;
+                }
+            }
+            __syncthreads();
+        }
+        {
+            const double* q = Vsm + 4 * DU;
+            const double s_ab = q[0] + q[1];
+            const int pbase = stat_pair_base(d, a.est);
+            for (int i = threadIdx.x; i < d; i += PMMA_THREADS) {
+                rec[stat_v(i)] = Vsm[i];
+                rec[stat_e(d, 0, i)] = Vsm[DU + i];
+            }
+            for (int e = threadIdx.x; e < d * d; e += PMMA_THREADS) {
+                const int k = e / d, j = e - k * d;
+                if (k < j) rec[pbase + pair_index(d, k, j)] = (Csm[k * DU + j] - q[4]) + c * ((Vsm[2 * DU + k] + Vsm[3 * DU + j]) - s_ab);
+            }
+            if (threadIdx.x == 0) {
+                // un-shift exactly (double-double): sum y = s' + m c ; sum y^2 = q' + 2 c s' + m c^2
+                auto unshift = [&](double s1, double q2, double m, dd& S, dd& Q) {
+                    double p = m * c, pe = __fma_rn(m, c, -p);
+                    S = dd{s1, 0.0};
+                    dd_add_dd(S, dd{p, pe});
+                    double c2 = c * c, c2e = __fma_rn(c, c, -c2);
+                    double m1 = m * c2, m1e = __fma_rn(m, c2, -m1);
+                    m1e = __fma_rn(m, c2e, m1e);
+                    double m2 = 2.0 * c * s1, m2e = __fma_rn(2.0 * c, s1, -m2);
+                    Q = dd{q2, 0.0};
+                    dd_add_dd(Q, quick_two_sum(m1, m1e));
+                    dd_add_dd(Q, quick_two_sum(m2, m2e));
+                };
+                dd S, Q, SA, QA;
+                dd sab2 = two_sum(q[0], q[1]), qab2 = two_sum(q[2], q[3]);
+                // [yA; yB]: shifted sums added first (in double-double), then un-shifted with 2m values
+                {
+                    const double m = 2.0 * (double)cnt;
+                    double p = m * c, pe = __fma_rn(m, c, -p);
+                    S = sab2;
+                    dd_add_dd(S, dd{p, pe});
+                    double c2 = c * c, c2e = __fma_rn(c, c, -c2);
+                    double m1 = m * c2, m1e = __fma_rn(m, c2, -m1);
+                    m1e = __fma_rn(m, c2e, m1e);
+                    double m2 = 2.0 * c * sab2.hi, m2e = __fma_rn(2.0 * c, sab2.hi, -m2);
+                    m2e = __fma_rn(2.0 * c, sab2.lo, m2e);
+                    Q = qab2;
+                    dd_add_dd(Q, quick_two_sum(m1, m1e));
+                    dd_add_dd(Q, quick_two_sum(m2, m2e));
+                }
+                unshift(q[0], q[2], (double)cnt, SA, QA);
+                rec[0] = S.hi; rec[1] = S.lo; rec[2] = Q.hi; rec[3] = Q.lo;
+                rec[4] = SA.hi; rec[5] = SA.lo; rec[6] = QA.hi; rec[7] = QA.lo;
+            }
+        }
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace gsa

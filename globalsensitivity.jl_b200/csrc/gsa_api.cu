@@ -434,7 +434,37 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
         // or 16 (the three-term estimators need 4d accumulators)
         const bool small = d <= (second ? SMALL_DMAX2 : (est == GSA_EI_JANSEN1999 ? SMALL_DMAX_Y : 16)) && !(force && atoi(force) != 0);
         int tpr = 1;
-        if (small) {
+        const char* em = getenv("GSA_PAIRS_MMA");   // tuning knob: 0 = never, 1 = whenever possible; default: d > 8 (the register kernel covers d <= 8)
+        const bool pairs_mma = second && est == GSA_EI_JANSEN1999 && d <= PMMA_DMAX && !(force && atoi(force) != 0) &&
+                               (em ? atoi(em) != 0 : !small);
+        if (pairs_mma) {
+            // second order, d <= 32: the pair sums run as FP64 mma over the samples (fused_pairs_mma.cuh), Y is read exactly once
+            size_t smem = 0;
+            // 16-byte copies when every block of every replicate starts on a 16-byte boundary
+            const bool vec = nout == 1 && n % 2 == 0 && (reinterpret_cast<uintptr_t>(Yd) & 15) == 0 && !getenv("GSA_PAIRS_NOVEC");
+            const void* kern = vec ? pairs_mma_kernel_for<true, true>((d + 7) / 8, &smem) : pairs_mma_kernel_for<true, false>((d + 7) / 8, &smem);
+            if (smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int nb = 0;
+            GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PMMA_THREADS, smem));
+            const int resident = h->sm_count * std::max(1, nb);
+            PairsArgs a{};
+            a.Y = Yd; a.n = n; a.nout = nout; a.d = d; a.nstat = nstat; a.est = est;
+            a.g.n = n; a.g.col_lo = 0; a.g.col_hi = (int64_t)o->nboot * n; a.g.buf_col0 = 0; a.g.rep_first = 0;
+            choose_tiles(n, o->nboot, std::max(1, resident / nout), 1, 4 * PMMA_UN * PMMA_NW, 1 << 30, 4 * PMMA_UN * PMMA_NW, &a.g.ts, &a.g.tpr);
+            a.g.ntiles = a.g.tpr * o->nboot;
+            tpr = a.g.tpr;
+            if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)a.g.ntiles * recsz))) return rc;
+            a.tile_rec = h->tile_rec.as<double>();
+            a.t_begin = 0; a.t_end = a.g.ntiles;
+            const int64_t units = (int64_t)a.g.ntiles * nout;
+            void* kargs[] = {&a};
+            GSA_CUDA(cudaEventRecord(h->evk0, h->stream));
+            GSA_CUDA(cudaLaunchKernel(kern, dim3((unsigned)std::min<int64_t>(units, resident)), dim3(PMMA_THREADS), kargs, smem, h->stream));
+            GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
+            h->kernel_timed = true;
+            h->last_launches++;
+            GSA_CUDA(cudaGetLastError());
+        } else if (small) {
             // thread-per-sample register kernel: every Y value is read exactly once, straight into registers
             TileGeom g;
             g.n = n; g.col_lo = 0; g.col_hi = (int64_t)o->nboot * n; g.buf_col0 = 0; g.rep_first = 0;

@@ -296,15 +296,32 @@ def test_analyze_y_large_d(second, d):
         assert_parity(res, ref, what=(est, second))
 
 
-def test_product2_kernel_small_d(monkeypatch):
-    """The lane-per-coordinate second-order kernel is only selected for 8 < d <= 32; force it on for small d too."""
-    monkeypatch.setenv("GSA_PRODUCT2", "1")
-    for d, N, nboot in ((2, 5003, 1), (3, 4099, 2), (8, 1 << 16, 3), (7, 30011, 1)):
-        a = np.array(([0.0, 1.0, 4.5, 9.0] + [99.0] * d)[:d])
-        A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
-        ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, order=(0, 1, 2), nboot=nboot)
-        res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2], nboot=nboot), A, B, batch=True)
-        assert_parity(res, ref, what=(d, N, nboot))
+@pytest.mark.parametrize("d,N,nboot", [(2, 5003, 1), (3, 4099, 2), (7, 30011, 1), (8, 1 << 16, 3), (9, 9001, 2), (16, 20000, 1), (20, 33333, 4),
+                                       (25, 4100, 1), (32, 6007, 3), (8, 5, 1), (12, 700, 50)])
+def test_pairs_mma_kernel(d, N, nboot, monkeypatch):
+    """Second order for product-form models, d <= 32: the pair sums run as FP64 mma over the samples (fused_pairs_mma.cuh).
+    Every block count, ragged tiles (N not a multiple of 4), many short replicates; fused source and Y source."""
+    a = np.array(([0.0, 1.0, 4.5, 9.0] + [99.0] * d)[:d])
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, order=(0, 1, 2), nboot=nboot)
+    res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2], nboot=nboot), A, B, batch=True)
+    assert_parity(res, ref, what=(d, N, nboot, "fused"))
+    monkeypatch.setenv("GSA_PAIRS_MMA", "1")                       # also for d <= 8, where the register kernel is the default
+    Y = np.stack([gsa_ref.model_batch("sobol_g", a, gsa_ref.all_points(A, B, nboot, True)),
+                  gsa_ref.model_batch("sobol_g", a[::-1].copy(), gsa_ref.all_points(A, B, nboot, True))])
+    refy = gsa_ref.analyze_y(Y, d, N // nboot, order=(0, 1, 2), nboot=nboot)
+    resy = g.gsa_sobol_all_y_analysis(g.Sobol(order=[0, 1, 2], nboot=nboot), Y, d, N // nboot)
+    assert_parity(resy, refy, what=(d, N, nboot, "Y, 2 outputs"))
+
+
+def test_pairs_mma_mean_dominates():
+    """Outputs with mean >> spread (all a_k = 99: y = 1 +- 1e-2): the shifted products keep the pair sums exact enough."""
+    d, N = 8, 1 << 17
+    a = np.full(d, 99.0)
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, order=(0, 1, 2))
+    res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2]), A, B, batch=True)
+    assert_parity(res, ref)
 
 
 def test_small_kernels_match_generic(monkeypatch):

@@ -19,4 +19,4 @@ for _ in range(5):
     ks.append(h.last_timing()[1])
 k = float(np.median(ks))
 step = 2 * d + 2 if second else d + 2
-print(f"FUSED {name} d={d} N=2^{log2n} second={second} nboot={nboot} [P2={os.environ.get('GSA_PRODUCT2','-')} GEN={os.environ.get('GSA_FORCE_GENERIC','-')}]: {k:.3f} ms  {N*step/k/1e6:.1f} Grows/s  {16.0*d*N/k/1e6:.0f} GB/s")
+print(f"FUSED {name} d={d} N=2^{log2n} second={second} nboot={nboot} [MMA={os.environ.get('GSA_PAIRS_MMA','-')} GEN={os.environ.get('GSA_FORCE_GENERIC','-')}]: {k:.3f} ms  {N*step/k/1e6:.1f} Grows/s  {16.0*d*N/k/1e6:.0f} GB/s")
