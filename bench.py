@@ -6,7 +6,7 @@
     strong-scaled over 1/2/4/8 B200 (contiguous column shards, ONE all-reduce of the partial sums).
 
 A "step" is one full pass of the path over the design: fused design-swap + model + estimator kernel on this
-rank's shard, tile reduction, (N>1) NCCL all-reduce of nboot*nout*nstat doubles, device->host read of the sums
+rank's shard, tile reduction, (N>1) all-reduce of nboot*nout*nstat doubles (one kernel per rank over NVLink peer memory that also writes the sums to pinned host memory; NCCL + a D2H copy as fallback)
 and the host epilogue that yields S1/ST.
 
   value      inputs (A, B shards) resident in HBM before the timed region; CUDA events, max over ranks
@@ -183,16 +183,41 @@ def gpu_arm(args):
     A, B = g.generate_design_matrices(N, lb, ub, 2, device=True, col0=col0, ncols=ncols, handle=h)
     torch.cuda.synchronize()
     k1_ms = h.last_timing()[0]
-    partials = torch.empty((1, 1, g.nstat(method, d)), dtype=torch.float64, device="cuda")
+    ns = g.nstat(method, d)
+    partials = torch.empty((1, 1, ns), dtype=torch.float64, device="cuda")
     host_part = torch.empty(partials.shape, dtype=torch.float64).pin_memory()
+
+    # the single collective of the path (a few KB): one kernel per rank over NVLink peer memory (csrc/peer.cu) that also
+    # writes the sums into pinned host memory; torch.distributed's NCCL all-reduce + a D2H copy if the mailboxes cannot be mapped
+    pg, collective = None, "none"
+    if world > 1:
+        collective = "nccl"
+        if args.collective == "peer":
+            try:
+                pg = g.PeerGroup(h, partials.numel())
+                okf = torch.ones(1, device="cuda")
+            except Exception as e:                          # noqa: BLE001 - any rank failing sends every rank to NCCL
+                sys.stderr.write(f"[bench rank {rank}] peer mailboxes unavailable ({e}); using NCCL\n")
+                pg, okf = None, torch.zeros(1, device="cuda")
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if float(okf) < 1.0:
+                pg = None
+            else:
+                collective = "peer-memory kernel (gsa_peer_allreduce)"
+
+    def reduce_to_host():
+        if pg is not None:
+            pg.allreduce(partials, ns, host_out=host_part)
+        else:
+            if world > 1:
+                dist.all_reduce(partials)
+            host_part.copy_(partials, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return g.sobol_finalize(method, host_part.numpy(), d, N)
 
     def step():
         g.sobol_partials(model, method, A, B, N, col0, handle=h, out=partials)
-        if world > 1:
-            dist.all_reduce(partials)                      # the single collective of the path (a few KB)
-        host_part.copy_(partials, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return g.sobol_finalize(method, host_part.numpy(), d, N)
+        return reduce_to_host()
 
     def barrier():
         if world > 1:
@@ -236,11 +261,7 @@ def gpu_arm(args):
     if not args.no_gen:
         def gen_step():
             g.sobol_partials_generated(model, method, lb, ub, N, col0, ncols, handle=h, out=partials)
-            if world > 1:
-                dist.all_reduce(partials)
-            host_part.copy_(partials, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return g.sobol_finalize(method, host_part.numpy(), d, N)
+            return reduce_to_host()
 
         for _ in range(args.warmup):
             res_g = gen_step()
@@ -282,10 +303,7 @@ def gpu_arm(args):
             if world == 1:
                 return g.gsa(model, method, hA, hB, batch=True, handle=h)          # the call a user makes
             g.sobol_partials(model, method, hA, hB, N, col0, handle=h, out=partials)
-            dist.all_reduce(partials)
-            host_part.copy_(partials, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return g.sobol_finalize(method, host_part.numpy(), d, N)
+            return reduce_to_host()
 
         for _ in range(args.e2e_warmup):
             res_e = e2e_step()
@@ -326,10 +344,14 @@ def gpu_arm(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": w, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-                "roofline": roofline, "generated_design": gen, "cpu_baseline": cb, "clocks": clocks,
+                "collective": collective, "roofline": roofline, "generated_design": gen, "cpu_baseline": cb, "clocks": clocks,
                 "check": {"S1_0": float(res.S1[0]), "S1_0_analytic": float(Vi[0] / V), "ST_0": float(res.ST[0]),
                           "ST_0_analytic": float(Vi[0] * np.prod(1 + Vi) / (1 + Vi[0]) / V)}}
         print(json.dumps(line), flush=True)
+    if pg is not None:
+        if pg.status() != 0:
+            raise SystemExit("peer all-reduce timed out waiting for a rank")
+        pg.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -347,6 +369,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gen", action="store_true")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"], help="N > 1: how the partial sums are all-reduced")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -66,6 +66,11 @@ SIGNATURES = {
     "gsa_multi_sobol_run": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
     "gsa_multi_sobol_run_generated": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
     "gsa_last_timing": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _ip],
+    "gsa_peer_export": [_vp, _sz, _vp],
+    "gsa_peer_connect": [_vp, _i, _i, _vp],
+    "gsa_peer_allreduce": [_vp, _vp, _sz, _i, _vp],
+    "gsa_peer_status": [_vp, _ip],
+    "gsa_peer_disconnect": [_vp],
 }
 
 _lib = None

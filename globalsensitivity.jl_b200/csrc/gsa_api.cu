@@ -598,6 +598,7 @@ int gsa_destroy(gsa_handle* h) {
         DeviceGuard guard(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);
         if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+        peer_release_handle(h);
         DevBuf* bufs[] = {&h->tile_rec, &h->partials, &h->params, &h->vtab, &h->lbub, &h->stage[0], &h->stage[1], &h->dev_in[0], &h->dev_in[1], &h->ybuf, &h->aux, &h->gram};
         for (DevBuf* b : bufs) b->release();
         for (auto& um : h->user_models)

@@ -48,6 +48,8 @@ struct UserModelEntry {
     int nout = 1;
 };
 int register_user_model(gsa_handle* h, const void* image, size_t len, const char* symbol, int nout, int* model_id);
+struct PeerState;                          // peer.cu: mailboxes of the NVLink all-reduce
+void peer_release_handle(gsa_handle* h);   // frees h->peer (no-op when absent)
 }  // namespace gsa
 
 struct gsa_handle {
@@ -66,4 +68,5 @@ struct gsa_handle {
     int vdims = 0;
     bool kernel_timed = false;   // evk0/evk1 bracket the dominant kernel of the last call
     int last_launches = 0;
+    gsa::PeerState* peer = nullptr;
 };

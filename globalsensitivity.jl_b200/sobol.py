@@ -133,6 +133,61 @@ class GsaHandle:
         return ms.value, kms.value, n.value
 
 
+class PeerGroup:
+    """K5 over NVLink peer memory (csrc/peer.cu), one process per GPU: the ranks of a torch.distributed group exchange the
+    IPC handles of their mailboxes once; after that `allreduce` is ONE small kernel per rank on the handle's stream -- no
+    collective library on the data path, bit-identical sums on every rank, result optionally written straight into pinned
+    host memory.
+
+        pg = PeerGroup(handle, max_doubles=nboot * nout * nstat)           # collective: every rank of the group
+        p = sobol_partials(model, method, A_local, B_local, N, col0, handle=handle)
+        pg.allreduce(p, nstat, host_out=pinned)                            # collective
+    """
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, handle: "GsaHandle", max_doubles: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.h = handle
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_ubyte * self.HANDLE_BYTES)()
+        check(lib().gsa_peer_export(handle.ptr, int(max_doubles), C.addressof(buf)))
+        mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            mine = mine.cuda()
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=group)
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in gathered)
+        self._blob = C.create_string_buffer(blob, len(blob))
+        check(lib().gsa_peer_connect(handle.ptr, self.rank, self.world, C.addressof(self._blob)))
+        dist.barrier(group=group)          # every mailbox is mapped before the first exchange
+
+    def allreduce(self, partials, nstat: int, host_out=None):
+        """In-place sum of the CUDA tensor `partials` over the ranks; `host_out` (a pinned CPU tensor of the same size) also
+        receives the sums, written by the kernel.  Asynchronous on torch's current stream."""
+        hp = host_out.data_ptr() if host_out is not None else None
+        with _TorchStream(self.h, True):
+            check(lib().gsa_peer_allreduce(self.h.ptr, partials.data_ptr(), partials.numel(), int(nstat), hp))
+        return partials
+
+    def status(self) -> int:
+        st = C.c_int()
+        check(lib().gsa_peer_status(self.h.ptr, C.byref(st)))
+        return st.value
+
+    def close(self):
+        import torch.distributed as dist
+        if getattr(self, "h", None) is not None:
+            try:
+                if dist.is_initialized():
+                    dist.barrier(group=self.group)      # nobody unmaps a mailbox a peer may still write to
+            finally:
+                lib().gsa_peer_disconnect(self.h.ptr)
+                self.h = None
+
+
 class GsaMulti:
     """Single-process, multi-device form (gsa_multi): one handle and one NCCL communicator per device.
 

@@ -171,6 +171,24 @@ GSA_API int gsa_sobol_all_points(gsa_handle* h, const gsa_sobol_opts* opts, cons
  * the call launched.  Used by bench.py's roofline line. */
 GSA_API int gsa_last_timing(gsa_handle* h, float* total_ms, float* kernel_ms, int* launches);
 
+/* ---- K5 over NVLink peer memory (one process per GPU) ------------------------------------------------------ */
+/* All-reduce of the partial sums without a collective library: every rank exports a mailbox (cudaIpcMemHandle), maps its
+ * peers' mailboxes, and ONE kernel per rank pushes its vector into all peers, waits for theirs and adds them in rank order
+ * (double-double entries error-free), so all ranks hold bit-identical sums.  Collective calls: every rank of the group must
+ * make the same sequence of gsa_peer_allreduce calls with the same count.
+ *   gsa_peer_export     allocates this rank's mailbox for vectors of up to max_doubles and writes its 64-byte IPC handle
+ *   gsa_peer_connect    handles = world * 64 bytes in rank order (exchanged by the caller, e.g. an all-gather)
+ *   gsa_peer_allreduce  in place on `data_dev` (count doubles = records of nstat doubles, see gsa_sobol_nstat), asynchronous on
+ *                       the handle's stream; host_out != NULL (pinned host memory) also receives the sums, written by the
+ *                       kernel itself (no device-to-host copy to wait for)
+ *   gsa_peer_status     0, or 1 after a wait for a peer timed out (GSA_PEER_TIMEOUT_MS, default 10000)               */
+#define GSA_PEER_HANDLE_BYTES 64
+GSA_API int gsa_peer_export(gsa_handle* h, size_t max_doubles, void* handle_out);
+GSA_API int gsa_peer_connect(gsa_handle* h, int rank, int world, const void* handles);
+GSA_API int gsa_peer_allreduce(gsa_handle* h, double* data_dev, size_t count, int nstat, double* host_out);
+GSA_API int gsa_peer_status(gsa_handle* h, int* status);
+GSA_API int gsa_peer_disconnect(gsa_handle* h);
+
 /* ---- single-process, multi-device form (a plain Julia `ccall` from one process) ------------------ */
 /* devices == NULL: devices 0..ndev-1.  Creates one gsa_handle per device and, for ndev > 1, NCCL communicators
  * (ncclCommInitAll; libnccl.so.2 is loaded with dlopen). */

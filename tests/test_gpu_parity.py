@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical inputs.
 
 Tolerance (SURVEY 8 / BASELINE.md): indices |delta| <= 1e-12 * max(1, |ref|); Sobol points bit-exact."""
+import os
+
 import numpy as np
 import pytest
 
@@ -478,6 +480,19 @@ def test_multi_device_single_process(ishigami_design):
     res = m.gsa_p_range(g.DeviceModel("sobol_g", a), g.Sobol(nboot=3), [[0.0, 1.0]] * 20, 30011)
     assert_parity(res, ref, what=("multi generated", ndev))
     m.close()
+
+
+def test_peer_allreduce_two_ranks():
+    """K5 over NVLink peer memory (csrc/peer.cu), one process per GPU under torchrun: sums equal NCCL's, are bit-identical on
+    every rank, and a sharded analysis equals the single-GPU one.  With one GPU the same protocol runs with world = 1."""
+    import subprocess, sys, torch
+    nproc = min(2, torch.cuda.device_count())
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "peer_probe.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '"e2e_max_abs_diff_vs_single_gpu"' in r.stdout
 
 
 def test_streamed_host_inputs_large():
