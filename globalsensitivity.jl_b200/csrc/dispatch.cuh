@@ -157,12 +157,23 @@ static int plan_product(gsa_handle* h, FusedPlan* p) {
 
 // ---- second-order pair sums on the FP64 tensor-core path (fused_pairs_mma.cuh) ----------------------
 constexpr int PMMA_UN = 2, PMMA_ST = 4;
-template <bool YSRC, bool VEC = false>
-static const void* pairs_mma_kernel_for(int NB, size_t* smem) {
+inline int pmma_y_stages(int NB) { return NB <= 2 ? 4 : (NB == 3 ? 3 : 2); }   // warp tiles: (2+2d) * 36 doubles per warp and stage
+static const void* pairs_mma_kernel_product(int NB, size_t* smem) {
     switch (NB) {
-#define GSA_PM(NBV) case NBV: *smem = pm_smem_bytes<YSRC, NBV, PMMA_UN, PMMA_ST>(); return (const void*)pairs_mma_kernel<YSRC, NBV, PMMA_UN, PMMA_ST, VEC>;
+#define GSA_PM(NBV) case NBV: *smem = pm_smem_bytes(pm_ring_doubles_product<NBV, PMMA_UN, PMMA_ST>(), NBV); return (const void*)pairs_mma_kernel<false, NBV, PMMA_UN, PMMA_ST>;
         GSA_PM(1) GSA_PM(2) GSA_PM(3) GSA_PM(4)
 #undef GSA_PM
+        default: return nullptr;
+    }
+}
+static const void* pairs_mma_kernel_y(int d, size_t* smem) {
+    const int NB = (d + 7) / 8;
+    *smem = pm_smem_bytes(pm_ring_doubles_y(d, pmma_y_stages(NB)), NB);
+    switch (NB) {
+        case 1: return (const void*)pairs_mma_kernel<true, 1, 1, 4>;
+        case 2: return (const void*)pairs_mma_kernel<true, 2, 1, 4>;
+        case 3: return (const void*)pairs_mma_kernel<true, 3, 1, 3>;
+        case 4: return (const void*)pairs_mma_kernel<true, 4, 1, 2>;
         default: return nullptr;
     }
 }
@@ -210,7 +221,7 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
         if (!generic_only && model == GSA_MODEL_SOBOL_G && second && est == GSA_EI_JANSEN1999 && d <= PMMA_DMAX && want_mma) {
             p->kind = PLAN_PAIRS_MMA;
             p->threads = PMMA_THREADS;
-            p->kernel = pairs_mma_kernel_for<false>((d + 7) / 8, &p->smem);
+            p->kernel = pairs_mma_kernel_product((d + 7) / 8, &p->smem);
             if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
             int nb = 0;
             GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));

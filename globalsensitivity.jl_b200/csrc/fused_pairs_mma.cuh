@@ -17,9 +17,9 @@
 //   * product-form models (Sobol G, BASELINE config 3): lane (g, t) loads coordinate 8*blk+g of rows A_s, B_s (the 8 lanes of a
 //     sample read 64 contiguous bytes), evaluates its factors, and one xor butterfly over the 8 lanes of the sample gives it the
 //     product of all OTHER factors (no division: a factor may be 0), hence yAB_i = gB_i * othersA_i, yBA_i = gA_i * othersB_i;
-//   * a precomputed Y = f(all_points) (estimator-only entry): lane (g, t) loads yAB_i(s+t), yBA_i(s+t) -- for a fixed block the
-//     4 lanes t read one 32-byte sector.
-// Operands of future steps are in flight as per-thread cp.async copies into a private shared-memory ring (no barriers).
+//   * a precomputed Y = f(all_points) (estimator-only entry): every warp streams chunks of 32 samples of all 2d+2 blocks into
+//     a private shared-memory tile (lane = sample: 256 contiguous bytes per block and copy) and reads the fragments from there.
+// Operands of future steps are in flight as cp.async copies (per-thread ring / per-warp tiles): no block-wide barrier.
 #pragma once
 #include "gsa_common.cuh"
 
@@ -47,34 +47,33 @@ struct PairsArgs {
 __device__ __forceinline__ void pm_cp_async8(double* smem_dst, const double* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void pm_cp_async16(double* smem_dst, const double* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void pm_dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// doubles staged per thread and step: product source 2*NB (xa, xb per block); Y source 2*NB + 2 (yAB, yBA per block, yA, yB)
-template <bool YSRC, int NB>
-__host__ __device__ constexpr int pm_step_doubles() { return YSRC ? 2 * NB + 2 : 2 * NB; }
-template <bool YSRC, int NB, int UN, int ST>
-constexpr size_t pm_smem_bytes() {
-    return sizeof(double) * ((size_t)ST * UN * pm_step_doubles<YSRC, NB>() * PMMA_THREADS + 64 * NB * NB + 4 * 8 * NB + 8);
-}
+// Staging.  Product source: every thread keeps ST groups of UN steps of ITS OWN operands (xa, xb per block) in flight as
+// cp.async copies into a private ring (no barrier).  Y source: every WARP keeps ST chunks of 32 samples in flight -- lane L
+// copies sample L of every block (256 contiguous bytes per block and instruction, the access pattern of a streaming read) into
+// a warp-private tile [block][36]; the fragments are then read back conflict-free (pitch 36: lanes (g, t) hit 16 distinct
+// 8-byte bank pairs per half-warp); only __syncwarp() separates the copies from the reads.
+constexpr int PM_CH = 32, PM_PITCH = 36;
+template <int NB, int UN, int ST>
+__host__ __device__ constexpr size_t pm_ring_doubles_product() { return (size_t)ST * UN * 2 * NB * PMMA_THREADS; }
+inline size_t pm_ring_doubles_y(int d, int ST) { return (size_t)PMMA_NW * ST * (2 + 2 * d) * PM_PITCH; }
+inline size_t pm_smem_bytes(size_t ring_doubles, int NB) { return sizeof(double) * (ring_doubles + 64 * NB * NB + 4 * 8 * NB + 8); }
 
-// NB = 8-coordinate blocks (d <= 8*NB); UN = warp steps per load group; ST = groups in flight per thread.
-// Sample -> (step j, lane t) assignment inside a group of 4*UN samples (any assignment is valid: the contraction runs over all
-// samples): product source 4j + t (the 4 lanes t read 4 consecutive rows); Y source UN*t + j (a lane reads UN consecutive
-// samples of each block: VEC = one 16-byte copy per block when nout == 1 and the block starts are 16-byte aligned, UN == 2).
-template <bool YSRC, int NB, int UN, int ST, bool VEC = false>
+// NB = 8-coordinate blocks (d <= 8*NB); UN = warp steps per load group (product source); ST = stages in flight
+template <bool YSRC, int NB, int UN, int ST>
 __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
-    static_assert(!VEC || (YSRC && UN == 2), "16-byte copies: Y source, two samples per lane");
-    constexpr int DU = 8 * NB, NP = NB * (NB + 1) / 2, SD = pm_step_doubles<YSRC, NB>();
+    constexpr int DU = 8 * NB, NP = NB * (NB + 1) / 2;
     extern __shared__ __align__(16) double pm_sm[];
-    double* ring = pm_sm + (YSRC ? UN * threadIdx.x : threadIdx.x);   // product: [ST][UN][SD][THREADS]; Y: [ST][SD][THREADS][UN]
-    double* Csm = pm_sm + (size_t)ST * UN * SD * PMMA_THREADS;  // [DU][DU]
-    double* Vsm = Csm + DU * DU;                                // V[DU], E[DU], SP[DU], SQ[DU], sums[8]
     const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g8 = lane >> 2, t4 = lane & 3;
+    const int nblk = 2 + 2 * d;                                   // Y blocks per sample: yA, yB, yAB_1..d, yBA_1..d
+    const size_t ring_doubles = YSRC ? (size_t)PMMA_NW * ST * nblk * PM_PITCH : pm_ring_doubles_product<NB, UN, ST>();
+    double* ring = pm_sm + threadIdx.x;                          // product: [ST][UN][2 NB][THREADS]
+    double* wtile = pm_sm + (size_t)warp * ST * nblk * PM_PITCH; // Y: [ST][nblk][PM_PITCH] per warp
+    double* Csm = pm_sm + ring_doubles;                          // [DU][DU]
+    double* Vsm = Csm + DU * DU;                                 // V[DU], E[DU], SP[DU], SQ[DU], sums[8]
     bool ok[NB];
     double2 cf[NB];
 #pragma unroll
@@ -125,46 +124,75 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
         for (int p = 0; p < NP; ++p) acc[p][0] = acc[p][1] = 0.0;
         double sfa = 0.0, sfb = 0.0, qfa = 0.0, qfb = 0.0, sab = 0.0;   // sums of fa', fb', fa'^2, fb'^2, fa' fb' (this lane's samples)
 
-        const int64_t ngroups = (cnt + 4 * UN - 1) / (4 * UN);
-        // slot of (stage st, step j, staged value v) in this thread's ring
-        auto slot_of = [&](int st, int j, int v) -> double* {
-            if constexpr (YSRC) return ring + ((size_t)(st * SD + v) * PMMA_THREADS) * UN + j;
-            else return ring + (size_t)((st * UN + j) * SD + v) * PMMA_THREADS;
+        // one warp step: this lane's sample contributes yA, yB and, per block, yAB_i / yBA_i of coordinate i = 8k + g
+        auto step = [&](bool valid, double yA, double yB, const double (&yab)[NB], const double (&yba)[NB]) {
+            const double fa = valid ? yA - c : 0.0, fb = valid ? yB - c : 0.0;
+            sfa += fa; sfb += fb;
+            qfa = fma(fa, fa, qfa); qfb = fma(fb, fb, qfb); sab = fma(fa, fb, sab);
+            double pv[NB], qv[NB];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                const bool lv = valid && ok[k];
+                const double df = lv ? yab[k] - yA : 0.0;
+                V[k] = fma(yB, df, V[k]);            // :192
+                E[k] = fma(df, df, E[k]);            // :213
+                pv[k] = lv ? yba[k] - c : 0.0;
+                qv[k] = lv ? yab[k] - c : 0.0;
+                SP[k] += pv[k];
+                SQ[k] += qv[k];
+            }
+            int p = 0;
+#pragma unroll
+            for (int rb = 0; rb < NB; ++rb)
+#pragma unroll
+                for (int cb = rb; cb < NB; ++cb, ++p) pm_dmma(acc[p][0], acc[p][1], pv[rb], qv[cb]);   // :197
         };
-        auto issue = [&](int64_t G, int st) {
-            if (G < ngroups) {
-                if constexpr (YSRC) {
-                    const int64_t s0 = G * (4 * UN) + UN * t4;
-                    if (VEC && s0 + 1 < cnt) {   // both samples of the lane exist: one 16-byte copy per block
-                        const double* yp = ybase + s0;
-                        pm_cp_async16(slot_of(st, 0, 0), yp);
-                        pm_cp_async16(slot_of(st, 0, 1), yp + ybs);
+
+        if constexpr (YSRC) {
+            // ---- Y source: warp-private tiles of 32 samples, the warps take chunks round-robin ----
+            const int64_t nchunks = (cnt + PM_CH - 1) / PM_CH;
+            auto issue = [&](int64_t ch, int st) {
+                const int64_t s = ch * PM_CH + lane;
+                if (ch < nchunks && s < cnt) {
+                    const double* yp = ybase + (size_t)a.nout * s;
+                    double* dst = wtile + (size_t)st * nblk * PM_PITCH + lane;
+#pragma unroll 6
+                    for (int b = 0; b < nblk; ++b) pm_cp_async8(dst + b * PM_PITCH, yp + ybs * b);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
 #pragma unroll
-                        for (int k = 0; k < NB; ++k)
-                            if (ok[k]) {
-                                const int i = 8 * k + g8;
-                                pm_cp_async16(slot_of(st, 0, 2 + 2 * k), yp + ybs * (2 + i));
-                                pm_cp_async16(slot_of(st, 0, 3 + 2 * k), yp + ybs * (2 + d + i));
-                            }
-                    } else {
+            for (int st = 0; st < ST - 1; ++st) issue(warp + (int64_t)st * PMMA_NW, st);
+            int st = 0;
+            for (int64_t ch = warp; ch < nchunks; ch += PMMA_NW) {
+                __syncwarp();   // every lane has finished reading the stage that is refilled now
+                issue(ch + (int64_t)(ST - 1) * PMMA_NW, st == 0 ? ST - 1 : st - 1);
+                asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
+                __syncwarp();   // the other lanes' copies of this chunk are visible
+                const double* tl = wtile + (size_t)st * nblk * PM_PITCH;
+#pragma unroll 2
+                for (int q = 0; q < PM_CH / 4; ++q) {
+                    const int sl = 4 * q + t4;
+                    const bool valid = ch * PM_CH + sl < cnt;
+                    double yab[NB], yba[NB];
+                    const double yA = valid ? tl[sl] : c, yB = valid ? tl[PM_PITCH + sl] : c;
 #pragma unroll
-                        for (int j = 0; j < UN; ++j) {
-                            const int64_t s = s0 + j;
-                            if (s < cnt) {
-                                const double* yp = ybase + (size_t)a.nout * s;
-                                pm_cp_async8(slot_of(st, j, 0), yp);
-                                pm_cp_async8(slot_of(st, j, 1), yp + ybs);
-#pragma unroll
-                                for (int k = 0; k < NB; ++k)
-                                    if (ok[k]) {
-                                        const int i = 8 * k + g8;
-                                        pm_cp_async8(slot_of(st, j, 2 + 2 * k), yp + ybs * (2 + i));
-                                        pm_cp_async8(slot_of(st, j, 3 + 2 * k), yp + ybs * (2 + d + i));
-                                    }
-                            }
-                        }
+                    for (int k = 0; k < NB; ++k) {
+                        const bool lv = valid && ok[k];
+                        yab[k] = lv ? tl[(2 + 8 * k + g8) * PM_PITCH + sl] : yA;
+                        yba[k] = lv ? tl[(2 + d + 8 * k + g8) * PM_PITCH + sl] : c;
                     }
-                } else {
+                    step(valid, yA, yB, yab, yba);
+                }
+                st = st + 1 == ST ? 0 : st + 1;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else {
+            // ---- product source: per-thread ring, sample 4j + t of a group of 4*UN samples ----
+            const int64_t ngroups = (cnt + 4 * UN - 1) / (4 * UN);
+            auto slot_of = [&](int st, int j, int v) -> double* { return ring + (size_t)((st * UN + j) * 2 * NB + v) * PMMA_THREADS; };
+            auto issue = [&](int64_t G, int st) {
+                if (G < ngroups) {
                     const int64_t s0 = G * (4 * UN) + t4;
 #pragma unroll
                     for (int j = 0; j < UN; ++j) {
@@ -180,24 +208,12 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
                         }
                     }
                 }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        auto consume = [&](int64_t G, int st) {
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            auto consume = [&](int64_t G, int st) {
 #pragma unroll
-            for (int j = 0; j < UN; ++j) {
-                const bool valid = (YSRC ? G * (4 * UN) + UN * t4 + j : G * (4 * UN) + t4 + 4 * j) < cnt;
-                double yA, yB, yab[NB], yba[NB];
-                if constexpr (YSRC) {
-                    yA = valid ? *slot_of(st, j, 0) : c;
-                    yB = valid ? *slot_of(st, j, 1) : c;
-#pragma unroll
-                    for (int k = 0; k < NB; ++k) {
-                        const bool lv = valid && ok[k];
-                        yab[k] = lv ? *slot_of(st, j, 2 + 2 * k) : yA;
-                        yba[k] = lv ? *slot_of(st, j, 3 + 2 * k) : c;
-                    }
-                } else {
+                for (int j = 0; j < UN; ++j) {
+                    const bool valid = G * (4 * UN) + t4 + 4 * j < cnt;
                     double ga[NB], gb[NB];
 #pragma unroll
                     for (int k = 0; k < NB; ++k) {
@@ -221,46 +237,26 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
                         oa *= ta; pa *= ta;
                         ob *= tb; pb *= tb;
                     }
-                    yA = pa;
-                    yB = pb;
+                    double yab[NB], yba[NB];
 #pragma unroll
                     for (int k = 0; k < NB; ++k) {
                         yab[k] = gb[k] * (ea[k] * oa);   // A with coordinate i from B (:96-99)
                         yba[k] = ga[k] * (eb[k] * ob);   // B with coordinate i from A (:100-104)
                     }
+                    step(valid, pa, pb, yab, yba);
                 }
-                const double fa = valid ? yA - c : 0.0, fb = valid ? yB - c : 0.0;
-                sfa += fa; sfb += fb;
-                qfa = fma(fa, fa, qfa); qfb = fma(fb, fb, qfb); sab = fma(fa, fb, sab);
-                double pv[NB], qv[NB];
+            };
 #pragma unroll
-                for (int k = 0; k < NB; ++k) {
-                    const bool lv = valid && ok[k];
-                    const double df = lv ? yab[k] - yA : 0.0;
-                    V[k] = fma(yB, df, V[k]);            // :192
-                    E[k] = fma(df, df, E[k]);            // :213
-                    pv[k] = lv ? yba[k] - c : 0.0;
-                    qv[k] = lv ? yab[k] - c : 0.0;
-                    SP[k] += pv[k];
-                    SQ[k] += qv[k];
-                }
-                int p = 0;
-#pragma unroll
-                for (int rb = 0; rb < NB; ++rb)
-#pragma unroll
-                    for (int cb = rb; cb < NB; ++cb, ++p) pm_dmma(acc[p][0], acc[p][1], pv[rb], qv[cb]);   // :197
+            for (int st = 0; st < ST - 1; ++st) issue(warp + (int64_t)st * PMMA_NW, st);
+            int st = 0;
+            for (int64_t G = warp; G < ngroups; G += PMMA_NW) {
+                issue(G + (int64_t)(ST - 1) * PMMA_NW, st == 0 ? ST - 1 : st - 1);
+                asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
+                consume(G, st);
+                st = st + 1 == ST ? 0 : st + 1;
             }
-        };
-#pragma unroll
-        for (int st = 0; st < ST - 1; ++st) issue(warp + (int64_t)st * PMMA_NW, st);
-        int st = 0;
-        for (int64_t G = warp; G < ngroups; G += PMMA_NW) {
-            issue(G + (int64_t)(ST - 1) * PMMA_NW, st == 0 ? ST - 1 : st - 1);
-            asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
-            consume(G, st);
-            st = st + 1 == ST ? 0 : st + 1;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
 
         // ---- flush: lanes of a coordinate (xor 1, 2), then the warps in a fixed order through shared memory ----
 #pragma unroll

@@ -440,9 +440,7 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
         if (pairs_mma) {
             // second order, d <= 32: the pair sums run as FP64 mma over the samples (fused_pairs_mma.cuh), Y is read exactly once
             size_t smem = 0;
-            // 16-byte copies when every block of every replicate starts on a 16-byte boundary
-            const bool vec = nout == 1 && n % 2 == 0 && (reinterpret_cast<uintptr_t>(Yd) & 15) == 0 && !getenv("GSA_PAIRS_NOVEC");
-            const void* kern = vec ? pairs_mma_kernel_for<true, true>((d + 7) / 8, &smem) : pairs_mma_kernel_for<true, false>((d + 7) / 8, &smem);
+            const void* kern = pairs_mma_kernel_y(d, &smem);
             if (smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int nb = 0;
             GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PMMA_THREADS, smem));
@@ -450,7 +448,7 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
             PairsArgs a{};
             a.Y = Yd; a.n = n; a.nout = nout; a.d = d; a.nstat = nstat; a.est = est;
             a.g.n = n; a.g.col_lo = 0; a.g.col_hi = (int64_t)o->nboot * n; a.g.buf_col0 = 0; a.g.rep_first = 0;
-            choose_tiles(n, o->nboot, std::max(1, resident / nout), 1, 4 * PMMA_UN * PMMA_NW, 1 << 30, 4 * PMMA_UN * PMMA_NW, &a.g.ts, &a.g.tpr);
+            choose_tiles(n, o->nboot, std::max(1, resident / nout), 1, PM_CH * PMMA_NW, 1 << 30, PM_CH * PMMA_NW, &a.g.ts, &a.g.tpr);
             a.g.ntiles = a.g.tpr * o->nboot;
             tpr = a.g.tpr;
             if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)a.g.ntiles * recsz))) return rc;
