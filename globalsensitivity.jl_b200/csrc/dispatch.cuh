@@ -31,6 +31,9 @@ struct FusedPlan {
     uint64_t gen_first = 0;
     int gen_nboot = 1, gen_unit_box = 0;
     double pa = 0.0, pb = 0.0;   // Ishigami parameters (small kernel)
+    bool pairs_tile = false;     // pairs kernel with thread-per-sample evaluation (even d <= 8)
+    const void* kernel_alt = nullptr;
+    size_t smem_alt = 0;
     int lin_NB = 0;              // 8-coordinate blocks of the stacked [a; b] vector (linear Gram kernel)
     bool writes_partials() const { return kind == PLAN_LINEAR; }   // the plan adds its records to `out_partials` itself
     double* out_partials = nullptr;
@@ -160,9 +163,20 @@ constexpr int PMMA_UN = 2, PMMA_ST = 4;
 inline int pmma_y_stages(int NB) { return NB <= 2 ? 4 : (NB == 3 ? 3 : 2); }   // warp tiles: (2+2d) * 36 doubles per warp and stage
 static const void* pairs_mma_kernel_product(int NB, size_t* smem) {
     switch (NB) {
-#define GSA_PM(NBV) case NBV: *smem = pm_smem_bytes(pm_ring_doubles_product<NBV, PMMA_UN, PMMA_ST>(), NBV); return (const void*)pairs_mma_kernel<false, NBV, PMMA_UN, PMMA_ST>;
+#define GSA_PM(NBV) case NBV: *smem = pm_smem_bytes(pm_ring_doubles_product<NBV, PMMA_UN, PMMA_ST>(), NBV); return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT, NBV, PMMA_UN, PMMA_ST>;
         GSA_PM(1) GSA_PM(2) GSA_PM(3) GSA_PM(4)
 #undef GSA_PM
+        default: return nullptr;
+    }
+}
+constexpr int PMMA_TILE_ST = 3;
+static const void* pairs_mma_kernel_tile(int d, size_t* smem) {
+    *smem = pm_smem_bytes(pm_ring_doubles_tile(d, PMMA_TILE_ST), 1);
+    switch (d) {
+        case 2: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 2, PMMA_TILE_ST>;
+        case 4: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 4, PMMA_TILE_ST>;
+        case 6: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 6, PMMA_TILE_ST>;
+        case 8: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 8, PMMA_TILE_ST>;
         default: return nullptr;
     }
 }
@@ -170,10 +184,10 @@ static const void* pairs_mma_kernel_y(int d, size_t* smem) {
     const int NB = (d + 7) / 8;
     *smem = pm_smem_bytes(pm_ring_doubles_y(d, pmma_y_stages(NB)), NB);
     switch (NB) {
-        case 1: return (const void*)pairs_mma_kernel<true, 1, 1, 4>;
-        case 2: return (const void*)pairs_mma_kernel<true, 2, 1, 4>;
-        case 3: return (const void*)pairs_mma_kernel<true, 3, 1, 3>;
-        case 4: return (const void*)pairs_mma_kernel<true, 4, 1, 2>;
+        case 1: return (const void*)pairs_mma_kernel<PM_SRC_Y, 1, 1, 4>;
+        case 2: return (const void*)pairs_mma_kernel<PM_SRC_Y, 2, 1, 4>;
+        case 3: return (const void*)pairs_mma_kernel<PM_SRC_Y, 3, 1, 3>;
+        case 4: return (const void*)pairs_mma_kernel<PM_SRC_Y, 4, 1, 2>;
         default: return nullptr;
     }
 }
@@ -213,21 +227,28 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
         return GSA_OK;
     }
     {
-        // d <= 8 stays on the thread-per-sample register kernel (config 3: 0.133 vs 0.158 ms: with one 8-coordinate block the
-        // per-step butterfly dominates); 8 < d <= 32: 7x faster than the
-        // lane-per-coordinate kernel with shuffled pair sums it replaced (d = 20, N = 2^21: 1.30 -> 0.19 ms).
-        const char* em = getenv("GSA_PAIRS_MMA");   // tuning knob: 0 = never, 1 = whenever possible
-        const bool want_mma = em ? atoi(em) != 0 : d > SMALL_DMAX2;
-        if (!generic_only && model == GSA_MODEL_SOBOL_G && second && est == GSA_EI_JANSEN1999 && d <= PMMA_DMAX && want_mma) {
+        // Second order, product-form model, Jansen: the pair sums run as FP64 mma over the samples (fused_pairs_mma.cuh).
+        // 8 < d <= 32: one coordinate block per lane group, 7x faster than the lane-per-coordinate kernel with shuffled pair sums it
+        // replaced (d = 20, N = 2^21: 1.30 -> 0.19 ms).  Even d <= 8: thread-per-sample evaluation into a warp tile (with a single
+        // 8-coordinate block the per-step butterfly of the lane-per-coordinate source dominates: 0.158 vs 0.133 ms for the register
+        // kernel on config 3).  Odd d <= 8 stays on the register kernel.
+        const char* em = getenv("GSA_PAIRS_MMA");   // tuning knob: 0 = never, 1 = lane-per-coordinate source, 2 = tile source (even d <= 8)
+        const int mode = em ? atoi(em) : (d > SMALL_DMAX2 ? 1 : (d % 2 == 0 ? 2 : 0));
+        if (!generic_only && model == GSA_MODEL_SOBOL_G && second && est == GSA_EI_JANSEN1999 && d <= PMMA_DMAX && mode != 0) {
             p->kind = PLAN_PAIRS_MMA;
             p->threads = PMMA_THREADS;
-            p->kernel = pairs_mma_kernel_product((d + 7) / 8, &p->smem);
+            p->pairs_tile = mode == 2 && d <= 8 && d % 2 == 0;   // (rows must be 16-byte aligned: checked at launch)
+            p->kernel = p->pairs_tile ? pairs_mma_kernel_tile(d, &p->smem) : pairs_mma_kernel_product((d + 7) / 8, &p->smem);
             if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
             int nb = 0;
             GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));
             p->resident = std::max(1, nb) * h->sm_count;
             p->tiles_per_cta = 1;
-            p->ts_min = p->ts_gran = 4 * PMMA_UN * PMMA_NW;
+            p->ts_min = p->ts_gran = p->pairs_tile ? PM_CH * PMMA_NW : 4 * PMMA_UN * PMMA_NW;
+            if (p->pairs_tile) {   // designs that are not 16-byte aligned take the lane-per-coordinate source at launch
+                p->kernel_alt = pairs_mma_kernel_product(1, &p->smem_alt);
+                if (p->smem_alt > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel_alt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_alt));
+            }
             return GSA_OK;
         }
     }
@@ -292,7 +313,9 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = h->tile_rec.as<double>(); a.nout = 1;
         a.g = g; a.d = d; a.nstat = nstat; a.est = est; a.t_begin = t0; a.t_end = t1;
         void* kargs[] = {&a};
-        GSA_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, h->stream));
+        const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
+        if (pairs_tile && !aligned) GSA_CUDA(cudaLaunchKernel(kernel_alt, dim3(grid), dim3(threads), kargs, smem_alt, h->stream));
+        else GSA_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, h->stream));
     }
     else if (kind == PLAN_PRODUCT) {
         ProductArgs a;

@@ -60,16 +60,22 @@ constexpr int PM_CH = 32, PM_PITCH = 36;
 template <int NB, int UN, int ST>
 __host__ __device__ constexpr size_t pm_ring_doubles_product() { return (size_t)ST * UN * 2 * NB * PMMA_THREADS; }
 inline size_t pm_ring_doubles_y(int d, int ST) { return (size_t)PMMA_NW * ST * (2 + 2 * d) * PM_PITCH; }
+// thread-per-sample product source (d <= 8, even): per warp ST stages of the chunk's raw A and B rows + one tile of model values
+__host__ __device__ inline size_t pm_ring_doubles_tile(int d, int ST) { return (size_t)PMMA_NW * ((size_t)ST * 2 * PM_CH * d + (2 + 2 * d) * PM_PITCH); }
 inline size_t pm_smem_bytes(size_t ring_doubles, int NB) { return sizeof(double) * (ring_doubles + 64 * NB * NB + 4 * 8 * NB + 8); }
 
 // NB = 8-coordinate blocks (d <= 8*NB); UN = warp steps per load group (product source); ST = stages in flight
-template <bool YSRC, int NB, int UN, int ST>
+enum { PM_SRC_PRODUCT = 0, PM_SRC_Y = 1, PM_SRC_PRODUCT_TILE = 2 };
+template <int SRC, int NB, int UN, int ST>
 __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
+    constexpr bool YSRC = SRC == PM_SRC_Y, TSRC = SRC == PM_SRC_PRODUCT_TILE;
+    static_assert(!TSRC || NB == 1, "thread-per-sample evaluation: one 8-coordinate block (UN carries d)");
     constexpr int DU = 8 * NB, NP = NB * (NB + 1) / 2;
     extern __shared__ __align__(16) double pm_sm[];
     const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g8 = lane >> 2, t4 = lane & 3;
     const int nblk = 2 + 2 * d;                                   // Y blocks per sample: yA, yB, yAB_1..d, yBA_1..d
-    const size_t ring_doubles = YSRC ? (size_t)PMMA_NW * ST * nblk * PM_PITCH : pm_ring_doubles_product<NB, UN, ST>();
+    const size_t ring_doubles = YSRC ? (size_t)PMMA_NW * ST * nblk * PM_PITCH
+                              : TSRC ? pm_ring_doubles_tile(d, ST) : pm_ring_doubles_product<NB, UN, ST>();
     double* ring = pm_sm + threadIdx.x;                          // product: [ST][UN][2 NB][THREADS]
     double* wtile = pm_sm + (size_t)warp * ST * nblk * PM_PITCH; // Y: [ST][nblk][PM_PITCH] per warp
     double* Csm = pm_sm + ring_doubles;                          // [DU][DU]
@@ -82,6 +88,7 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
         cf[k] = (!YSRC && ok[k]) ? __ldg(a.coef + 8 * k + g8) : make_double2(0.0, 1.0);   // padded coordinates: factor 1
     }
     const int units = (a.t_end - a.t_begin) * (YSRC ? a.nout : 1);
+    (void)ring; (void)wtile;
 
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
         const int tile = a.t_begin + (YSRC ? u / a.nout : u), o = YSRC ? u % a.nout : 0;
@@ -125,10 +132,13 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
         double sfa = 0.0, sfb = 0.0, qfa = 0.0, qfb = 0.0, sab = 0.0;   // sums of fa', fb', fa'^2, fb'^2, fa' fb' (this lane's samples)
 
         // one warp step: this lane's sample contributes yA, yB and, per block, yAB_i / yBA_i of coordinate i = 8k + g
-        auto step = [&](bool valid, double yA, double yB, const double (&yab)[NB], const double (&yba)[NB]) {
+        auto sample_sums = [&](bool valid, double yA, double yB) {
             const double fa = valid ? yA - c : 0.0, fb = valid ? yB - c : 0.0;
             sfa += fa; sfb += fb;
             qfa = fma(fa, fa, qfa); qfb = fma(fb, fb, qfb); sab = fma(fa, fb, sab);
+        };
+        auto step = [&](bool valid, double yA, double yB, const double (&yab)[NB], const double (&yba)[NB]) {
+            if constexpr (!TSRC) sample_sums(valid, yA, yB);   // (tile source: added once per sample by the lane that evaluated it)
             double pv[NB], qv[NB];
 #pragma unroll
             for (int k = 0; k < NB; ++k) {
@@ -183,6 +193,108 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
                         yba[k] = lv ? tl[(2 + d + 8 * k + g8) * PM_PITCH + sl] : c;
                     }
                     step(valid, yA, yB, yab, yba);
+                }
+                st = st + 1 == ST ? 0 : st + 1;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else if constexpr (TSRC) {
+            // ---- product source, thread-per-sample evaluation (even d = TD <= 8, the UN template slot): lane L evaluates sample L of a
+            //      32-sample chunk -- all 2d+2 model values from prefix/suffix products, no shuffles -- and writes them to the warp's
+            //      tile; the mma fragments are read back from there.  The chunk's raw rows (32*d contiguous doubles of A and of B)
+            //      arrive by 16-byte cp.async copies, fully coalesced, ST chunks ahead; pieces are xor-swizzled so that a lane reads
+            //      its own row conflict-free.  Full chunks take a path without any validity selects. ----
+            constexpr int TD = UN, HP = TD / 2;                      // 16-byte pieces per row
+            static_assert(TD % 2 == 0 && TD >= 2 && TD <= 8, "tile source: even d <= 8");
+            const int gi = g8 < TD ? g8 : 0;                        // lanes of padded coordinates read a valid row and are masked
+            const int64_t nchunks = (cnt + PM_CH - 1) / PM_CH;
+            double* wbase = pm_sm + (size_t)warp * ((size_t)ST * 2 * PM_CH * TD + (2 + 2 * TD) * PM_PITCH);
+            double* ytile = wbase + (size_t)ST * 2 * PM_CH * TD;
+            auto swz = [](int row, int j) { return HP == 4 ? (j ^ ((row >> 1) & 3)) : HP == 2 ? (j ^ ((row >> 2) & 1)) : j; };
+            auto issue = [&](int64_t ch, int st) {
+                if (ch < nchunks) {
+                    const int rows = (int)min((int64_t)PM_CH, cnt - ch * PM_CH);
+                    const double* ga = a.A + (size_t)(row0 + ch * PM_CH) * TD;
+                    const double* gb = a.B + (size_t)(row0 + ch * PM_CH) * TD;
+                    double* sa = wbase + (size_t)st * 2 * PM_CH * TD;
+                    double* sb = sa + PM_CH * TD;
+#pragma unroll
+                    for (int i = 0; i < HP; ++i) {
+                        const int p = i * 32 + lane, row = p / HP, j = p % HP, q = 2 * (row * HP + swz(row, j));
+                        if (row < rows) {
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sa + q)), "l"(ga + 2 * p) : "memory");
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sb + q)), "l"(gb + 2 * p) : "memory");
+                        }
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            double2 cfd[TD];
+#pragma unroll
+            for (int i = 0; i < TD; ++i) cfd[i] = __ldg(a.coef + i);
+            auto phase_a = [&](int st, bool valid) {   // this lane's sample
+                const double* sa = wbase + (size_t)st * 2 * PM_CH * TD;
+                const double* sb = sa + PM_CH * TD;
+                double ga[TD], gb[TD];
+#pragma unroll
+                for (int j = 0; j < HP; ++j) {
+                    const int q = 2 * (lane * HP + swz(lane, j));
+                    double2 va = *reinterpret_cast<const double2*>(sa + q), vb = *reinterpret_cast<const double2*>(sb + q);
+                    ga[2 * j] = fma(fabs(va.x - 0.5), cfd[2 * j].x, cfd[2 * j].y);
+                    ga[2 * j + 1] = fma(fabs(va.y - 0.5), cfd[2 * j + 1].x, cfd[2 * j + 1].y);
+                    gb[2 * j] = fma(fabs(vb.x - 0.5), cfd[2 * j].x, cfd[2 * j].y);
+                    gb[2 * j + 1] = fma(fabs(vb.y - 0.5), cfd[2 * j + 1].x, cfd[2 * j + 1].y);
+                }
+                double PA[TD + 1], PB[TD + 1];
+                PA[0] = PB[0] = 1.0;
+#pragma unroll
+                for (int i = 0; i < TD; ++i) { PA[i + 1] = PA[i] * ga[i]; PB[i + 1] = PB[i] * gb[i]; }
+                double* yt = ytile + lane;
+                yt[0] = PA[TD];
+                yt[PM_PITCH] = PB[TD];
+                double ra = 1.0, rb = 1.0;
+#pragma unroll
+                for (int k = TD - 1; k >= 0; --k) {
+                    yt[(2 + k) * PM_PITCH] = PA[k] * (gb[k] * ra);        // AB_k: A with coordinate k from B (:96-99)
+                    yt[(2 + TD + k) * PM_PITCH] = PB[k] * (ga[k] * rb);   // BA_k (:100-104)
+                    ra *= ga[k];
+                    rb *= gb[k];
+                }
+                sample_sums(valid, PA[TD], PB[TD]);
+            };
+#pragma unroll
+            for (int st = 0; st < ST - 1; ++st) issue(warp + (int64_t)st * PMMA_NW, st);
+            int st = 0;
+            for (int64_t ch = warp; ch < nchunks; ch += PMMA_NW) {
+                __syncwarp();   // the previous chunk's fragments have been read; the stage refilled now is free
+                issue(ch + (int64_t)(ST - 1) * PMMA_NW, st == 0 ? ST - 1 : st - 1);
+                asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
+                __syncwarp();
+                const bool full = (ch + 1) * PM_CH <= cnt;
+                if (full) {
+                    phase_a(st, true);
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < PM_CH / 4; ++q) {   // the same 32 samples as 8 mma steps (padded lanes are masked by ok[0])
+                        const int sl = 4 * q + t4;
+                        double yab[1], yba[1];
+                        yab[0] = ytile[(2 + gi) * PM_PITCH + sl];
+                        yba[0] = ytile[(2 + TD + gi) * PM_PITCH + sl];
+                        step(true, ytile[sl], ytile[PM_PITCH + sl], yab, yba);
+                    }
+                } else {
+                    phase_a(st, ch * PM_CH + lane < cnt);   // (lanes beyond the tile read stale rows: finite or not, they are masked)
+                    __syncwarp();
+#pragma unroll 2
+                    for (int q = 0; q < PM_CH / 4; ++q) {
+                        const int sl = 4 * q + t4;
+                        const bool valid = ch * PM_CH + sl < cnt;
+                        const bool lv = valid && g8 < TD;
+                        const double yA = valid ? ytile[sl] : c, yB = valid ? ytile[PM_PITCH + sl] : c;   // (0 * NaN would poison V)
+                        double yab[1], yba[1];
+                        yab[0] = lv ? ytile[(2 + gi) * PM_PITCH + sl] : yA;
+                        yba[0] = lv ? ytile[(2 + TD + gi) * PM_PITCH + sl] : c;
+                        step(valid, yA, yB, yab, yba);
+                    }
                 }
                 st = st + 1 == ST ? 0 : st + 1;
             }
@@ -271,6 +383,14 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
             sfa += __shfl_xor_sync(0xffffffffu, sfa, x); sfb += __shfl_xor_sync(0xffffffffu, sfb, x);
             qfa += __shfl_xor_sync(0xffffffffu, qfa, x); qfb += __shfl_xor_sync(0xffffffffu, qfb, x);
             sab += __shfl_xor_sync(0xffffffffu, sab, x);
+        }
+        if constexpr (TSRC) {   // every lane added its own samples: finish the reduction over the 8 lane groups
+#pragma unroll
+            for (int x = 4; x < 32; x <<= 1) {
+                sfa += __shfl_xor_sync(0xffffffffu, sfa, x); sfb += __shfl_xor_sync(0xffffffffu, sfb, x);
+                qfa += __shfl_xor_sync(0xffffffffu, qfa, x); qfb += __shfl_xor_sync(0xffffffffu, qfb, x);
+                sab += __shfl_xor_sync(0xffffffffu, sab, x);
+            }
         }
         __syncthreads();   // nobody still reads the shared arrays of the previous tile
         for (int i = threadIdx.x; i < DU * DU + 4 * DU + 8; i += PMMA_THREADS) Csm[i] = 0.0;

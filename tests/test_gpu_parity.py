@@ -299,7 +299,7 @@ def test_analyze_y_large_d(second, d):
 
 
 @pytest.mark.parametrize("d,N,nboot", [(2, 5003, 1), (3, 4099, 2), (7, 30011, 1), (8, 1 << 16, 3), (9, 9001, 2), (16, 20000, 1), (20, 33333, 4),
-                                       (25, 4100, 1), (32, 6007, 3), (8, 5, 1), (12, 700, 50)])
+                                       (25, 4100, 1), (32, 6007, 3), (8, 5, 1), (12, 700, 50), (4, 10007, 2), (6, 12345, 1), (8, 33, 1)])
 def test_pairs_mma_kernel(d, N, nboot, monkeypatch):
     """Second order for product-form models, d <= 32: the pair sums run as FP64 mma over the samples (fused_pairs_mma.cuh).
     Every block count, ragged tiles (N not a multiple of 4), many short replicates; fused source and Y source."""
@@ -314,6 +314,28 @@ def test_pairs_mma_kernel(d, N, nboot, monkeypatch):
     refy = gsa_ref.analyze_y(Y, d, N // nboot, order=(0, 1, 2), nboot=nboot)
     resy = g.gsa_sobol_all_y_analysis(g.Sobol(order=[0, 1, 2], nboot=nboot), Y, d, N // nboot)
     assert_parity(resy, refy, what=(d, N, nboot, "Y, 2 outputs"))
+
+
+def test_pairs_mma_sources_agree(monkeypatch):
+    """d = 8 through all three fused second-order kernels (register kernel, lane-per-coordinate mma source, thread-per-sample
+    tile source) and through a design that is NOT 16-byte aligned (the tile source needs 16-byte rows and must step aside)."""
+    import torch
+    d, N, nboot = 8, 50001, 2
+    a = np.array([0.0, 1.0, 4.5, 9.0, 99.0, 99.0, 99.0, 99.0])
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, order=(0, 1, 2), nboot=nboot)
+    model, method = g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2], nboot=nboot)
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("GSA_PAIRS_MMA", mode)
+        assert_parity(g.gsa(model, method, A, B, batch=True), ref, what=("mode", mode))
+    monkeypatch.delenv("GSA_PAIRS_MMA")
+    bufA = torch.empty(d * N + 1, dtype=torch.float64, device="cuda")
+    bufB = torch.empty(d * N + 1, dtype=torch.float64, device="cuda")
+    At, Bt = bufA[1:].view(N, d).t(), bufB[1:].view(N, d).t()          # (d, N) views in Julia layout, 8 bytes off a 16-byte boundary
+    At.copy_(torch.from_numpy(np.ascontiguousarray(A)))
+    Bt.copy_(torch.from_numpy(np.ascontiguousarray(B)))
+    assert At.data_ptr() % 16 == 8
+    assert_parity(g.gsa(model, method, At, Bt, batch=True), ref, what="unaligned")
 
 
 def test_pairs_mma_mean_dominates():
