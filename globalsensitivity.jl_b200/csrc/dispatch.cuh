@@ -160,7 +160,7 @@ static int plan_product(gsa_handle* h, FusedPlan* p) {
 
 // ---- second-order pair sums on the FP64 tensor-core path (fused_pairs_mma.cuh) ----------------------
 constexpr int PMMA_UN = 2, PMMA_ST = 4;
-inline int pmma_y_stages(int NB) { return NB <= 2 ? 4 : (NB == 3 ? 3 : 2); }   // warp tiles: (2+2d) * 36 doubles per warp and stage
+inline int pmma_y_stages(int NB) { return NB == 1 ? 3 : 2; }   // warp tiles of (2+2d) * 36 doubles per stage: two CTAs per SM beat deeper rings
 static const void* pairs_mma_kernel_product(int NB, size_t* smem) {
     switch (NB) {
 #define GSA_PM(NBV) case NBV: *smem = pm_smem_bytes(pm_ring_doubles_product<NBV, PMMA_UN, PMMA_ST>(), NBV); return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT, NBV, PMMA_UN, PMMA_ST>;
@@ -182,14 +182,15 @@ static const void* pairs_mma_kernel_tile(int d, size_t* smem) {
 }
 static const void* pairs_mma_kernel_y(int d, size_t* smem) {
     const int NB = (d + 7) / 8;
-    *smem = pm_smem_bytes(pm_ring_doubles_y(d, pmma_y_stages(NB)), NB);
-    switch (NB) {
-        case 1: return (const void*)pairs_mma_kernel<PM_SRC_Y, 1, 1, 4>;
-        case 2: return (const void*)pairs_mma_kernel<PM_SRC_Y, 2, 1, 4>;
-        case 3: return (const void*)pairs_mma_kernel<PM_SRC_Y, 3, 1, 3>;
-        case 4: return (const void*)pairs_mma_kernel<PM_SRC_Y, 4, 1, 2>;
-        default: return nullptr;
-    }
+    int st = pmma_y_stages(NB);
+    if (const char* e = getenv("GSA_PAIRS_YST")) st = std::max(2, std::min(4, atoi(e)));   // tuning knob: stages of the warp tiles
+    if (NB >= 3 && st > 3) st = 3;
+    if (NB == 4) st = 2;
+    *smem = pm_smem_bytes(pm_ring_doubles_y(d, st), NB);
+#define GSA_PMY(NBV, STV) if (NB == NBV && st == STV) return (const void*)pairs_mma_kernel<PM_SRC_Y, NBV, 1, STV>;
+    GSA_PMY(1, 2) GSA_PMY(1, 3) GSA_PMY(1, 4) GSA_PMY(2, 2) GSA_PMY(2, 3) GSA_PMY(2, 4) GSA_PMY(3, 2) GSA_PMY(3, 3) GSA_PMY(4, 2)
+#undef GSA_PMY
+    return nullptr;
 }
 
 static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool second, int est, FusedPlan* p, bool gen = false) {
@@ -303,7 +304,7 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         LinearRecArgs r;
         r.red = red; r.A = A; r.W = h->params.as<double>(); r.partials = out_partials;
         r.g = g; r.d = d; r.NB = lin_NB; r.nout = nout; r.nstat = nstat; r.rl_first = rl0;
-        linear_records_kernel<<<nrl, 256, sizeof(double) * (2 * (size_t)d * d + 4 * d), h->stream>>>(r);
+        linear_records_kernel<<<dim3(nrl, (nout + LREC_OB - 1) / LREC_OB), LREC_OB * LREC_J, lin_rec_smem_bytes(d), h->stream>>>(r);
         h->last_launches += 3;
         GSA_CUDA(cudaGetLastError());
         return GSA_OK;

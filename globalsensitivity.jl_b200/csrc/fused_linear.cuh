@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_gram_kernel(LinearArgs a) 
 }
 
 // moments of the tiles [t_begin, t_end) of each replicate -> one moment set per replicate of the launch (fixed order)
-constexpr int LGR_X = 64, LGR_Y = 16;
+constexpr int LGR_X = 32, LGR_Y = 32;
 __global__ void __launch_bounds__(LGR_X* LGR_Y) linear_gram_reduce_kernel(const double* __restrict__ gram, double* __restrict__ red, int gs, int tpr,
                                                                          int t_begin, int t_end, int rl_first) {
     __shared__ double sh[LGR_Y][LGR_X];
@@ -208,8 +208,10 @@ __global__ void __launch_bounds__(LGR_X* LGR_Y) linear_gram_reduce_kernel(const 
     }
 }
 
-// moments of a replicate -> standard record of every output, ADDED to partials[replicate][output].  One CTA per replicate of the
-// launch, one thread per output.  Launches are serialised on the handle's stream, so the read-modify-write is race-free.
+// moments of a replicate -> standard record of every output, ADDED to partials[replicate][output].  Grid (replicates of the launch,
+// groups of LREC_OB outputs); thread (output, j) owns the coordinates j, j + 16: every dot product is a chain of d FMAs, the 16
+// lanes of an output are combined by a butterfly (fixed order).  Launches are serialised on the handle's stream and one thread
+// owns each entry of a record, so the read-modify-write of `partials` is race-free.
 struct LinearRecArgs {
     const double* red;   // [nrep_launch][gs]
     const double* A;     // the launch's A buffer (shift rows)
@@ -218,6 +220,9 @@ struct LinearRecArgs {
     TileGeom g;
     int d, NB, nout, nstat, rl_first;
 };
+constexpr int LREC_OB = 16, LREC_J = 16;   // outputs per CTA, lanes per output (d <= 2 * LREC_J)
+static_assert(LIN_DMAX <= 2 * LREC_J, "two coordinates per lane");
+__host__ __device__ inline size_t lin_rec_smem_bytes(int d) { return sizeof(double) * (2 * (size_t)d * (d + 1) + 4 * d + (size_t)d * LREC_OB); }
 
 __device__ __forceinline__ dd dd_from(double x) { return dd{x, 0.0}; }
 __device__ __forceinline__ dd dd_mul_d(dd a, double b) {  // a * b
@@ -227,27 +232,30 @@ __device__ __forceinline__ dd dd_mul_d(dd a, double b) {  // a * b
     return quick_two_sum(p, e);
 }
 
-__global__ void __launch_bounds__(256) linear_records_kernel(LinearRecArgs a) {
-    extern __shared__ double sg[];  // G[d*d] (Uaa + Ubb), H[d*d] (Ubb - Uba), g1[d] (sa + sb), h1[d] (sb - sa), D[d], c[d]
-    const int d = a.d, DU = 8 * a.NB, gs = lin_gram_size(a.NB);
+__global__ void __launch_bounds__(LREC_OB* LREC_J) linear_records_kernel(LinearRecArgs a) {
+    extern __shared__ double sg[];  // G[d][d+1] (Uaa + Ubb), H[d][d+1] (Ubb - Uba), g1[d] (sa + sb), h1[d] (sb - sa), D[d], c[d], Wt[d][LREC_OB]
+    const int d = a.d, P = d + 1, DU = 8 * a.NB, gs = lin_gram_size(a.NB);
     const int rl = a.rl_first + blockIdx.x, r = a.g.rep_first + rl;
     const double* red = a.red + (size_t)blockIdx.x * gs;
     const double* S = red + DU * DU;
     const double m = red[DU * DU + DU];   // samples of the replicate in this launch
     if (m == 0.0) return;
     double* G = sg;
-    double* H = G + d * d;
-    double* g1 = H + d * d;
+    double* H = G + d * P;
+    double* g1 = H + d * P;
     double* h1 = g1 + d;
     double* D = h1 + d;
     double* c = D + d;
+    double* Wt = c + d;
+    const int ol = threadIdx.x / LREC_J, j = threadIdx.x % LREC_J, o = blockIdx.y * LREC_OB + ol;
+    const bool live = o < a.nout;
     // U is stored block-upper-triangular: entry (l, k) lives at [l][k] when block(l) <= block(k), else at [k][l]
     auto Us = [&](int l, int k) { return (l >> 3) <= (k >> 3) ? red[l * DU + k] : red[k * DU + l]; };
     const int64_t cs = lin_shift_col(a.g, r);
     for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
         const int l = e / d, k = e - l * d;
-        G[e] = Us(l, k) + Us(d + l, d + k);
-        H[e] = Us(d + l, d + k) - Us(d + l, k);
+        G[l * P + k] = Us(l, k) + Us(d + l, d + k);
+        H[l * P + k] = Us(d + l, d + k) - Us(d + l, k);
     }
     for (int k = threadIdx.x; k < d; k += blockDim.x) {
         g1[k] = S[k] + S[d + k];
@@ -255,21 +263,30 @@ __global__ void __launch_bounds__(256) linear_records_kernel(LinearRecArgs a) {
         D[k] = (Us(d + k, d + k) - 2.0 * Us(k, d + k)) + Us(k, k);
         c[k] = __ldg(a.A + (size_t)(cs - a.g.buf_col0) * d + k);
     }
+    for (int e = threadIdx.x; e < d * LREC_OB; e += blockDim.x) {
+        const int l = e / LREC_OB, oo = blockIdx.y * LREC_OB + (e % LREC_OB);
+        Wt[e] = oo < a.nout ? __ldg(a.W + oo + (size_t)a.nout * l) : 0.0;
+    }
     __syncthreads();
-    for (int o = threadIdx.x; o < a.nout; o += blockDim.x) {
-        double* rec = a.partials + ((size_t)r * a.nout + o) * a.nstat;
-        double w[LIN_DMAX];                           // this output's row of W (coalesced loads across outputs)
-        for (int l = 0; l < d; ++l) w[l] = __ldg(a.W + o + (size_t)a.nout * l);
-        // y0 = w.c ; S' = w.g1 ; Q' = w' G w
-        double y0 = 0.0, S1 = 0.0, Q = 0.0;
-        for (int l = 0; l < d; ++l) {
-            const double wl = w[l];
-            y0 = fma(wl, c[l], y0);
-            S1 = fma(wl, g1[l], S1);
-            double row = 0.0;
-            for (int k = 0; k < d; ++k) row = fma(w[k], G[l * d + k], row);
-            Q = fma(wl, row, Q);
-        }
+    // phase 1: y0 = w.c ; S' = w.g1 ; Q' = w' G w  -- lane j adds the rows l = j, j + 16, then a 16-lane butterfly
+    double y0 = 0.0, S1 = 0.0, Q = 0.0;
+    for (int l = j; l < d; l += LREC_J) {
+        const double wl = Wt[l * LREC_OB + ol];
+        double row = 0.0;
+        for (int k = 0; k < d; ++k) row = fma(Wt[k * LREC_OB + ol], G[l * P + k], row);
+        y0 = fma(wl, c[l], y0);
+        S1 = fma(wl, g1[l], S1);
+        Q = fma(wl, row, Q);
+    }
+#pragma unroll
+    for (int x = 1; x < LREC_J; x <<= 1) {
+        y0 += __shfl_xor_sync(0xffffffffu, y0, x);
+        S1 += __shfl_xor_sync(0xffffffffu, S1, x);
+        Q += __shfl_xor_sync(0xffffffffu, Q, x);
+    }
+    if (!live) return;
+    double* rec = a.partials + ((size_t)r * a.nout + o) * a.nstat;
+    if (j == 0) {
         // un-shift exactly: sum y = S' + 2m y0 ; sum y^2 = Q' + 2 y0 S' + 2m y0^2   (double-double)
         dd sy = dd_from(S1);
         dd_add_dd(sy, dd_mul_d(dd_from(2.0 * m), y0));
@@ -281,13 +298,14 @@ __global__ void __launch_bounds__(256) linear_records_kernel(LinearRecArgs a) {
         dd_add_dd(p0, sy);
         dd_add_dd(p1, syy);
         rec[0] = p0.hi; rec[1] = p0.lo; rec[2] = p1.hi; rec[3] = p1.lo;
-        for (int k = 0; k < d; ++k) {
-            const double wk = w[k];
-            double hv = y0 * h1[k];
-            for (int l = 0; l < d; ++l) hv = fma(w[l], H[l * d + k], hv);
-            rec[stat_v(k)] += wk * hv;                  // sum yB (yAB_k - yA)       (:192)
-            rec[stat_e(d, 0, k)] += wk * wk * D[k];     // sum (yA - yAB_k)^2        (:213)
-        }
+    }
+    // phase 2: the coordinates k = j, j + 16 of this output
+    for (int k = j; k < d; k += LREC_J) {
+        const double wk = Wt[k * LREC_OB + ol];
+        double hv = y0 * h1[k];
+        for (int l = 0; l < d; ++l) hv = fma(Wt[l * LREC_OB + ol], H[l * P + k], hv);
+        rec[stat_v(k)] += wk * hv;                  // sum yB (yAB_k - yA)       (:192)
+        rec[stat_e(d, 0, k)] += wk * wk * D[k];     // sum (yA - yAB_k)^2        (:213)
     }
 }
 #endif  // __CUDACC__

@@ -28,7 +28,7 @@ from typing import Any, Callable, Optional, Sequence, Union
 import numpy as np
 
 from . import _lib
-from ._lib import EI_ESTIMATORS, LOC_DEVICE, LOC_HOST, SobolOpts, SobolResultC, check, lib
+from ._lib import EI_ESTIMATORS, LOC_DEVICE, LOC_HOST, GsaError, SobolOpts, SobolResultC, check, lib
 
 
 @dataclass
@@ -571,8 +571,19 @@ def reduce_and_finalize(method: Sobol, partials, d: int, N: int, *, Ei_estimator
 
 
 def gsa_sharded(f: DeviceModel, method: Sobol, A_local, B_local, N: int, col0: int, *, Ei_estimator="Jansen1999",
-                group=None, handle: Optional[GsaHandle] = None) -> SobolResult:
+                group=None, handle: Optional[GsaHandle] = None, peers: Optional["PeerGroup"] = None) -> SobolResult:
     """gsa(f, Sobol(...), A, B; batch=true) with the d x N design sharded by contiguous column ranges over the ranks of a
-    torch.distributed group (one process per GPU): local fused kernel -> one all-reduce -> epilogue."""
-    p = sobol_partials(f, method, A_local, B_local, N, col0, Ei_estimator=Ei_estimator, handle=handle)
-    return reduce_and_finalize(method, p, _Mat(A_local).d, N, Ei_estimator=Ei_estimator, group=group)
+    torch.distributed group (one process per GPU): local fused kernel -> one all-reduce -> epilogue.
+    `peers` (a PeerGroup built once on the same handle) runs the all-reduce as one kernel per rank over NVLink peer memory
+    (csrc/peer.cu) instead of torch.distributed's collective."""
+    h = handle or (peers.h if peers is not None else None)
+    p = sobol_partials(f, method, A_local, B_local, N, col0, Ei_estimator=Ei_estimator, handle=h)
+    if peers is None:
+        return reduce_and_finalize(method, p, _Mat(A_local).d, N, Ei_estimator=Ei_estimator, group=group)
+    import torch
+    host = torch.empty(p.shape, dtype=torch.float64).pin_memory()
+    peers.allreduce(p, p.shape[-1], host_out=host)
+    torch.cuda.current_stream().synchronize()
+    if peers.status() != 0:
+        raise GsaError(2, "peer all-reduce timed out waiting for a rank")
+    return sobol_finalize(method, host.numpy(), _Mat(A_local).d, N, Ei_estimator=Ei_estimator)

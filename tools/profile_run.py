@@ -29,16 +29,24 @@ del Y
 Y = torch.rand(18 * (1 << 22), dtype=torch.float64, device="cuda")
 run(lambda: g.gsa_sobol_all_y_analysis(g.Sobol(order=[0, 1, 2]), Y, 8, 1 << 22, handle=h))
 del Y
-# config 3: Sobol G d = 8 order 2 (thread-per-sample register kernel)
+# config 3: Sobol G d = 8 order 2 (thread-per-sample evaluation into a warp tile + FP64 mma pair sums)
 A, B = g.generate_design_matrices(1 << 22, np.zeros(8), np.ones(8), 2, device=True, handle=h)
 m3 = g.DeviceModel("sobol_g", [0, 1, 4.5, 9, 99, 99, 99, 99])
 run(lambda: g.sobol_partials(m3, g.Sobol(order=[0, 1, 2]), A, B, 1 << 22, 0, handle=h))
 del A, B
+# second order beyond the register kernels: Sobol G d = 20 (lane-per-coordinate mma source) and the estimator on its Y (warp tiles)
+A, B = g.generate_design_matrices(1 << 21, np.zeros(20), np.ones(20), 2, device=True, handle=h)
+m20 = g.DeviceModel("sobol_g", [0, 1, 4.5, 9] + [99.0] * 16)
+run(lambda: g.sobol_partials(m20, g.Sobol(order=[0, 1, 2]), A, B, 1 << 21, 0, handle=h))
+del A, B
+Y = torch.rand(42 * (1 << 21), dtype=torch.float64, device="cuda")
+run(lambda: g.gsa_sobol_all_y_analysis(g.Sobol(order=[0, 1, 2]), Y, 20, 1 << 21, handle=h))
+del Y
 # config 2: Ishigami d = 3, order 2, 1000 replicates
 A, B = g.generate_design_matrices(1 << 20, -np.pi * np.ones(3), np.pi * np.ones(3), 2, device=True, handle=h)
 run(lambda: g.sobol_partials(g.DeviceModel("ishigami", [7.0, 0.1]), g.Sobol(order=[0, 1, 2], nboot=1000), A, B, 1 << 20, 0, handle=h))
 del A, B
-# config 4: linear, d = 20, 256 outputs
+# config 4: linear, d = 20, 256 outputs (FP64 mma Gram kernel)
 o, i = np.meshgrid(np.arange(1, 257), np.arange(1, 21), indexing="ij")
 W = 1.0 + ((o * 31 + i * 17) % 13) / 13.0
 A, B = g.generate_design_matrices(1 << 22, np.zeros(20), np.ones(20), 2, device=True, handle=h)
