@@ -115,7 +115,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -124,6 +124,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
+
+    def wait_first_sample(self, timeout_s: float = 5.0):
+        """nvidia-smi takes ~1 s to print its first line: a short timed region would otherwise end before it (no samples)"""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.01)
 
     def stop(self, t0, t1):
         """terminate nvidia-smi and summarise the samples taken inside the timed region [t0, t1] (perf_counter clock)"""
@@ -135,7 +141,9 @@ class ClockSampler:
                 self.proc.kill()
         rows = list(self.rows)
         inside = [r[1:] for r in rows if t0 <= r[0] <= t1]
-        self.rows = inside if inside else [r[1:] for r in rows[-3:]]
+        if not inside:   # region shorter than the sampling period: take the samples closest to it
+            inside = [r[1:] for r in sorted(rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:3]]
+        self.rows = inside
         sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = []
@@ -227,6 +235,7 @@ def gpu_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                                     # nvidia-smi needs ~1 s to start: launch it before the warm-up
+        sampler.wait_first_sample()
     for _ in range(args.warmup):
         res = step()
     launches_per_step = h.last_timing()[2]
