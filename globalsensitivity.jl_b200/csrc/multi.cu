@@ -1,12 +1,12 @@
 // multi.cu -- single-process, multi-device form of the path (what a plain Julia `ccall` needs: SURVEY 8(b) "Threading").
 //
-// gsa_multi owns one gsa_handle per device and one NCCL communicator per device (ncclCommInitAll).  A run shards the
-// columns of A/B contiguously over the devices, launches the fused kernel of every shard from its own host
-// thread (each streams its part of the host design through its own PCIe link), then issues ONE grouped
-// ncclAllReduce(sum, fp64) of the nboot*nout*nstat partial sums -- a few KB over NVLink -- and runs the host epilogue.
-// NCCL is loaded with dlopen, so libgsa_cuda.so has no link-time dependency on it.
-#include <dlfcn.h>
-
+// gsa_multi owns one gsa_handle per device.  A run shards the columns of A/B contiguously over the devices,
+// launches the fused kernel of every shard from its own host thread (each streams its part of the host design through its own
+// PCIe link), then ONE kernel on the first device pulls the nboot*nout*nstat partial sums of every device over NVLink peer
+// memory (cudaDeviceEnablePeerAccess; all devices live in this process, so no IPC is needed), adds them in device order --
+// double-double entries error-free -- and writes the result straight into pinned host memory for the host epilogue.  No
+// collective library is involved.  Devices without peer access to the first one fall back to a copy of their few KB through
+// the host, summed in the same order.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -30,43 +30,37 @@ using namespace gsa;
 #define MDBG(...) do { if (getenv("GSA_DEBUG")) { fprintf(stderr, "[gsa_multi] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
 
 namespace {
-struct NcclApi {
-    void* so = nullptr;
-    int (*CommInitAll)(void**, int, const int*) = nullptr;
-    int (*CommDestroy)(void*) = nullptr;
-    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
-    int (*GroupStart)() = nullptr;
-    int (*GroupEnd)() = nullptr;
-    const char* (*GetErrorString)(int) = nullptr;
+constexpr int MULTI_MAX_DEV = 16;
+struct GatherArgs {
+    const double* part[MULTI_MAX_DEV];   // partial sums of every device that the first device can read (peer memory)
+    double* out;                         // mapped pinned host memory
+    size_t count;
+    int ndev, nstat;
 };
-NcclApi g_nccl;
-std::mutex g_nccl_mu;
-
-int load_nccl() {
-    std::lock_guard<std::mutex> lk(g_nccl_mu);
-    if (g_nccl.so) return GSA_OK;
-    for (const char* n : {"libnccl.so.2", "libnccl.so"})
-        if ((g_nccl.so = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
-    if (!g_nccl.so) return fail(GSA_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
-    g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))dlsym(g_nccl.so, "ncclCommInitAll");
-    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.so, "ncclCommDestroy");
-    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.so, "ncclAllReduce");
-    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(g_nccl.so, "ncclGroupStart");
-    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(g_nccl.so, "ncclGroupEnd");
-    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.so, "ncclGetErrorString");
-    if (!g_nccl.CommInitAll || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.GroupStart || !g_nccl.GroupEnd)
-        return fail(GSA_ERR_NCCL, "libnccl does not export the expected entry points");
-    return GSA_OK;
+// sum over the devices, in device order; (hi, lo) pairs of the double-double entries are added error-free
+__global__ void __launch_bounds__(256) multi_gather_sum_kernel(GatherArgs a) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i % a.nstat);
+        if (e < STAT_DD) {
+            if (e & 1) continue;
+            dd s{0.0, 0.0};
+            for (int g = 0; g < a.ndev; ++g) dd_add_dd(s, dd{a.part[g][i], a.part[g][i + 1]});
+            a.out[i] = s.hi;
+            a.out[i + 1] = s.lo;
+        } else {
+            double s = 0.0;
+            for (int g = 0; g < a.ndev; ++g) s += a.part[g][i];
+            a.out[i] = s;
+        }
+    }
 }
-int nccl_fail(int e, const char* what) {
-    return fail(GSA_ERR_NCCL, "NCCL error %d (%s) in %s", e, g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "?", what);
-}
-constexpr int NCCL_DOUBLE = 8, NCCL_SUM = 0;   // nccl.h: ncclFloat64 = 8, ncclSum = 0
 }  // namespace
 
 struct gsa_multi {
     std::vector<gsa_handle*> h;
-    std::vector<void*> comm;
+    std::vector<char> peer_ok;      // device g's memory is readable from the first device
+    double* host_sum = nullptr;     // pinned + mapped, host_cap doubles
+    size_t host_cap = 0;
     std::mutex mu;
     float last_ms = 0.f;
 };
@@ -86,16 +80,25 @@ int gsa_multi_create(const int* devices, int ndev, gsa_multi** out) {
         rc = gsa_create(devs[i], &hh);
         if (rc == GSA_OK) m->h.push_back(hh);
     }
-    if (rc == GSA_OK && ndev > 1) {
-        rc = load_nccl();
-        if (rc == GSA_OK) {
-            m->comm.assign(ndev, nullptr);
-            int e = g_nccl.CommInitAll(m->comm.data(), ndev, devs.data());
-            if (e) {
-                m->comm.clear();
-                rc = nccl_fail(e, "ncclCommInitAll");
+    if (rc == GSA_OK && ndev > MULTI_MAX_DEV) rc = fail(GSA_ERR_UNSUPPORTED, "gsa_multi supports up to %d devices", MULTI_MAX_DEV);
+    if (rc == GSA_OK) {
+        m->peer_ok.assign(ndev, 0);
+        m->peer_ok[0] = 1;
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(devs[0]);
+        for (int i = 1; i < ndev; ++i) {
+            int can = 0;
+            if (devs[i] == devs[0]) can = 1;
+            else if (cudaDeviceCanAccessPeer(&can, devs[0], devs[i]) == cudaSuccess && can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(devs[i], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+                can = e == cudaSuccess;
+                if (!can) cudaGetLastError();
             }
+            m->peer_ok[i] = (char)can;
         }
+        cudaSetDevice(prev);
     }
     if (rc != GSA_OK) {
         char keep[512];
@@ -110,8 +113,7 @@ int gsa_multi_create(const int* devices, int ndev, gsa_multi** out) {
 
 int gsa_multi_destroy(gsa_multi* m) {
     if (!m) return GSA_OK;
-    for (void* c : m->comm)
-        if (c && g_nccl.CommDestroy) g_nccl.CommDestroy(c);
+    if (m->host_sum) cudaFreeHost(m->host_sum);
     for (gsa_handle* hh : m->h) gsa_destroy(hh);
     delete m;
     return GSA_OK;
@@ -177,32 +179,62 @@ static int multi_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, con
     MDBG("joined");
     for (int g = 0; g < G; ++g)
         if (rcs[g] != GSA_OK) return fail(rcs[g], "device %d: %s", m->h[g]->device, errs[g].c_str());
-    if (G > 1) {   // the single collective of the path
-        int e = g_nccl.GroupStart();
-        if (e) return nccl_fail(e, "ncclGroupStart");
-        for (int g = 0; g < G && !e; ++g)
-            e = g_nccl.AllReduce(m->h[g]->partials.p, m->h[g]->partials.p, cnt, NCCL_DOUBLE, NCCL_SUM, m->comm[g], m->h[g]->stream);
-        int e2 = g_nccl.GroupEnd();
-        if (e || e2) return nccl_fail(e ? e : e2, "ncclAllReduce");
-    }
+    // ---- the single exchange of the path: the first device gathers and adds the partial sums over NVLink peer memory ----
     gsa_handle* h0 = m->h[0];
     cudaSetDevice(h0->device);
-    if (getenv("GSA_DEBUG")) {
-        for (int it = 0; it < 20; ++it) {
-            cudaError_t q1 = cudaStreamQuery(h0->stream), q2 = cudaStreamQuery(h0->copy_stream);
-            MDBG("query: stream %d copy %d", (int)q1, (int)q2);
-            if (q1 == cudaSuccess && q2 == cudaSuccess) break;
-            std::this_thread::sleep_for(std::chrono::milliseconds(250));
+    if (m->host_cap < cnt) {
+        if (m->host_sum) cudaFreeHost(m->host_sum);
+        m->host_sum = nullptr;
+        m->host_cap = 0;
+        GSA_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&m->host_sum), sizeof(double) * cnt, cudaHostAllocMapped));
+        m->host_cap = cnt;
+    }
+    GatherArgs ga{};
+    ga.count = cnt;
+    ga.nstat = nstat;
+    std::vector<std::vector<double>> via_host;   // shards of devices without peer access to the first one
+    std::vector<int> via_host_dev;
+    for (int g = 0; g < G; ++g) {
+        if (m->peer_ok[g]) {
+            ga.part[ga.ndev++] = m->h[g]->partials.as<double>();
+            if (g > 0) GSA_CUDA(cudaStreamWaitEvent(h0->stream, m->h[g]->ev1, 0));   // ev1: end of that device's partials call
+        } else {
+            via_host.emplace_back(cnt);
+            via_host_dev.push_back(g);
         }
     }
-    std::vector<double> host(cnt);
-    GSA_CUDA(cudaMemcpyAsync(host.data(), h0->partials.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h0->stream));
+    void* out_dev = nullptr;
+    GSA_CUDA(cudaHostGetDevicePointer(&out_dev, m->host_sum, 0));
+    ga.out = static_cast<double*>(out_dev);
+    const int grid = (int)std::min<size_t>((cnt + 255) / 256, 64);
+    multi_gather_sum_kernel<<<grid, 256, 0, h0->stream>>>(ga);
+    GSA_CUDA(cudaGetLastError());
+    for (size_t k = 0; k < via_host.size(); ++k) {
+        gsa_handle* hh = m->h[via_host_dev[k]];
+        cudaSetDevice(hh->device);
+        GSA_CUDA(cudaMemcpyAsync(via_host[k].data(), hh->partials.p, sizeof(double) * cnt, cudaMemcpyDeviceToHost, hh->stream));
+    }
+    cudaSetDevice(h0->device);
     GSA_CUDA(cudaStreamSynchronize(h0->stream));
     MDBG("partials on host");
     for (int g = 1; g < G; ++g) {
         cudaSetDevice(m->h[g]->device);
         GSA_CUDA(cudaStreamSynchronize(m->h[g]->stream));
     }
+    std::vector<double> host(m->host_sum, m->host_sum + cnt);
+    for (const auto& v : via_host)
+        for (size_t i = 0; i < cnt; ++i) {
+            const int e = (int)(i % nstat);
+            if (e < STAT_DD) {
+                if (e & 1) continue;
+                dd s{host[i], host[i + 1]};
+                dd_add_dd(s, dd{v[i], v[i + 1]});
+                host[i] = s.hi;
+                host[i + 1] = s.lo;
+            } else {
+                host[i] += v[i];
+            }
+        }
     return finalize_host(*opts, host.data(), nout, d, N / opts->nboot, out);
 }
 

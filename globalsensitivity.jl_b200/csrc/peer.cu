@@ -203,6 +203,7 @@ int gsa_peer_connect(gsa_handle* h, int rank, int world, const void* handles) {
     std::lock_guard<std::mutex> lk(h->mu);
     DevGuard guard(h->device);
     PeerState* ps = h->peer;
+    if (ps->peer_dev) return fail(GSA_ERR_INVALID, "gsa_peer_connect: already connected (gsa_peer_export starts a new group)");
     ps->rank = rank;
     ps->world = world;
     ps->peer.assign(world, nullptr);

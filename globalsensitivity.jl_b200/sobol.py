@@ -189,7 +189,8 @@ class PeerGroup:
 
 
 class GsaMulti:
-    """Single-process, multi-device form (gsa_multi): one handle and one NCCL communicator per device.
+    """Single-process, multi-device form (gsa_multi): one handle per device, the partial sums are gathered by one kernel over
+    NVLink peer memory.
 
         m = GsaMulti([0, 1, 2, 3]);  res = m.gsa(DeviceModel("sobol_g", a), Sobol(), A, B)      # A, B on the host"""
 
@@ -496,6 +497,13 @@ def gsa(f, method: Sobol, A, B=None, *, batch: bool = False, Ei_estimator="Janse
 # ---------------------------------------------------------------------------------------------------
 # sharded form (one process per GPU): local partial sums -> all-reduce -> finalize
 # ---------------------------------------------------------------------------------------------------
+def sample(n: int, lb, ub, *, device: bool = False, handle: Optional["GsaHandle"] = None):
+    """QuasiMonteCarlo.sample(n, lb, ub, SobolSample()): the d x n unrandomised Sobol design the reference's other methods draw
+    (call sites src/regression_sensitivity.jl:151, src/delta_sensitivity.jl:170, src/easi_sensitivity.jl:164,
+    src/mutual_information_sensitivity.jl:140) -- K1 with a single matrix, bit-exact."""
+    return generate_design_matrices(n, lb, ub, 1, device=device, handle=handle)[0]
+
+
 def shard_columns(N: int, rank: int, world: int):
     """Contiguous column range [col0, col0+ncols) of rank `rank`."""
     base, rem = divmod(N, world)

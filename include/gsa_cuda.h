@@ -44,7 +44,7 @@ enum {
     GSA_ERR_CUDA = 2,        /* a CUDA runtime/driver call failed */
     GSA_ERR_UNSUPPORTED = 3, /* valid request outside what this build implements */
     GSA_ERR_NOMEM = 4,
-    GSA_ERR_NCCL = 5
+    GSA_ERR_NCCL = 5         /* reserved (no collective library is used any more) */
 };
 
 /* Ei_estimator of the reference (src/sobol_sensitivity.jl:112, :202-236) */
@@ -63,7 +63,7 @@ enum {
 };
 
 typedef struct gsa_handle gsa_handle; /* opaque */
-typedef struct gsa_multi gsa_multi;   /* opaque: one handle + one NCCL communicator per device of a single process */
+typedef struct gsa_multi gsa_multi;   /* opaque: one handle per device of a single process */
 
 /* mirrors `struct Sobol` (reference :77-83) + the call's keyword arguments (:112) */
 typedef struct gsa_sobol_opts {
@@ -190,16 +190,17 @@ GSA_API int gsa_peer_status(gsa_handle* h, int* status);
 GSA_API int gsa_peer_disconnect(gsa_handle* h);
 
 /* ---- single-process, multi-device form (a plain Julia `ccall` from one process) ------------------ */
-/* devices == NULL: devices 0..ndev-1.  Creates one gsa_handle per device and, for ndev > 1, NCCL communicators
- * (ncclCommInitAll; libnccl.so.2 is loaded with dlopen). */
+/* devices == NULL: devices 0..ndev-1.  Creates one gsa_handle per device and enables peer access from the first device to
+ * the others (up to 16 devices). */
 GSA_API int gsa_multi_create(const int* devices, int ndev, gsa_multi** out);
 GSA_API int gsa_multi_destroy(gsa_multi* m);
 GSA_API int gsa_multi_device_count(gsa_multi* m, int* ndev);
 /* the i-th per-device handle (owned by `m`), e.g. for gsa_sobol_design on that device */
 GSA_API int gsa_multi_handle(gsa_multi* m, int i, gsa_handle** out);
 /* gsa(model, Sobol(...), A, B; batch=true) (:110-149 + :169-405) with the HOST design sharded by contiguous column ranges
- * over the devices: every device streams and reduces its shard, ONE grouped ncclAllReduce(sum, fp64) of the
- * nboot*nout*nstat partial sums crosses NVLink, then the host epilogue. */
+ * over the devices: every device streams and reduces its shard, ONE kernel on the first device gathers and adds the
+ * nboot*nout*nstat partial sums of all devices over NVLink peer memory (error-free for the double-double entries) and
+ * writes them to pinned host memory; then the host epilogue. */
 GSA_API int gsa_multi_sobol_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams,
                         const double* A, const double* B, int d, int64_t N, gsa_sobol_result* out);
 

@@ -163,7 +163,7 @@ function gsa_sobol_all_y_analysis(method::Sobol, all_y::VecOrMat{Float64}, d::In
     return r
 end
 
-# ---- one process, all GPUs (gsa_multi_*): contiguous column shards, one grouped ncclAllReduce of the partial sums ----------------
+# ---- one process, all GPUs (gsa_multi_*): contiguous column shards, one gather-and-add kernel over NVLink peer memory for the partial sums ----------------
 mutable struct Multi
     ptr::Ptr{Cvoid}
     function Multi(devices::Vector{<:Integer} = Int[])

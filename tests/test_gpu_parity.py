@@ -233,6 +233,13 @@ def test_p_range_entry():
     assert_parity(res, ref)
 
 
+def test_sample_matches_single_matrix_design():
+    """QuasiMonteCarlo.sample(n, lb, ub, SobolSample()): K1 with one matrix."""
+    lb, ub = np.array([-1.0, 0.0, 2.0, -5.0, 0.5]), np.array([1.0, 3.0, 2.5, 5.0, 0.75])
+    X = g.sample(777, lb, ub)
+    assert X.shape == (5, 777) and np.array_equal(X, gsa_ref.sobol_design(777, lb, ub, 1)[0])
+
+
 # ------------------------------------------------------------------------------------------------ K5 (sharding)
 def test_sharded_partials_are_additive():
     import torch
@@ -476,7 +483,7 @@ def test_user_device_model_from_fatbin(tmp_path):
 
 
 def test_multi_device_single_process(ishigami_design):
-    """gsa_multi: one process, all visible GPUs, one grouped ncclAllReduce of the partial sums.  Runs with
+    """gsa_multi: one process, all visible GPUs, one gather-and-add kernel over NVLink peer memory for the partial sums.  Runs with
     a single device too (then no collective is issued)."""
     import torch
     ndev = torch.cuda.device_count()
