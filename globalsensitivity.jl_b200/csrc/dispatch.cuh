@@ -204,7 +204,7 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
     if (gen)
         return fail(GSA_ERR_UNSUPPORTED, "fused design generation is implemented for product-form models (sobol_g), S1/ST, Jansen1999, d <= 416; "
                                          "use gsa_sobol_design + gsa_sobol_run for this request");
-    if (!generic_only && model == GSA_MODEL_LINEAR && !second && est == GSA_EI_JANSEN1999 && d <= LIN_DMAX) {
+    if (!generic_only && model == GSA_MODEL_LINEAR && d <= LIN_DMAX) {   // every estimator and S2 are moment forms of the same Gram matrix
         p->kind = PLAN_LINEAR;
         p->threads = LIN_THREADS;
         const int NB = (2 * d + 7) / 8;
@@ -217,6 +217,7 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
 #undef GSA_LIN_CASE
         if (!kern) return fail(GSA_ERR_UNSUPPORTED, "linear kernel: no instantiation for %d blocks", NB);
         p->lin_NB = NB;
+        GSA_CUDA(cudaFuncSetAttribute((const void*)linear_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_rec_smem_bytes(LIN_DMAX)));
         p->lin_smem = lin_smem_bytes(NB, un, st);
         if (p->lin_smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->lin_smem));
         int nbl = 0;
@@ -303,7 +304,7 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         linear_gram_reduce_kernel<<<dim3((gs + LGR_X - 1) / LGR_X, nrl), dim3(LGR_X, LGR_Y), 0, h->stream>>>(a.gram, red, gs, g.tpr, t0, t1, rl0);
         LinearRecArgs r;
         r.red = red; r.A = A; r.W = h->params.as<double>(); r.partials = out_partials;
-        r.g = g; r.d = d; r.NB = lin_NB; r.nout = nout; r.nstat = nstat; r.rl_first = rl0;
+        r.g = g; r.d = d; r.NB = lin_NB; r.nout = nout; r.nstat = nstat; r.rl_first = rl0; r.est = est; r.second = second ? 1 : 0;
         linear_records_kernel<<<dim3(nrl, (nout + LREC_OB - 1) / LREC_OB), LREC_OB * LREC_J, lin_rec_smem_bytes(d), h->stream>>>(r);
         h->last_launches += 3;
         GSA_CUDA(cudaGetLastError());

@@ -212,17 +212,29 @@ __global__ void __launch_bounds__(LGR_X* LGR_Y) linear_gram_reduce_kernel(const 
 // groups of LREC_OB outputs); thread (output, j) owns the coordinates j, j + 16: every dot product is a chain of d FMAs, the 16
 // lanes of an output are combined by a butterfly (fixed order).  Launches are serialised on the handle's stream and one thread
 // owns each entry of a record, so the read-modify-write of `partials` is race-free.
+//
+// With fa = yA - y0 = w.a', fb = w.b', delta = b - a (a', b' the shifted rows) every term of every estimator is a moment form:
+//     sum yB delta_k = y0 sd_k + hB_k,   hB_k = sum_l w_l (Sbb - Sba)[l][k]          sum yA delta_k = y0 sd_k + hA_k,   hA_k = sum_l w_l (Sab - Saa)[l][k]
+//     V_k      (:192)  sum yB (yAB_k - yA)          =  w_k (y0 sd_k + hB_k)
+//     Jansen   (:213)  sum (yA - yAB_k)^2            =  w_k^2 DD_kk,              DD = sum delta delta'
+//     Sobol2007(:211)  sum yA (yA - yAB_k)           = -w_k (y0 sd_k + hA_k)
+//     Homma/Janon (:207, :224)  sum yA yAB_k         =  sum yA^2 + w_k (y0 sd_k + hA_k)
+//     Janon    (:219)  sum (yA^2 + yAB_k^2)          =  2 sum yA^2 + 2 w_k (y0 sd_k + hA_k) + w_k^2 DD_kk ;   (:220) sum (yA + yAB_k) = 2 sum yA + w_k sd_k
+//     pairs    (:197)  sum (yBA_k yAB_j - yA yB)     =  w_j (y0 sd_j + hB_j) - w_k (y0 sd_k + hA_k) - w_k w_j DD_kj          (k < j)
 struct LinearRecArgs {
     const double* red;   // [nrep_launch][gs]
     const double* A;     // the launch's A buffer (shift rows)
     const double* W;     // nout x d column-major
     double* partials;    // [nboot][nout][nstat]
     TileGeom g;
-    int d, NB, nout, nstat, rl_first;
+    int d, NB, nout, nstat, rl_first, est, second;
 };
 constexpr int LREC_OB = 16, LREC_J = 16;   // outputs per CTA, lanes per output (d <= 2 * LREC_J)
 static_assert(LIN_DMAX <= 2 * LREC_J, "two coordinates per lane");
-__host__ __device__ inline size_t lin_rec_smem_bytes(int d) { return sizeof(double) * (2 * (size_t)d * (d + 1) + 4 * d + (size_t)d * LREC_OB); }
+// G, H always; HA, DD, AA when the options need them (5 matrices of d x (d+1)); 4 vectors; Wt[d][OB]; hB, hA per (output, k)
+__host__ __device__ inline size_t lin_rec_smem_bytes(int d) {
+    return sizeof(double) * (5 * (size_t)d * (d + 1) + 4 * d + (size_t)d * LREC_OB + 2 * (size_t)LREC_OB * LIN_DMAX);
+}
 
 __device__ __forceinline__ dd dd_from(double x) { return dd{x, 0.0}; }
 __device__ __forceinline__ dd dd_mul_d(dd a, double b) {  // a * b
@@ -231,22 +243,37 @@ __device__ __forceinline__ dd dd_mul_d(dd a, double b) {  // a * b
     e = __fma_rn(a.lo, b, e);
     return quick_two_sum(p, e);
 }
+// shifted sums -> sum y (dd), sum y^2 (dd) of m values:  s' + m y0 ;  q' + 2 y0 s' + m y0^2
+__device__ __forceinline__ void lin_unshift(double s1, double q2, double m, double y0, dd& S, dd& Q) {
+    S = dd_from(s1);
+    dd_add_dd(S, dd_mul_d(dd_from(m), y0));
+    Q = dd_from(q2);
+    dd_add_dd(Q, dd_mul_d(dd_from(2.0 * y0), s1));
+    dd_add_dd(Q, dd_mul_d(dd_mul_d(dd_from(y0), y0), m));
+}
 
 __global__ void __launch_bounds__(LREC_OB* LREC_J) linear_records_kernel(LinearRecArgs a) {
-    extern __shared__ double sg[];  // G[d][d+1] (Uaa + Ubb), H[d][d+1] (Ubb - Uba), g1[d] (sa + sb), h1[d] (sb - sa), D[d], c[d], Wt[d][LREC_OB]
-    const int d = a.d, P = d + 1, DU = 8 * a.NB, gs = lin_gram_size(a.NB);
+    extern __shared__ double sg[];
+    const int d = a.d, P = d + 1, DU = 8 * a.NB, gs = lin_gram_size(a.NB), est = a.est;
+    const bool second = a.second != 0, need_a = second || est != GSA_EI_JANSEN1999;
+    const bool need_ya = est == GSA_EI_HOMMA1996 || est == GSA_EI_JANON2014;
     const int rl = a.rl_first + blockIdx.x, r = a.g.rep_first + rl;
     const double* red = a.red + (size_t)blockIdx.x * gs;
     const double* S = red + DU * DU;
     const double m = red[DU * DU + DU];   // samples of the replicate in this launch
     if (m == 0.0) return;
-    double* G = sg;
-    double* H = G + d * P;
-    double* g1 = H + d * P;
-    double* h1 = g1 + d;
-    double* D = h1 + d;
-    double* c = D + d;
-    double* Wt = c + d;
+    double* G = sg;              // Saa + Sbb
+    double* H = G + d * P;       // Sbb - Sba
+    double* HA = H + d * P;      // Sab - Saa
+    double* DD = HA + d * P;     // sum delta delta'
+    double* AA = DD + d * P;     // Saa
+    double* g1 = AA + d * P;     // sa + sb
+    double* sd = g1 + d;         // sb - sa
+    double* sa = sd + d;
+    double* c = sa + d;
+    double* Wt = c + d;          // [d][LREC_OB]
+    double* hBs = Wt + d * LREC_OB;             // [LREC_OB][LIN_DMAX]
+    double* hAs = hBs + LREC_OB * LIN_DMAX;
     const int ol = threadIdx.x / LREC_J, j = threadIdx.x % LREC_J, o = blockIdx.y * LREC_OB + ol;
     const bool live = o < a.nout;
     // U is stored block-upper-triangular: entry (l, k) lives at [l][k] when block(l) <= block(k), else at [k][l]
@@ -254,13 +281,17 @@ __global__ void __launch_bounds__(LREC_OB* LREC_J) linear_records_kernel(LinearR
     const int64_t cs = lin_shift_col(a.g, r);
     for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
         const int l = e / d, k = e - l * d;
-        G[l * P + k] = Us(l, k) + Us(d + l, d + k);
-        H[l * P + k] = Us(d + l, d + k) - Us(d + l, k);
+        const double saa = Us(l, k), sbb = Us(d + l, d + k), sba = Us(d + l, k), sab = Us(l, d + k);
+        G[l * P + k] = saa + sbb;
+        H[l * P + k] = sbb - sba;
+        if (need_a) HA[l * P + k] = sab - saa;
+        DD[l * P + k] = ((sbb - sba) - sab) + saa;
+        if (need_ya) AA[l * P + k] = saa;
     }
     for (int k = threadIdx.x; k < d; k += blockDim.x) {
         g1[k] = S[k] + S[d + k];
-        h1[k] = S[d + k] - S[k];
-        D[k] = (Us(d + k, d + k) - 2.0 * Us(k, d + k)) + Us(k, k);
+        sd[k] = S[d + k] - S[k];
+        sa[k] = S[k];
         c[k] = __ldg(a.A + (size_t)(cs - a.g.buf_col0) * d + k);
     }
     for (int e = threadIdx.x; e < d * LREC_OB; e += blockDim.x) {
@@ -268,44 +299,82 @@ __global__ void __launch_bounds__(LREC_OB* LREC_J) linear_records_kernel(LinearR
         Wt[e] = oo < a.nout ? __ldg(a.W + oo + (size_t)a.nout * l) : 0.0;
     }
     __syncthreads();
-    // phase 1: y0 = w.c ; S' = w.g1 ; Q' = w' G w  -- lane j adds the rows l = j, j + 16, then a 16-lane butterfly
-    double y0 = 0.0, S1 = 0.0, Q = 0.0;
+    // phase 1: y0 = w.c ; S' = w.g1 ; Q' = w' G w (and the same of yA alone) -- lane j adds the rows l = j, j + 16, then a butterfly
+    double y0 = 0.0, S1 = 0.0, Q = 0.0, SA1 = 0.0, QA = 0.0;
     for (int l = j; l < d; l += LREC_J) {
         const double wl = Wt[l * LREC_OB + ol];
-        double row = 0.0;
+        double row = 0.0, rowa = 0.0;
         for (int k = 0; k < d; ++k) row = fma(Wt[k * LREC_OB + ol], G[l * P + k], row);
+        if (need_ya)
+            for (int k = 0; k < d; ++k) rowa = fma(Wt[k * LREC_OB + ol], AA[l * P + k], rowa);
         y0 = fma(wl, c[l], y0);
         S1 = fma(wl, g1[l], S1);
         Q = fma(wl, row, Q);
+        SA1 = fma(wl, sa[l], SA1);
+        QA = fma(wl, rowa, QA);
     }
 #pragma unroll
     for (int x = 1; x < LREC_J; x <<= 1) {
         y0 += __shfl_xor_sync(0xffffffffu, y0, x);
         S1 += __shfl_xor_sync(0xffffffffu, S1, x);
         Q += __shfl_xor_sync(0xffffffffu, Q, x);
+        SA1 += __shfl_xor_sync(0xffffffffu, SA1, x);
+        QA += __shfl_xor_sync(0xffffffffu, QA, x);
     }
-    if (!live) return;
-    double* rec = a.partials + ((size_t)r * a.nout + o) * a.nstat;
-    if (j == 0) {
-        // un-shift exactly: sum y = S' + 2m y0 ; sum y^2 = Q' + 2 y0 S' + 2m y0^2   (double-double)
-        dd sy = dd_from(S1);
-        dd_add_dd(sy, dd_mul_d(dd_from(2.0 * m), y0));
-        dd t = dd_mul_d(dd_from(y0), y0);              // y0^2
-        dd syy = dd_from(Q);
-        dd_add_dd(syy, dd_mul_d(dd_from(2.0 * y0), S1));
-        dd_add_dd(syy, dd_mul_d(t, 2.0 * m));
+    double* rec = a.partials + ((size_t)r * a.nout + (live ? o : 0)) * a.nstat;
+    dd sya{0.0, 0.0}, syya{0.0, 0.0};   // sum yA, sum yA^2 of this launch's samples
+    if (need_ya) lin_unshift(SA1, QA, m, y0, sya, syya);
+    if (live && j == 0) {
+        dd sy, syy;
+        lin_unshift(S1, Q, 2.0 * m, y0, sy, syy);
         dd p0{rec[0], rec[1]}, p1{rec[2], rec[3]};
         dd_add_dd(p0, sy);
         dd_add_dd(p1, syy);
         rec[0] = p0.hi; rec[1] = p0.lo; rec[2] = p1.hi; rec[3] = p1.lo;
+        if (need_ya) {
+            dd p2{rec[4], rec[5]}, p3{rec[6], rec[7]};
+            dd_add_dd(p2, sya);
+            dd_add_dd(p3, syya);
+            rec[4] = p2.hi; rec[5] = p2.lo; rec[6] = p3.hi; rec[7] = p3.lo;
+        }
     }
     // phase 2: the coordinates k = j, j + 16 of this output
     for (int k = j; k < d; k += LREC_J) {
         const double wk = Wt[k * LREC_OB + ol];
-        double hv = y0 * h1[k];
-        for (int l = 0; l < d; ++l) hv = fma(Wt[l * LREC_OB + ol], H[l * P + k], hv);
-        rec[stat_v(k)] += wk * hv;                  // sum yB (yAB_k - yA)       (:192)
-        rec[stat_e(d, 0, k)] += wk * wk * D[k];     // sum (yA - yAB_k)^2        (:213)
+        double hb = 0.0, ha = 0.0;
+        for (int l = 0; l < d; ++l) hb = fma(Wt[l * LREC_OB + ol], H[l * P + k], hb);
+        if (need_a)
+            for (int l = 0; l < d; ++l) ha = fma(Wt[l * LREC_OB + ol], HA[l * P + k], ha);
+        const double yb_d = fma(y0, sd[k], hb), ya_d = fma(y0, sd[k], ha);   // sum yB delta_k, sum yA delta_k
+        hBs[ol * LIN_DMAX + k] = yb_d;
+        hAs[ol * LIN_DMAX + k] = ya_d;
+        if (live) {
+            const double dkk = wk * wk * DD[k * P + k];
+            rec[stat_v(k)] += wk * yb_d;                                                    // :192
+            if (est == GSA_EI_JANSEN1999) rec[stat_e(d, 0, k)] += dkk;                      // :213
+            else if (est == GSA_EI_SOBOL2007) rec[stat_e(d, 0, k)] += -(wk * ya_d);         // :211
+            else {
+                const double syya_d = syya.hi + syya.lo;
+                rec[stat_e(d, 0, k)] += syya_d + wk * ya_d;                                 // :207 / :224
+                if (est == GSA_EI_JANON2014) {
+                    rec[stat_e(d, 1, k)] += (2.0 * syya_d + 2.0 * (wk * ya_d)) + dkk;       // :219
+                    rec[stat_e(d, 2, k)] += 2.0 * (sya.hi + sya.lo) + wk * sd[k];           // :220
+                }
+            }
+        }
+    }
+    if (!second) return;
+    __syncthreads();
+    // phase 3: the pairs k < jj of this output, 16 lanes take them round-robin
+    if (live) {
+        const int pbase = stat_pair_base(d, est), npairs = d * (d - 1) / 2;
+        int k = 0, first = 0;   // pairs of row k start at index `first`
+        for (int p = j; p < npairs; p += LREC_J) {
+            while (p >= first + (d - 1 - k)) { first += d - 1 - k; ++k; }
+            const int jj = k + 1 + (p - first);
+            const double wk = Wt[k * LREC_OB + ol], wj = Wt[jj * LREC_OB + ol];
+            rec[pbase + p] += (wj * hBs[ol * LIN_DMAX + jj] - wk * hAs[ol * LIN_DMAX + k]) - (wk * wj) * DD[k * P + jj];   // :197
+        }
     }
 }
 #endif  // __CUDACC__

@@ -393,6 +393,21 @@ def test_linear_gram_kernel(d, nout, N, nboot):
         assert np.abs(np.reshape(res.ST, (nout, d)) - S).max() < 2e-2
 
 
+@pytest.mark.parametrize("est", so.EI_ESTIMATORS)
+@pytest.mark.parametrize("d,nout,N,nboot", [(20, 40, 8192, 1), (7, 3, 5001, 3), (32, 2, 3000, 1), (1, 2, 1000, 2)])
+def test_linear_all_estimators_and_second_order(est, d, nout, N, nboot):
+    """Every Ei_estimator and the second-order indices of a linear multi-output model are moment forms of the same Gram matrix
+    (fused_linear.cuh): no limit on the number of outputs, nothing evaluated per sample and output."""
+    rng = np.random.default_rng(100 * d + nout)
+    W = rng.normal(size=(nout, d)) + 0.5
+    lb, ub = -rng.random(d), rng.random(d) + 1.0
+    A, B = gsa_ref.sobol_design(N, lb, ub)
+    for order in ((0, 1), (0, 1, 2)):
+        ref = gsa_ref.gsa_sobol("linear", W, A, B, order=order, nboot=nboot, Ei_estimator=est)
+        res = g.gsa(g.DeviceModel("linear", W), g.Sobol(order=list(order), nboot=nboot), A, B, batch=True, Ei_estimator=est)
+        assert_parity(res, ref, what=(est, d, nout, N, nboot, order))
+
+
 def test_linear_large_offset_inputs():
     """mean >> spread: the tile-local shift + double-double recentring keeps the variance exact."""
     d, nout, N = 6, 5, 50000
