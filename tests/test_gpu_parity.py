@@ -526,6 +526,34 @@ def test_multi_device_single_process(ishigami_design):
     m.close()
 
 
+def test_plain_c_client_of_the_abi(tmp_path):
+    """include/gsa_cuda.h from plain C (gcc, no Python/torch/CUDA headers on the client side): same numbers as the Python mirror."""
+    import subprocess
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    pkg = os.path.join(root, "globalsensitivity.jl_b200")
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.check_call(["gcc", "-O1", "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c_abi_smoke.c"),
+                           "-o", exe, "-L", pkg, "-lgsa_cuda", "-Wl,-rpath," + pkg, "-lm"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d, n, nboot = 4, 40000, 4
+    A, B = g.generate_design_matrices(n, -np.pi * np.ones(d), np.pi * np.ones(d))
+    res = g.gsa(g.DeviceModel("ishigami", [7.0, 0.1]), g.Sobol(order=[0, 1, 2], nboot=nboot), A, B, batch=True)
+    ref = gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=(0, 1, 2), nboot=nboot)
+    got = {"S1": np.zeros(d), "S1c": np.zeros(d), "ST": np.zeros(d), "STc": np.zeros(d), "S2": np.zeros((d, d)), "S2c": np.zeros((d, d))}
+    for line in r.stdout.splitlines():
+        t = line.split()
+        if t[0] in ("S1", "ST"):
+            got[t[0]][int(t[1])], got[t[0] + "c"][int(t[1])] = float(t[2]), float(t[3])
+        elif t[0] == "S2":
+            got["S2"][int(t[1]), int(t[2])], got["S2c"][int(t[1]), int(t[2])] = float(t[3]), float(t[4])
+    assert "ERR" in r.stdout
+    for name, mine, theirs in (("S1", got["S1"], res.S1), ("ST", got["ST"], res.ST), ("S2", got["S2"], res.S2),
+                               ("S1c", got["S1c"], res.S1_Conf_Int), ("STc", got["STc"], res.ST_Conf_Int), ("S2c", got["S2c"], res.S2_Conf_Int)):
+        assert np.array_equal(mine, theirs), name                     # the same library, the same kernels: bit-identical
+    assert_parity(res, ref)
+
+
 def test_peer_allreduce_two_ranks():
     """K5 over NVLink peer memory (csrc/peer.cu), one process per GPU under torchrun: sums equal NCCL's, are bit-identical on
     every rank, and a sharded analysis equals the single-GPU one.  With one GPU the same protocol runs with world = 1."""

@@ -26,6 +26,9 @@ CONFIGS = {
     "c3": dict(model=("sobol_g", [0, 1, 4.5, 9, 99, 99, 99, 99]), d=8, N=1 << 22, order=[0, 1, 2], nboot=1, lb=0.0, ub=1.0),
     "c4": dict(model=("linear", W_c4()), d=20, N=1 << 22, order=[0, 1], nboot=1, lb=0.0, ub=1.0),
     "p20": dict(model=("sobol_g", [0, 1, 4.5, 9] + [99.0] * 16), d=20, N=1 << 21, order=[0, 1, 2], nboot=1, lb=0.0, ub=1.0),   # second order, d > 8
+    # the replicate ("bootstrap") path at sizes that are not launch-latency-bound
+    "b5": dict(model=("sobol_g", [0, 1, 4.5, 9] + [99.0] * 96), d=100, N=1 << 24, order=[0, 1], nboot=100, lb=0.0, ub=1.0),
+    "b2": dict(model=("ishigami", [7.0, 0.1]), d=3, N=1 << 25, order=[0, 1, 2], nboot=1000, lb=-np.pi, ub=np.pi),
     "c5": dict(model=("sobol_g", [0, 1, 4.5, 9] + [99.0] * 96), d=100, N=1 << 24, order=[0, 1], nboot=1, lb=0.0, ub=1.0),
 }
 
