@@ -13,12 +13,15 @@
 //     sum (yBA_k yAB_j - yA yB) = [P'_kj - sum fa' fb'] + c [(sum p_k + sum q_j) - (sum fa' + sum fb')],   fa' = yA - c, fb' = yB - c.
 // The first- and total-order terms are formed per sample exactly as the reference forms them (difference first, :192, :213).
 //
-// Two sources feed the same engine:
-//   * product-form models (Sobol G, BASELINE config 3): lane (g, t) loads coordinate 8*blk+g of rows A_s, B_s (the 8 lanes of a
-//     sample read 64 contiguous bytes), evaluates its factors, and one xor butterfly over the 8 lanes of the sample gives it the
-//     product of all OTHER factors (no division: a factor may be 0), hence yAB_i = gB_i * othersA_i, yBA_i = gA_i * othersB_i;
-//   * a precomputed Y = f(all_points) (estimator-only entry): every warp streams chunks of 32 samples of all 2d+2 blocks into
-//     a private shared-memory tile (lane = sample: 256 contiguous bytes per block and copy) and reads the fragments from there.
+// Three sources feed the same engine (template parameter SRC):
+//   * PRODUCT -- product-form models (Sobol G), 8 < d <= 32: lane (g, t) loads coordinate 8*blk+g of rows A_s, B_s (the 8 lanes
+//     of a sample read 64 contiguous bytes), evaluates its factors, and one xor butterfly over the 8 lanes of the sample gives it
+//     the product of all OTHER factors (no division: a factor may be 0), hence yAB_i = gB_i * othersA_i, yBA_i = gA_i * othersB_i;
+//   * PRODUCT_TILE -- the same models for even d <= 8 (BASELINE config 3): with a single block the butterfly would dominate, so
+//     lane L evaluates ALL 2d+2 values of sample L of a 32-sample chunk from prefix/suffix products (no shuffles), writes them
+//     to a warp-private tile, and the mma fragments are read back from the tile;
+//   * Y -- a precomputed Y = f(all_points) (estimator-only entry): every warp streams chunks of 32 samples of all 2d+2 blocks
+//     into such a tile (lane = sample: 256 contiguous bytes per block and copy) and reads the fragments from there.
 // Operands of future steps are in flight as cp.async copies (per-thread ring / per-warp tiles): no block-wide barrier.
 #pragma once
 #include "gsa_common.cuh"
@@ -64,7 +67,7 @@ inline size_t pm_ring_doubles_y(int d, int ST) { return (size_t)PMMA_NW * ST * (
 __host__ __device__ inline size_t pm_ring_doubles_tile(int d, int ST) { return (size_t)PMMA_NW * ((size_t)ST * 2 * PM_CH * d + (2 + 2 * d) * PM_PITCH); }
 inline size_t pm_smem_bytes(size_t ring_doubles, int NB) { return sizeof(double) * (ring_doubles + 64 * NB * NB + 4 * 8 * NB + 8); }
 
-// NB = 8-coordinate blocks (d <= 8*NB); UN = warp steps per load group (product source); ST = stages in flight
+// NB = 8-coordinate blocks (d <= 8*NB); UN = warp steps per load group (PRODUCT) or d itself (PRODUCT_TILE); ST = stages in flight
 enum { PM_SRC_PRODUCT = 0, PM_SRC_Y = 1, PM_SRC_PRODUCT_TILE = 2 };
 template <int SRC, int NB, int UN, int ST>
 __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
