@@ -345,6 +345,36 @@ def test_pairs_mma_sources_agree(monkeypatch):
     assert_parity(g.gsa(model, method, At, Bt, batch=True), ref, what="unaligned")
 
 
+def test_pairs_mma_large_analytic_and_additive():
+    """Second order at a size the oracle cannot materialise (d = 20, N = 2^20: all_points would be 7 GB): analytic Sobol-G indices
+    (S2_ij = V_i V_j / V) and shard additivity of the mma kernel's records; the same on the model's Y is not
+    possible at this size, so the Y source is checked against the fused source on a slice."""
+    import torch
+    d, N = 20, 1 << 20
+    a = np.array([0.0, 0.5, 1.0, 2.0, 4.5, 9.0] + [50.0] * 14)
+    model, method = g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2])
+    A, B = g.generate_design_matrices(N, np.zeros(d), np.ones(d), 2, device=True)
+    res = g.gsa(model, method, A, B, batch=True)
+    Vi = 1.0 / (3.0 * (1.0 + a) ** 2)
+    V = np.prod(1.0 + Vi) - 1.0
+    assert np.abs(res.S1 - Vi / V).max() < 2e-3 and np.abs(res.ST - Vi * np.prod(1.0 + Vi) / (1.0 + Vi) / V).max() < 2e-3
+    S2 = np.triu(np.outer(Vi, Vi) / V, 1)
+    assert np.abs(res.S2 - S2).max() < 3e-3 and np.all(np.tril(res.S2) == 0.0)
+    total = None
+    for rank in range(3):
+        c0, nc = g.shard_columns(N, rank, 3)
+        p = g.sobol_partials(model, method, A[:, c0:c0 + nc], B[:, c0:c0 + nc], N, c0)
+        total = p.clone() if total is None else total + p
+    torch.cuda.synchronize()
+    assert_parity(g.sobol_finalize(method, total, d, N), res)
+    n = 1 << 14                                                   # Y source against the fused source and the oracle on a slice
+    An, Bn = A[:, :n].cpu().numpy(), B[:, :n].cpu().numpy()
+    Y = gsa_ref.model_batch("sobol_g", a, gsa_ref.all_points(An, Bn, 1, True))
+    ref = gsa_ref.analyze_y(Y, d, n, order=(0, 1, 2))
+    assert_parity(g.gsa_sobol_all_y_analysis(method, Y, d, n), ref, what="Y source")
+    assert_parity(g.gsa(model, method, An, Bn, batch=True), ref, what="fused source")
+
+
 def test_pairs_mma_mean_dominates():
     """Outputs with mean >> spread (all a_k = 99: y = 1 +- 1e-2): the shifted products keep the pair sums exact enough."""
     d, N = 8, 1 << 17
