@@ -37,6 +37,7 @@ struct FusedPlan {
     int lin_NB = 0;              // 8-coordinate blocks of the stacked [a; b] vector (linear Gram kernel)
     bool writes_partials() const { return kind == PLAN_LINEAR; }   // the plan adds its records to `out_partials` itself
     double* out_partials = nullptr;
+    double* rec_base = nullptr;   // where the tile records go: h->tile_rec, or straight into `partials` when a replicate is one tile
 
     int prepare(gsa_handle* h, const double* params, int np);
     int launch(gsa_handle* h, const double* A, const double* B, const TileGeom& g, int t0, int t1);
@@ -276,18 +277,19 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
 inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, const TileGeom& g, int t0, int t1) {
     if (t1 <= t0) return GSA_OK;
     const int grid = std::min(t1 - t0, resident);
+    double* recs = rec_base ? rec_base : h->tile_rec.as<double>();
     GSA_CUDA(cudaEventRecord(h->evk0, h->stream));
     if (kind == PLAN_GENERIC) {
         GenericArgs a;
-        a.A = A; a.B = B; a.params = h->params.as<double>(); a.tile_rec = h->tile_rec.as<double>();
+        a.A = A; a.B = B; a.params = h->params.as<double>(); a.tile_rec = recs;
         a.g = g; a.d = d; a.np = np; a.nout = nout; a.nstat = nstat; a.est = est; a.t_begin = t0; a.t_end = t1;
         void* kargs[] = {&a};
         GSA_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, h->stream));   // also takes cudaKernel_t handles
     }
     else if (kind == PLAN_SMALL_ISHIGAMI)
-        return launch_small_ishigami(h, d, second, est, A, B, pa, pb, g, t0, t1, nstat, h->tile_rec.as<double>());
+        return launch_small_ishigami(h, d, second, est, A, B, pa, pb, g, t0, t1, nstat, recs);
     else if (kind == PLAN_SMALL_SOBOLG)
-        return launch_small_sobolg(h, d, second, est, A, B, h->aux.as<double2>(), g, t0, t1, nstat, h->tile_rec.as<double>());
+        return launch_small_sobolg(h, d, second, est, A, B, h->aux.as<double2>(), g, t0, t1, nstat, recs);
     else if (kind == PLAN_LINEAR) {
         // moments per tile -> moments per replicate of this launch -> records added to `partials` (no tile records, no stage 2)
         const int gs = lin_gram_size(lin_NB);
@@ -312,7 +314,7 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
     }
     else if (kind == PLAN_PAIRS_MMA) {
         PairsArgs a{};
-        a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = h->tile_rec.as<double>(); a.nout = 1;
+        a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = recs; a.nout = 1;
         a.g = g; a.d = d; a.nstat = nstat; a.est = est; a.t_begin = t0; a.t_end = t1;
         void* kargs[] = {&a};
         const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
@@ -321,7 +323,7 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
     }
     else if (kind == PLAN_PRODUCT) {
         ProductArgs a;
-        a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = h->tile_rec.as<double>();
+        a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = recs;
         a.g = g; a.d = d; a.nstat = nstat; a.t_begin = t0; a.t_end = t1;
         a.V = h->vtab.as<uint32_t>(); a.box = h->lbub.as<double2>(); a.first = gen_first; a.nboot = gen_nboot; a.unit_box = gen_unit_box;
         ((ProductKernel)kernel)<<<grid, threads, smem, h->stream>>>(a);

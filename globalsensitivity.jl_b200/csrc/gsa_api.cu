@@ -350,8 +350,14 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         }
         g.ntiles = nrep * g.tpr;
         if ((int64_t)nrep * g.tpr > (int64_t)INT32_MAX / 2) return fail(GSA_ERR_UNSUPPORTED, "too many tiles (%lld)", (long long)nrep * g.tpr);
-        const bool direct = plan.writes_partials();   // the plan's own kernels add per-replicate records to `partials`
+        bool direct = plan.writes_partials();   // the plan's own kernels add per-replicate records to `partials`
         plan.out_partials = partials;
+        if (!direct && !host_in && g.tpr == 1) {
+            // one tile per replicate and one launch (many short replicates: BASELINE config 2): the tile record IS the replicate's
+            // partial sum, so the kernel writes it straight into `partials` (zeroed above) -- no tile records, no stage-2 launch
+            plan.rec_base = partials + (size_t)g.rep_first * recsz;
+            direct = true;
+        }
         if (!direct && (rc = h->tile_rec.reserve(sizeof(double) * (size_t)g.ntiles * recsz))) return rc;
         // tiles that intersect the shard form one contiguous index range [t_lo, t_hi); the others are all-zero records
         const int t_lo = (int)((col0 - (int64_t)g.rep_first * n) / g.ts);
