@@ -95,37 +95,38 @@ static int plan_generic(gsa_handle* h, FusedPlan* p) {
 using ProductKernel = void (*)(ProductArgs);
 static const int kProdCpl[] = {1, 2, 3, 4, 6, 8, 10, 13};
 
-template <int T, bool GEN>
+template <int T, bool GEN, bool JANSEN>
 static ProductKernel product_kernel_T(int cpl) {
     switch (cpl) {
-        case 8: return fused_product_kernel<T, 8, GEN>;
-        case 10: return fused_product_kernel<T, 10, GEN>;
-        case 13: return fused_product_kernel<T, 13, GEN>;
+        case 8: return fused_product_kernel<T, 8, GEN, JANSEN>;
+        case 10: return fused_product_kernel<T, 10, GEN, JANSEN>;
+        case 13: return fused_product_kernel<T, 13, GEN, JANSEN>;
         default: return nullptr;
     }
 }
-template <bool GEN>
+template <bool GEN, bool JANSEN>
 static ProductKernel product_kernel_sel(int T, int cpl) {
     switch (T) {
         case 1:
             switch (cpl) {
-                case 1: return fused_product_kernel<1, 1, GEN>;
-                case 2: return fused_product_kernel<1, 2, GEN>;
-                case 3: return fused_product_kernel<1, 3, GEN>;
-                case 4: return fused_product_kernel<1, 4, GEN>;
-                case 6: return fused_product_kernel<1, 6, GEN>;
-                default: return product_kernel_T<1, GEN>(cpl);
+                case 1: return fused_product_kernel<1, 1, GEN, JANSEN>;
+                case 2: return fused_product_kernel<1, 2, GEN, JANSEN>;
+                case 3: return fused_product_kernel<1, 3, GEN, JANSEN>;
+                case 4: return fused_product_kernel<1, 4, GEN, JANSEN>;
+                case 6: return fused_product_kernel<1, 6, GEN, JANSEN>;
+                default: return product_kernel_T<1, GEN, JANSEN>(cpl);
             }
-        case 2: return product_kernel_T<2, GEN>(cpl);
-        case 4: return product_kernel_T<4, GEN>(cpl);
-        case 8: return product_kernel_T<8, GEN>(cpl);
-        case 16: return product_kernel_T<16, GEN>(cpl);
-        case 32: return product_kernel_T<32, GEN>(cpl);
+        case 2: return product_kernel_T<2, GEN, JANSEN>(cpl);
+        case 4: return product_kernel_T<4, GEN, JANSEN>(cpl);
+        case 8: return product_kernel_T<8, GEN, JANSEN>(cpl);
+        case 16: return product_kernel_T<16, GEN, JANSEN>(cpl);
+        case 32: return product_kernel_T<32, GEN, JANSEN>(cpl);
         default: return nullptr;
     }
 }
-static ProductKernel product_kernel_for(int T, int cpl, bool gen = false) {
-    return gen ? product_kernel_sel<true>(T, cpl) : product_kernel_sel<false>(T, cpl);
+static ProductKernel product_kernel_for(int T, int cpl, bool gen = false, bool jansen = true) {
+    if (!jansen) return gen ? nullptr : product_kernel_sel<false, false>(T, cpl);
+    return gen ? product_kernel_sel<true, true>(T, cpl) : product_kernel_sel<false, true>(T, cpl);
 }
 
 static bool product_shape(int d, int* T, int* cpl) {
@@ -147,7 +148,7 @@ static bool product_shape(int d, int* T, int* cpl) {
 
 static int plan_product(gsa_handle* h, FusedPlan* p) {
     p->kind = PLAN_PRODUCT;
-    p->kernel = (const void*)product_kernel_for(p->prod_T, p->prod_CPL, p->gen);
+    p->kernel = (const void*)product_kernel_for(p->prod_T, p->prod_CPL, p->gen, p->est == GSA_EI_JANSEN1999);
     p->threads = PROD_THREADS;
     const int slots = p->prod_T * p->prod_CPL;
     p->smem = sizeof(double) * (2 * slots + (PROD_THREADS / 32) * (2 * slots + 8) + (p->gen ? 2 * slots + (32 * (2 * slots + 1) + 1) / 2 : 0));
@@ -200,7 +201,8 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
     p->nstat = stat_count(d, est, second);
     const char* force = getenv("GSA_FORCE_GENERIC");   // testing knob: always take the generic kernel
     const bool generic_only = force && atoi(force) != 0;
-    if (!generic_only && model == GSA_MODEL_SOBOL_G && !second && est == GSA_EI_JANSEN1999 && product_shape(d, &p->prod_T, &p->prod_CPL))
+    const bool one_term = est == GSA_EI_JANSEN1999 || (!gen && (est == GSA_EI_SOBOL2007 || est == GSA_EI_HOMMA1996));
+    if (!generic_only && model == GSA_MODEL_SOBOL_G && !second && one_term && product_shape(d, &p->prod_T, &p->prod_CPL))
         return plan_product(h, p);
     if (gen)
         return fail(GSA_ERR_UNSUPPORTED, "fused design generation is implemented for product-form models (sobol_g), S1/ST, Jansen1999, d <= 416; "
@@ -324,7 +326,7 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
     else if (kind == PLAN_PRODUCT) {
         ProductArgs a;
         a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = recs;
-        a.g = g; a.d = d; a.nstat = nstat; a.t_begin = t0; a.t_end = t1;
+        a.g = g; a.d = d; a.nstat = nstat; a.t_begin = t0; a.t_end = t1; a.est = est;
         a.V = h->vtab.as<uint32_t>(); a.box = h->lbub.as<double2>(); a.first = gen_first; a.nboot = gen_nboot; a.unit_box = gen_unit_box;
         ((ProductKernel)kernel)<<<grid, threads, smem, h->stream>>>(a);
     }

@@ -12,7 +12,7 @@
 //     others = prod of the OTHER lanes' A-products   (xor butterfly, log2 T shuffles; also yields yA, yB)
 //     yAB_k  = (others * prod_{i'<i} gA[i']) * gB[i] * prod_{i'>i} gA[i']
 //     V[i] += yB (yAB_k - yA)        (reference src/sobol_sensitivity.jl:192)
-//     E[i] += (yA - yAB_k)^2         (:213, Jansen1999)
+//     E[i] += (yA - yAB_k)^2         (:213, Jansen1999;  yA (yA - yAB_k) for Sobol2007 :211,  yA yAB_k for Homma1996 :207)
 // Accumulators stay in registers for the whole tile; one butterfly + shared-memory combine per tile, in a fixed
 // order (bitwise reproducible).  The AB_k matrices of fuse_designs (:94-108) never exist.
 #pragma once
@@ -27,6 +27,7 @@ struct ProductArgs {
     double* tile_rec;     // [ntiles][nstat]
     TileGeom g;
     int d, nstat, t_begin, t_end;
+    int est;              // GSA_EI_* (kernels with JANSEN = false: Sobol2007 or Homma1996)
     // GEN only (K1 fused in: the design is generated, never read): gsa(f, ::Sobol, p_range; samples) (:407-417)
     const uint32_t* V;    // [2*nboot*d][32] direction numbers of the 2*nboot*d-dimensional sequence
     const double2* box;   // [d] (ub-lb, lb)
@@ -50,8 +51,12 @@ constexpr size_t product_smem_doubles() {
 // GEN = true: the kernel GENERATES the Sobol points of the samples it evaluates (K1 fused into K2+K3): no HBM reads at all.
 // A group then owns a CONTIGUOUS run of samples, so consecutive points differ by one direction number per coordinate
 // (Gray code: x ^= V[j][ctz(q+1)]); the table of the replicate's 2d dimensions sits transposed in shared memory.
-template <int T, int CPL, bool GEN>
+// JANSEN = false: the total-order term is sum yA (yA - yAB_k) (Sobol2007, :211) or sum yA yAB_k (Homma1996, :207) instead of
+// sum (yA - yAB_k)^2 (:213) -- one accumulator per coordinate either way, so the same kernel serves all three (the headline
+// instantiation keeps its code unchanged; Janon2014 needs three terms per coordinate and stays on the generic kernel).
+template <int T, int CPL, bool GEN, bool JANSEN = true>
 __global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fused_product_kernel(ProductArgs a) {
+    const bool sobol2007 = a.est == GSA_EI_SOBOL2007;   // (only read when !JANSEN)
     constexpr int NW = PROD_THREADS / 32;
     constexpr int NG = PROD_THREADS / T;  // sample groups per CTA
     constexpr int SLOTS = T * CPL;        // padded coordinate count
@@ -182,7 +187,8 @@ __global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fu
                 suf *= gA[i];
                 const double df = yAB - yA;
                 V[i] = fma(yB, df, V[i]);  // :192
-                E[i] = fma(df, df, E[i]);  // :213
+                if constexpr (JANSEN) E[i] = fma(df, df, E[i]);  // :213
+                else E[i] = fma(yA, sobol2007 ? -df : yAB, E[i]);  // :211 / :207
             }
             if (T == 1) {
                 dd_add(sA1, yA); dd_add_sq(sA2, yA);

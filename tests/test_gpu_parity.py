@@ -280,6 +280,21 @@ def test_product_path_matches_generic_path(monkeypatch):
 
 
 @pytest.mark.parametrize("est", so.EI_ESTIMATORS)
+@pytest.mark.parametrize("d,N,nboot", [(100, 8000, 2), (5, 30011, 1), (40, 12345, 3)])
+def test_product_kernel_all_estimators(est, d, N, nboot):
+    """Config-5-type models with every Ei_estimator: Jansen1999, Sobol2007 and Homma1996 share the product-form kernel (one
+    accumulator per coordinate each); Janon2014 takes the generic kernel.  Host and device inputs."""
+    import torch
+    a = np.array(([0.0, 1.0, 4.5, 9.0] + [99.0] * d)[:d])
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, nboot=nboot, Ei_estimator=est)
+    model, method = g.DeviceModel("sobol_g", a), g.Sobol(nboot=nboot)
+    assert_parity(g.gsa(model, method, A, B, batch=True, Ei_estimator=est), ref, what=(est, d, "host"))
+    At, Bt = torch.from_numpy(np.ascontiguousarray(A)).cuda(), torch.from_numpy(np.ascontiguousarray(B)).cuda()
+    assert_parity(g.gsa(model, method, At, Bt, batch=True, Ei_estimator=est), ref, what=(est, d, "device"))
+
+
+@pytest.mark.parametrize("est", so.EI_ESTIMATORS)
 @pytest.mark.parametrize("d,second,nboot", [(3, False, 1), (3, True, 1000), (4, False, 7)])
 def test_ishigami_small_kernels(est, d, second, nboot):
     """BASELINE configs 1 and 2 shapes (d = 3; README.md:46-56) through the thread-per-sample register kernel."""
