@@ -163,36 +163,48 @@ static int plan_product(gsa_handle* h, FusedPlan* p) {
 // ---- second-order pair sums on the FP64 tensor-core path (fused_pairs_mma.cuh) ----------------------
 constexpr int PMMA_UN = 2, PMMA_ST = 4;
 inline int pmma_y_stages(int NB) { return NB == 1 ? 3 : 2; }   // warp tiles of (2+2d) * 36 doubles per stage: two CTAs per SM beat deeper rings
-static const void* pairs_mma_kernel_product(int NB, size_t* smem) {
+template <bool J>
+static const void* pairs_mma_kernel_product_j(int NB, size_t* smem) {
     switch (NB) {
-#define GSA_PM(NBV) case NBV: *smem = pm_smem_bytes(pm_ring_doubles_product<NBV, PMMA_UN, PMMA_ST>(), NBV); return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT, NBV, PMMA_UN, PMMA_ST>;
+#define GSA_PM(NBV) case NBV: *smem = pm_smem_bytes(pm_ring_doubles_product<NBV, PMMA_UN, PMMA_ST>(), NBV); return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT, NBV, PMMA_UN, PMMA_ST, J>;
         GSA_PM(1) GSA_PM(2) GSA_PM(3) GSA_PM(4)
 #undef GSA_PM
         default: return nullptr;
     }
 }
+static const void* pairs_mma_kernel_product(int NB, size_t* smem, bool jansen = true) {
+    return jansen ? pairs_mma_kernel_product_j<true>(NB, smem) : pairs_mma_kernel_product_j<false>(NB, smem);
+}
 constexpr int PMMA_TILE_ST = 3;
-static const void* pairs_mma_kernel_tile(int d, size_t* smem) {
+template <bool J>
+static const void* pairs_mma_kernel_tile_j(int d, size_t* smem) {
     *smem = pm_smem_bytes(pm_ring_doubles_tile(d, PMMA_TILE_ST), 1);
     switch (d) {
-        case 2: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 2, PMMA_TILE_ST>;
-        case 4: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 4, PMMA_TILE_ST>;
-        case 6: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 6, PMMA_TILE_ST>;
-        case 8: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 8, PMMA_TILE_ST>;
+        case 2: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 2, PMMA_TILE_ST, J>;
+        case 4: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 4, PMMA_TILE_ST, J>;
+        case 6: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 6, PMMA_TILE_ST, J>;
+        case 8: return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT_TILE, 1, 8, PMMA_TILE_ST, J>;
         default: return nullptr;
     }
 }
-static const void* pairs_mma_kernel_y(int d, size_t* smem) {
+static const void* pairs_mma_kernel_tile(int d, size_t* smem, bool jansen = true) {
+    return jansen ? pairs_mma_kernel_tile_j<true>(d, smem) : pairs_mma_kernel_tile_j<false>(d, smem);
+}
+template <bool J>
+static const void* pairs_mma_kernel_y_j(int NB, int st) {
+#define GSA_PMY(NBV, STV) if (NB == NBV && st == STV) return (const void*)pairs_mma_kernel<PM_SRC_Y, NBV, 1, STV, J>;
+    GSA_PMY(1, 2) GSA_PMY(1, 3) GSA_PMY(1, 4) GSA_PMY(2, 2) GSA_PMY(2, 3) GSA_PMY(2, 4) GSA_PMY(3, 2) GSA_PMY(3, 3) GSA_PMY(4, 2)
+#undef GSA_PMY
+    return nullptr;
+}
+static const void* pairs_mma_kernel_y(int d, size_t* smem, bool jansen = true) {
     const int NB = (d + 7) / 8;
     int st = pmma_y_stages(NB);
     if (const char* e = getenv("GSA_PAIRS_YST")) st = std::max(2, std::min(4, atoi(e)));   // tuning knob: stages of the warp tiles
     if (NB >= 3 && st > 3) st = 3;
     if (NB == 4) st = 2;
     *smem = pm_smem_bytes(pm_ring_doubles_y(d, st), NB);
-#define GSA_PMY(NBV, STV) if (NB == NBV && st == STV) return (const void*)pairs_mma_kernel<PM_SRC_Y, NBV, 1, STV>;
-    GSA_PMY(1, 2) GSA_PMY(1, 3) GSA_PMY(1, 4) GSA_PMY(2, 2) GSA_PMY(2, 3) GSA_PMY(2, 4) GSA_PMY(3, 2) GSA_PMY(3, 3) GSA_PMY(4, 2)
-#undef GSA_PMY
-    return nullptr;
+    return jansen ? pairs_mma_kernel_y_j<true>(NB, st) : pairs_mma_kernel_y_j<false>(NB, st);
 }
 
 static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool second, int est, FusedPlan* p, bool gen = false) {
@@ -239,11 +251,12 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
         // kernel on config 3).  Odd d <= 8 stays on the register kernel.
         const char* em = getenv("GSA_PAIRS_MMA");   // tuning knob: 0 = never, 1 = lane-per-coordinate source, 2 = tile source (even d <= 8)
         const int mode = em ? atoi(em) : (d > SMALL_DMAX2 ? 1 : (d % 2 == 0 ? 2 : 0));
-        if (!generic_only && model == GSA_MODEL_SOBOL_G && second && est == GSA_EI_JANSEN1999 && d <= PMMA_DMAX && mode != 0) {
+        if (!generic_only && model == GSA_MODEL_SOBOL_G && second && est != GSA_EI_JANON2014 && d <= PMMA_DMAX && mode != 0) {
             p->kind = PLAN_PAIRS_MMA;
             p->threads = PMMA_THREADS;
             p->pairs_tile = mode == 2 && d <= 8 && d % 2 == 0;   // (rows must be 16-byte aligned: checked at launch)
-            p->kernel = p->pairs_tile ? pairs_mma_kernel_tile(d, &p->smem) : pairs_mma_kernel_product((d + 7) / 8, &p->smem);
+            const bool jn = est == GSA_EI_JANSEN1999;
+            p->kernel = p->pairs_tile ? pairs_mma_kernel_tile(d, &p->smem, jn) : pairs_mma_kernel_product((d + 7) / 8, &p->smem, jn);
             if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
             int nb = 0;
             GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));
@@ -251,7 +264,7 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
             p->tiles_per_cta = 1;
             p->ts_min = p->ts_gran = p->pairs_tile ? PM_CH * PMMA_NW : 4 * PMMA_UN * PMMA_NW;
             if (p->pairs_tile) {   // designs that are not 16-byte aligned take the lane-per-coordinate source at launch
-                p->kernel_alt = pairs_mma_kernel_product(1, &p->smem_alt);
+                p->kernel_alt = pairs_mma_kernel_product(1, &p->smem_alt, jn);
                 if (p->smem_alt > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel_alt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_alt));
             }
             return GSA_OK;

@@ -11,7 +11,8 @@
 // Values enter the products shifted by c = yA of the tile's first sample (p = yBA - c, q = yAB - c), so the sums stay of the
 // order of the output's spread, not its mean:
 //     sum (yBA_k yAB_j - yA yB) = [P'_kj - sum fa' fb'] + c [(sum p_k + sum q_j) - (sum fa' + sum fb')],   fa' = yA - c, fb' = yB - c.
-// The first- and total-order terms are formed per sample exactly as the reference forms them (difference first, :192, :213).
+// The first- and total-order terms are formed per sample exactly as the reference forms them (difference first, :192, :213;
+// Sobol2007 :211 and Homma1996 :207 are one-accumulator estimators too and share the kernel; Janon2014 needs three terms).
 //
 // Three sources feed the same engine (template parameter SRC):
 //   * PRODUCT -- product-form models (Sobol G), 8 < d <= 32: lane (g, t) loads coordinate 8*blk+g of rows A_s, B_s (the 8 lanes
@@ -69,7 +70,7 @@ inline size_t pm_smem_bytes(size_t ring_doubles, int NB) { return sizeof(double)
 
 // NB = 8-coordinate blocks (d <= 8*NB); UN = warp steps per load group (PRODUCT) or d itself (PRODUCT_TILE); ST = stages in flight
 enum { PM_SRC_PRODUCT = 0, PM_SRC_Y = 1, PM_SRC_PRODUCT_TILE = 2 };
-template <int SRC, int NB, int UN, int ST>
+template <int SRC, int NB, int UN, int ST, bool JANSEN = true>
 __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
     constexpr bool YSRC = SRC == PM_SRC_Y, TSRC = SRC == PM_SRC_PRODUCT_TILE;
     static_assert(!TSRC || NB == 1, "thread-per-sample evaluation: one 8-coordinate block (UN carries d)");
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
         ok[k] = 8 * k + g8 < d;
         cf[k] = (!YSRC && ok[k]) ? __ldg(a.coef + 8 * k + g8) : make_double2(0.0, 1.0);   // padded coordinates: factor 1
     }
+    const bool sobol2007 = a.est == GSA_EI_SOBOL2007;   // JANSEN = false: Sobol2007 or Homma1996 (block-uniform)
     const int units = (a.t_end - a.t_begin) * (YSRC ? a.nout : 1);
     (void)ring; (void)wtile;
 
@@ -148,7 +150,9 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
                 const bool lv = valid && ok[k];
                 const double df = lv ? yab[k] - yA : 0.0;
                 V[k] = fma(yB, df, V[k]);            // :192
-                E[k] = fma(df, df, E[k]);            // :213
+                // total-order term: (yA - yAB)^2 (Jansen1999, :213), yA (yA - yAB) (Sobol2007, :211) or yA yAB (Homma1996, :207)
+                if constexpr (JANSEN) E[k] = fma(df, df, E[k]);
+                else E[k] = fma(lv ? yA : 0.0, sobol2007 ? -df : yab[k], E[k]);
                 pv[k] = lv ? yba[k] - c : 0.0;
                 qv[k] = lv ? yab[k] - c : 0.0;
                 SP[k] += pv[k];

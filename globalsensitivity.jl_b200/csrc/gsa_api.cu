@@ -459,12 +459,12 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
         const bool small = d <= (second ? SMALL_DMAX2 : (est == GSA_EI_JANSEN1999 ? SMALL_DMAX_Y : 16)) && !(force && atoi(force) != 0);
         int tpr = 1;
         const char* em = getenv("GSA_PAIRS_MMA");   // tuning knob: 0 = never, 1 = whenever possible; default: d > 8 (the register kernel covers d <= 8)
-        const bool pairs_mma = second && est == GSA_EI_JANSEN1999 && d <= PMMA_DMAX && !(force && atoi(force) != 0) &&
+        const bool pairs_mma = second && est != GSA_EI_JANON2014 && d <= PMMA_DMAX && !(force && atoi(force) != 0) &&
                                (em ? atoi(em) != 0 : !small);
         if (pairs_mma) {
             // second order, d <= 32: the pair sums run as FP64 mma over the samples (fused_pairs_mma.cuh), Y is read exactly once
             size_t smem = 0;
-            const void* kern = pairs_mma_kernel_y(d, &smem);
+            const void* kern = pairs_mma_kernel_y(d, &smem, est == GSA_EI_JANSEN1999);
             if (smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int nb = 0;
             GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, PMMA_THREADS, smem));

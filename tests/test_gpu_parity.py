@@ -338,6 +338,21 @@ def test_pairs_mma_kernel(d, N, nboot, monkeypatch):
     assert_parity(resy, refy, what=(d, N, nboot, "Y, 2 outputs"))
 
 
+@pytest.mark.parametrize("est", ["Sobol2007", "Homma1996", "Janon2014"])
+@pytest.mark.parametrize("d,N,nboot", [(8, 20011, 2), (20, 9001, 1), (6, 4099, 3)])
+def test_pairs_mma_other_estimators(est, d, N, nboot):
+    """Second order with the other Ei_estimators: Sobol2007 and Homma1996 share the mma pair kernels (fused sources and Y source),
+    Janon2014 falls back to the generic / shared-memory kernels; all against the oracle."""
+    a = np.array(([0.0, 1.0, 4.5, 9.0] + [99.0] * d)[:d])
+    A, B = gsa_ref.sobol_design(N, np.zeros(d), np.ones(d))
+    ref = gsa_ref.gsa_sobol("sobol_g", a, A, B, order=(0, 1, 2), nboot=nboot, Ei_estimator=est)
+    res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2], nboot=nboot), A, B, batch=True, Ei_estimator=est)
+    assert_parity(res, ref, what=(est, d, "fused"))
+    Y = gsa_ref.model_batch("sobol_g", a, gsa_ref.all_points(A, B, nboot, True))
+    resy = g.gsa_sobol_all_y_analysis(g.Sobol(order=[0, 1, 2], nboot=nboot), Y, d, N // nboot, est)
+    assert_parity(resy, ref, what=(est, d, "Y"))
+
+
 def test_pairs_mma_sources_agree(monkeypatch):
     """d = 8 through all three fused second-order kernels (register kernel, lane-per-coordinate mma source, thread-per-sample
     tile source) and through a design that is NOT 16-byte aligned (the tile source needs 16-byte rows and must step aside)."""
