@@ -63,6 +63,7 @@ SIGNATURES = {
     "gsa_multi_destroy": [_vp],
     "gsa_multi_device_count": [_vp, _ip],
     "gsa_multi_handle": [_vp, _i, C.POINTER(_vp)],
+    "gsa_multi_model_register_fatbin": [_vp, _vp, _sz, C.c_char_p, _i, _ip],
     "gsa_multi_sobol_run": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
     "gsa_multi_sobol_run_generated": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
     "gsa_last_timing": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _ip],

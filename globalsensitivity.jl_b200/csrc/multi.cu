@@ -125,6 +125,22 @@ int gsa_multi_device_count(gsa_multi* m, int* ndev) {
     return GSA_OK;
 }
 
+int gsa_multi_model_register_fatbin(gsa_multi* m, const void* image, size_t len, const char* symbol, int nout, int* model_id) {
+    if (!m || !model_id) return fail(GSA_ERR_INVALID, "NULL argument to gsa_multi_model_register_fatbin");
+    std::lock_guard<std::mutex> lk(m->mu);
+    int first = -1;
+    for (gsa_handle* hh : m->h) {
+        int id = -1;
+        const int rc = gsa_model_register_fatbin(hh, image, len, symbol, nout, &id);
+        if (rc != GSA_OK) return rc;
+        if (first < 0) first = id;
+        else if (id != first)   // ids are per-handle sequence numbers: they agree as long as models are only registered through `m`
+            return fail(GSA_ERR_INVALID, "user model got id %d on device %d but %d on the first device: register models through gsa_multi only", id, hh->device, first);
+    }
+    *model_id = first;
+    return GSA_OK;
+}
+
 int gsa_multi_handle(gsa_multi* m, int i, gsa_handle** out) {
     if (!m || !out || i < 0 || i >= (int)m->h.size()) return fail(GSA_ERR_INVALID, "bad arguments to gsa_multi_handle");
     *out = m->h[i];
@@ -138,7 +154,6 @@ int gsa_multi_handle(gsa_multi* m, int i, gsa_handle** out) {
 static int multi_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams, const double* A,
                      const double* B, const double* lb, const double* ub, int64_t samples, int d, int64_t N, gsa_sobol_result* out) {
     const bool generated = lb != nullptr;
-    if (model_id >= GSA_MODEL_USER_BASE) return fail(GSA_ERR_UNSUPPORTED, "user models are registered per handle; not supported by the multi-device entry yet");
     MDBG("run: enter");
     std::lock_guard<std::mutex> lk(m->mu);
     const int G = (int)m->h.size();

@@ -133,6 +133,13 @@ class GsaHandle:
         return ms.value, kms.value, n.value
 
 
+class _BorrowedHandle:
+    """A gsa_handle owned by someone else (a GsaMulti): only its pointer is used (DeviceModel.nout)."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+
 class PeerGroup:
     """K5 over NVLink peer memory (csrc/peer.cu), one process per GPU: the ranks of a torch.distributed group exchange the
     IPC handles of their mailboxes once; after that `allreduce` is ONE small kernel per rank on the handle's stream -- no
@@ -215,6 +222,21 @@ class GsaMulti:
             self.close()
         except Exception:
             pass
+
+    def model_from_fatbin(self, image, symbol: str, nout: int = 1, params=()) -> "DeviceModel":
+        """A user `__device__` model linked on every device of this object (gsa_multi_model_register_fatbin); see
+        DeviceModel.from_fatbin for the image format."""
+        if isinstance(image, str):
+            with open(image, "rb") as f:
+                image = f.read()
+        m = DeviceModel("user:" + symbol, params)
+        mid = C.c_int()
+        buf = C.create_string_buffer(bytes(image), len(image))
+        check(lib().gsa_multi_model_register_fatbin(self._m, buf, len(image), symbol.encode(), int(nout), C.byref(mid)))
+        h = C.c_void_p()
+        check(lib().gsa_multi_handle(self._m, 0, C.byref(h)))
+        m.model_id, m.handle = mid.value, _BorrowedHandle(h)
+        return m
 
     def gsa(self, f: "DeviceModel", method: "Sobol", A, B, *, batch: bool = True, Ei_estimator="Jansen1999") -> "SobolResult":
         Am, Bm = _Mat(A), _Mat(B)

@@ -197,6 +197,9 @@ GSA_API int gsa_multi_destroy(gsa_multi* m);
 GSA_API int gsa_multi_device_count(gsa_multi* m, int* ndev);
 /* the i-th per-device handle (owned by `m`), e.g. for gsa_sobol_design on that device */
 GSA_API int gsa_multi_handle(gsa_multi* m, int i, gsa_handle** out);
+/* gsa_model_register_fatbin on every device of `m`: the same image is linked once per device and gets the same id on all */
+GSA_API int gsa_multi_model_register_fatbin(gsa_multi* m, const void* image, size_t len, const char* symbol, int nout,
+                                    int* model_id);
 /* gsa(model, Sobol(...), A, B; batch=true) (:110-149 + :169-405) with the HOST design sharded by contiguous column ranges
  * over the devices: every device streams and reduces its shard, ONE kernel on the first device gathers and adds the
  * nboot*nout*nstat partial sums of all devices over NVLink peer memory (error-free for the double-double entries) and

@@ -557,6 +557,27 @@ def test_user_device_model_from_fatbin(tmp_path):
         g.DeviceModel.from_fatbin(fat1.read_bytes(), "other_name", nout=1)             # trampoline would redefine gsa_user_model
 
 
+def test_multi_device_user_model(tmp_path):
+    """A user `__device__` model on the single-process multi-device entry: linked once per device, same id everywhere."""
+    import shutil
+    import subprocess
+    import torch
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    src = tmp_path / "um.cu"
+    src.write_text(USER_MODEL_CU)
+    fat = tmp_path / "um.fatbin"
+    subprocess.check_call([nvcc, "-ccbin", "/usr/bin/g++", "-rdc=true", "-fatbin", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(fat), str(src)])
+    d, N = 5, 30011
+    p = np.array([0.5, 1.0, 1.5, 2.0, 2.5])
+    A, B = gsa_ref.sobol_design(N, -np.ones(d), 2 * np.ones(d))
+    m = g.GsaMulti(ndev=torch.cuda.device_count())
+    model = m.model_from_fatbin(str(fat), "my_model", nout=1, params=p)
+    res = m.gsa(model, g.Sobol(order=[0, 1, 2], nboot=2), A, B)
+    ref = so.gsa_sobol(lambda X: (p[:, None] * X * X).sum(axis=0) + X[0] * X[1], A, B, order=(0, 1, 2), nboot=2)
+    assert_parity(res, ref, tol=1e-11)
+    m.close()
+
+
 def test_multi_device_single_process(ishigami_design):
     """gsa_multi: one process, all visible GPUs, one gather-and-add kernel over NVLink peer memory for the partial sums.  Runs with
     a single device too (then no collective is issued)."""
