@@ -101,7 +101,7 @@ def reference_arm(args):
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
             "note": "Julia is not installed in the image: this is oracle/gsa_ref.c (C + OpenMP restatement of "
                     "src/sobol_sensitivity.jl:94-405), pinned to the reference's golden vectors"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -356,7 +356,7 @@ def gpu_arm(args):
                 "collective": collective, "roofline": roofline, "generated_design": gen, "cpu_baseline": cb, "clocks": clocks,
                 "check": {"S1_0": float(res.S1[0]), "S1_0_analytic": float(Vi[0] / V), "ST_0": float(res.ST[0]),
                           "ST_0_analytic": float(Vi[0] * np.prod(1 + Vi) / (1 + Vi[0]) / V)}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if pg is not None:
         if pg.status() != 0:
             raise SystemExit("peer all-reduce timed out waiting for a rank")
@@ -365,7 +365,29 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to file descriptor 1 (NCCL's version banner, library
+    chatter of any rank) goes to stderr from here on."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
