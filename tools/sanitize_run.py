@@ -1,5 +1,6 @@
-"""Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
-    compute-sanitizer --tool memcheck python tools/sanitize_run.py"""
+"""Small invocations of every kernel family (ragged sizes, every block count, all estimators) without the oracle: a quick
+exercise run, and the workload for `compute-sanitizer --tool memcheck|racecheck python tools/sanitize_run.py` where the tool is
+available (it is closed on the round-1 GPU pool)."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
