@@ -280,6 +280,17 @@ def test_product_path_matches_generic_path(monkeypatch):
 
 
 @pytest.mark.parametrize("est", so.EI_ESTIMATORS)
+def test_survey_estimator_known_answers_on_gpu(golden, ishigami_design, est):
+    """SURVEY Appendix B known answers (the survey's independent probe) for all four Ei_estimators on the reference's test design."""
+    A, B = ishigami_design
+    ka = golden["survey_appendix_b_estimators"]
+    for name, model in (("ishigami", g.DeviceModel("ishigami", [7.0, 0.1])), ("linear", g.DeviceModel("linear", np.array([[7.0, 0.1, 0.0, 0.0]])))):
+        r = g.gsa(model, g.Sobol(), A, B, batch=True, Ei_estimator=est)
+        assert np.abs(np.ravel(r.S1) - np.array(ka[name]["S1"])).max() < 1e-12, (name, est)
+        assert np.abs(np.ravel(r.ST) - np.array(ka[name]["ST"][est])).max() < 1e-12, (name, est)
+
+
+@pytest.mark.parametrize("est", so.EI_ESTIMATORS)
 @pytest.mark.parametrize("d,N,nboot", [(100, 8000, 2), (5, 30011, 1), (40, 12345, 3)])
 def test_product_kernel_all_estimators(est, d, N, nboot):
     """Config-5-type models with every Ei_estimator: Jansen1999, Sobol2007 and Homma1996 share the product-form kernel (one

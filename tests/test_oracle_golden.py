@@ -77,6 +77,18 @@ def test_reference_goldens(golden, ishigami_design, impl):
     assert np.abs(r.S2 - np.array(golden["ishigami_S2_order012"]["value"])).max() < 1e-4
 
 
+@pytest.mark.parametrize("est", so.EI_ESTIMATORS)
+def test_survey_estimator_known_answers(golden, ishigami_design, est):
+    """S1 / ST of all four Ei_estimators on the reference's test design, from the survey's independent probe."""
+    A, B = ishigami_design
+    ka = golden["survey_appendix_b_estimators"]
+    for name, model, params in (("ishigami", "ishigami", [7.0, 0.1]), ("linear", "linear", np.array([[7.0, 0.1, 0.0, 0.0]]))):
+        for r in (gsa_ref.gsa_sobol(model, params, A, B, Ei_estimator=est),
+                  so.gsa_sobol(so.ishigami_batch if name == "ishigami" else so.linear_batch, A, B, Ei_estimator=est)):
+            assert np.abs(np.ravel(r.S1) - np.array(ka[name]["S1"])).max() < 2e-14, (name, est)
+            assert np.abs(np.ravel(r.ST) - np.array(ka[name]["ST"][est])).max() < 2e-14, (name, est)
+
+
 def test_linear_goldens(golden, ishigami_design):
     A, B = ishigami_design
     W = np.array([[7.0, 0.1, 0.0, 0.0]])
