@@ -59,13 +59,16 @@ default_handle() = something(DEFAULT[], (DEFAULT[] = Handle()))
 struct DeviceModel
     id::Cint
     params::Vector{Float64}        # a 2-D W is passed as vec(W) (column-major, as the C side expects)
+    nout::Int                      # user models: fixed at registration; built-in models: 0 = ask the library
 end
+DeviceModel(id::Integer, params::Vector{Float64}) = DeviceModel(Cint(id), params, 0)
 function DeviceModel(name::AbstractString, params = Float64[])
     id = Ref{Cint}(0)
     check(ccall((:gsa_model_lookup, libgsa), Cint, (Cstring, Ref{Cint}), name, id))
     return DeviceModel(id[], vec(Float64.(params)))
 end
 function nout(m::DeviceModel, d::Integer)
+    m.nout > 0 && return m.nout
     n = Ref{Cint}(0)
     check(ccall((:gsa_model_nout, libgsa), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ref{Cint}),
                 C_NULL, m.id, length(m.params), d, n))
@@ -188,5 +191,42 @@ function gsa(m::Multi, model::DeviceModel, method::Sobol, A::Matrix{Float64}, B:
     end
     return finish()
 end
+
+# gsa(model, Sobol(...), p_range; samples) over all devices with the design generated inside the fused kernel (no A/B at all)
+function gsa(m::Multi, model::DeviceModel, method::Sobol, p_range::AbstractVector; samples, Ei_estimator = :Jansen1999)
+    lb = [float(p[1]) for p in p_range]; ub = [float(p[2]) for p in p_range]
+    d = length(lb); second = 2 in method.order
+    opts = Ref(GsaSobolOpts(second, method.nboot, method.conf_level, EI[Ei_estimator], 1))
+    res, finish, keep = alloc(nout(model, d), d, method.nboot, second)
+    GC.@preserve keep model lb ub begin
+        check(ccall((:gsa_multi_sobol_run_generated, libgsa), Cint,
+                    (Ptr{Cvoid}, Ref{GsaSobolOpts}, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Int64, Ref{GsaSobolResult}),
+                    m.ptr, opts, model.id, model.params, length(model.params), lb, ub, d, samples, Ref(res)))
+    end
+    return finish()
+end
+
+# ---- user `__device__` models: a relocatable fatbin (nvcc -rdc=true -fatbin -gencode arch=compute_100a,code=sm_100a) that defines
+#      extern "C" __device__ void <symbol>(const double* x, int d, const double* p, int np, double* y, int nout) -----------------
+function DeviceModel(image::Vector{UInt8}, symbol::AbstractString, params = Float64[]; nout::Integer = 1, handle::Handle = default_handle())
+    id = Ref{Cint}(0)
+    GC.@preserve image begin
+        check(ccall((:gsa_model_register_fatbin, libgsa), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Csize_t, Cstring, Cint, Ref{Cint}),
+                    handle.ptr, image, length(image), symbol, nout, id))
+    end
+    return DeviceModel(id[], vec(Float64.(params)), Int(nout))
+end
+function DeviceModel(m::Multi, image::Vector{UInt8}, symbol::AbstractString, params = Float64[]; nout::Integer = 1)
+    id = Ref{Cint}(0)
+    GC.@preserve image begin
+        check(ccall((:gsa_multi_model_register_fatbin, libgsa), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Csize_t, Cstring, Cint, Ref{Cint}),
+                    m.ptr, image, length(image), symbol, nout, id))
+    end
+    return DeviceModel(id[], vec(Float64.(params)), Int(nout))
+end
+
+# QuasiMonteCarlo.sample(n, lb, ub, SobolSample()): the single-matrix design the reference's other methods draw (SURVEY 8(f) N3)
+sample(n::Integer, lb::Vector{Float64}, ub::Vector{Float64}; handle::Handle = default_handle()) =
+    generate_design_matrices(n, lb, ub, 1; handle = handle)[1]
 
 end # module
