@@ -154,22 +154,47 @@ class PeerGroup:
     HANDLE_BYTES = 64
 
     def __init__(self, handle: "GsaHandle", max_doubles: int, group=None):
+        import os
         import torch
         import torch.distributed as dist
         self.h = handle
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        on_gpu = dist.get_backend(group) == "nccl"
+
+        def all_ok(ok: bool, what: str, err):
+            """Every local step is followed by an agreement: either all ranks go on, or all raise -- a rank that failed alone
+            must not leave its peers waiting inside the next collective."""
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32)
+            if on_gpu:
+                flag = flag.cuda()
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                lib().gsa_peer_disconnect(handle.ptr)
+                self.h = None
+                raise GsaError(2, f"peer all-reduce unavailable: {what} failed on " + (f"this rank ({err})" if not ok else "another rank"))
+
         buf = (C.c_ubyte * self.HANDLE_BYTES)()
-        check(lib().gsa_peer_export(handle.ptr, int(max_doubles), C.addressof(buf)))
+        err = None
+        try:
+            if os.environ.get("GSA_PEER_TEST_FAIL") == str(self.rank):      # test hook: this rank cannot export its mailbox
+                raise GsaError(2, "GSA_PEER_TEST_FAIL")
+            check(lib().gsa_peer_export(handle.ptr, int(max_doubles), C.addressof(buf)))
+        except GsaError as e:
+            err = e
+        all_ok(err is None, "gsa_peer_export", err)
         mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
-        if dist.get_backend(group) == "nccl":
+        if on_gpu:
             mine = mine.cuda()
         gathered = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(gathered, mine, group=group)
         blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in gathered)
         self._blob = C.create_string_buffer(blob, len(blob))
-        check(lib().gsa_peer_connect(handle.ptr, self.rank, self.world, C.addressof(self._blob)))
-        dist.barrier(group=group)          # every mailbox is mapped before the first exchange
+        try:
+            check(lib().gsa_peer_connect(handle.ptr, self.rank, self.world, C.addressof(self._blob)))
+        except GsaError as e:
+            err = e
+        all_ok(err is None, "gsa_peer_connect", err)      # (also the barrier: every mailbox is mapped before the first exchange)
 
     def allreduce(self, partials, nstat: int, host_out=None):
         """In-place sum of the CUDA tensor `partials` over the ranks; `host_out` (a pinned CPU tensor of the same size) also
