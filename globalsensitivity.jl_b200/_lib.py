@@ -71,6 +71,7 @@ SIGNATURES = {
     "gsa_peer_connect": [_vp, _i, _i, _vp],
     "gsa_peer_allreduce": [_vp, _vp, _sz, _i, _vp],
     "gsa_peer_status": [_vp, _ip],
+    "gsa_peer_unmap": [_vp],
     "gsa_peer_disconnect": [_vp],
 }
 

@@ -138,12 +138,19 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(PeerArgs a
     }
 }
 
+// unmap the peers' mailboxes (this rank's own mailbox stays allocated: peers may still have it mapped)
+static void peer_unmap(PeerState* ps) {
+    for (int r = 0; r < (int)ps->peer.size(); ++r)
+        if (ps->peer[r] && r != ps->rank) cudaIpcCloseMemHandle(ps->peer[r]);
+    ps->peer.clear();
+    if (ps->peer_dev) cudaFree(ps->peer_dev);
+    ps->peer_dev = nullptr;
+}
+
 static void peer_release(gsa_handle* h) {
     PeerState* ps = h->peer;
     if (!ps) return;
-    for (int r = 0; r < (int)ps->peer.size(); ++r)
-        if (ps->peer[r] && r != ps->rank) cudaIpcCloseMemHandle(ps->peer[r]);
-    if (ps->peer_dev) cudaFree(ps->peer_dev);
+    peer_unmap(ps);
     if (ps->counter_dev) cudaFree(ps->counter_dev);
     if (ps->mailbox) cudaFree(ps->mailbox);
     if (ps->status_host) cudaFreeHost(ps->status_host);
@@ -263,6 +270,15 @@ int gsa_peer_allreduce(gsa_handle* h, double* data_dev, size_t count, int nstat,
 int gsa_peer_status(gsa_handle* h, int* status) {
     if (!h || !status) return fail(GSA_ERR_INVALID, "bad arguments to gsa_peer_status");
     *status = (h->peer && h->peer->status_host) ? *h->peer->status_host : 0;
+    return GSA_OK;
+}
+
+int gsa_peer_unmap(gsa_handle* h) {
+    if (!h) return GSA_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DevGuard guard(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->peer) peer_unmap(h->peer);
     return GSA_OK;
 }
 

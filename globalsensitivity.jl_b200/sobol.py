@@ -215,6 +215,9 @@ class PeerGroup:
             try:
                 if dist.is_initialized():
                     dist.barrier(group=self.group)      # nobody unmaps a mailbox a peer may still write to
+                lib().gsa_peer_unmap(self.h.ptr)
+                if dist.is_initialized():
+                    dist.barrier(group=self.group)      # nobody frees a mailbox a peer still has mapped
             finally:
                 lib().gsa_peer_disconnect(self.h.ptr)
                 self.h = None

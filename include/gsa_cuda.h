@@ -181,12 +181,15 @@ GSA_API int gsa_last_timing(gsa_handle* h, float* total_ms, float* kernel_ms, in
  *   gsa_peer_allreduce  in place on `data_dev` (count doubles = records of nstat doubles, see gsa_sobol_nstat), asynchronous on
  *                       the handle's stream; host_out != NULL (pinned host memory) also receives the sums, written by the
  *                       kernel itself (no device-to-host copy to wait for)
- *   gsa_peer_status     0, or 1 after a wait for a peer timed out (GSA_PEER_TIMEOUT_MS, default 10000)               */
+ *   gsa_peer_status     0, or 1 after a wait for a peer timed out (GSA_PEER_TIMEOUT_MS, default 10000)
+ *   teardown            every rank: gsa_peer_unmap (closes its mappings of the peers' mailboxes), a barrier of the caller's, then
+ *                       gsa_peer_disconnect (frees its own mailbox, which no peer maps any more)                         */
 #define GSA_PEER_HANDLE_BYTES 64
 GSA_API int gsa_peer_export(gsa_handle* h, size_t max_doubles, void* handle_out);
 GSA_API int gsa_peer_connect(gsa_handle* h, int rank, int world, const void* handles);
 GSA_API int gsa_peer_allreduce(gsa_handle* h, double* data_dev, size_t count, int nstat, double* host_out);
 GSA_API int gsa_peer_status(gsa_handle* h, int* status);
+GSA_API int gsa_peer_unmap(gsa_handle* h);
 GSA_API int gsa_peer_disconnect(gsa_handle* h);
 
 /* ---- single-process, multi-device form (a plain Julia `ccall` from one process) ------------------ */
