@@ -19,8 +19,8 @@ _dp = C.POINTER(C.c_double)
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "gsa_ref.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("gsa_ref.c", "gsa_ref_streamed.c", "Makefile")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(src) for src in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libgsa_ref.so"])
     return _SO
 
@@ -52,6 +52,23 @@ def lib():
         L.ref_model_batch.argtypes = [C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int64, _dp]
         L.ref_model_nout.restype = C.c_int
         L.ref_model_nout.argtypes = [C.c_int, C.c_int, C.c_int]
+        # gsa_ref_streamed.c: the streamed exact-sum oracle
+        L.ref_stream_new.restype = C.c_void_p
+        L.ref_stream_new.argtypes = [C.c_int, _dp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int]
+        L.ref_stream_free.restype = None
+        L.ref_stream_free.argtypes = [C.c_void_p]
+        L.ref_stream_push.restype = None
+        L.ref_stream_push.argtypes = [C.c_void_p, _dp, _dp, C.c_int64, C.c_int64]
+        L.ref_stream_finish.restype = C.c_int64
+        L.ref_stream_finish.argtypes = [C.c_void_p, C.c_double] + [_dp] * 6
+        L.ref_gsa_sobol_streamed.restype = C.c_int64
+        L.ref_gsa_sobol_streamed.argtypes = [C.c_int, _dp, C.c_int, _dp, _dp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                             C.c_double, C.c_int64] + [_dp] * 6
+        L.ref_gsa_sobol_streamed_generated.restype = C.c_int64
+        L.ref_gsa_sobol_streamed_generated.argtypes = [C.c_int, _dp, C.c_int, C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_int64, C.c_int,
+                                                       C.c_int, C.c_int, C.c_double, C.c_int64] + [_dp] * 6
+        L.ref_analyze_y_exact.restype = None
+        L.ref_analyze_y_exact.argtypes = [_dp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double] + [_dp] * 6
         _lib = L
     return _lib
 
@@ -130,14 +147,16 @@ def gsa_sobol(model, params, A, B, order=(0, 1), nboot=1, conf_level=0.95, Ei_es
     return res
 
 
-def analyze_y(Y, d, n, order=(0, 1), nboot=1, conf_level=0.95, Ei_estimator="Jansen1999"):
+def analyze_y(Y, d, n, order=(0, 1), nboot=1, conf_level=0.95, Ei_estimator="Jansen1999", exact=False):
+    """gsa_sobol_all_y_analysis on a given all_y.  exact=True: the same per-sample terms summed EXACTLY
+    (gsa_ref_streamed.c) instead of with Julia's pairwise sum."""
     Y = np.asarray(Y, dtype=np.float64)
     nout = 1 if Y.ndim == 1 else Y.shape[0]
     Yf = np.asfortranarray(Y.reshape(nout, -1))
     second = 2 in order
     bufs, fin = _alloc_result(nout, d, nboot, second)
-    lib().ref_analyze_y(_p(Yf), nout, d, n, nboot, int(second), ESTIMATORS[Ei_estimator], conf_level,
-                        *[_p(b) for b in bufs])
+    fn = lib().ref_analyze_y_exact if exact else lib().ref_analyze_y
+    fn(_p(Yf), nout, d, n, nboot, int(second), ESTIMATORS[Ei_estimator], conf_level, *[_p(b) for b in bufs])
     res = fin()
     if Y.ndim == 2 and nout == 1:   # a 1 x cols matrix is still "multioutput" in the reference
         res.S1, res.ST = res.S1[None, :], res.ST[None, :]
@@ -162,3 +181,80 @@ def model_batch(model, params, X):
     Y = np.empty((cols, nout))
     lib().ref_model_batch(mid, _p(params), params.size, _p(X), d, cols, _p(Y))
     return Y.T if nout > 1 else Y[:, 0]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# streamed exact-sum oracle (gsa_ref_streamed.c): full model per swapped coordinate, per-sample terms formed as the
+# reference forms them, summed exactly; never holds more than a chunk of the design
+# ---------------------------------------------------------------------------------------------------------------
+def gsa_sobol_streamed(model, params, A, B, order=(0, 1), nboot=1, conf_level=0.95, Ei_estimator="Jansen1999", chunk=1 << 16):
+    A, B = _f(A), _f(B)
+    d, N = A.shape
+    params = np.ascontiguousarray(np.asarray(params, dtype=np.float64).ravel(order="F"))
+    mid = MODELS[model]
+    nout = lib().ref_model_nout(mid, params.size, d)
+    second = 2 in order
+    bufs, fin = _alloc_result(nout, d, nboot, second)
+    rows = lib().ref_gsa_sobol_streamed(mid, _p(params), params.size, _p(A), _p(B), d, N, nboot, int(second),
+                                        ESTIMATORS[Ei_estimator], conf_level, chunk, *[_p(b) for b in bufs])
+    if rows < 0:
+        raise MemoryError("streamed oracle: allocation failed")
+    res = fin()
+    res.rows = rows
+    return res
+
+
+def gsa_sobol_streamed_generated(model, params, lb, ub, N, order=(0, 1), nboot=1, conf_level=0.95, Ei_estimator="Jansen1999",
+                                 p_range_design=False, chunk=1 << 16):
+    """The same with the design generated chunk by chunk inside the oracle: generate_design_matrices(N, lb, ub, 2), or, with
+    p_range_design=True, the 2*nboot*d-dimensional design of gsa(f, ::Sobol, p_range; samples=N//nboot) (:407-417)."""
+    global _table
+    if _table is None:
+        _table = np.fromfile(_TABLE, dtype="<u4")
+    lb = np.ascontiguousarray(lb, dtype=np.float64)
+    ub = np.ascontiguousarray(ub, dtype=np.float64)
+    d = lb.size
+    params = np.ascontiguousarray(np.asarray(params, dtype=np.float64).ravel(order="F"))
+    mid = MODELS[model]
+    nout = lib().ref_model_nout(mid, params.size, d)
+    second = 2 in order
+    bufs, fin = _alloc_result(nout, d, nboot, second)
+    rows = lib().ref_gsa_sobol_streamed_generated(mid, _p(params), params.size, _table.ctypes.data, _p(lb), _p(ub),
+                                                  2 if p_range_design else 1, d, N, nboot, int(second), ESTIMATORS[Ei_estimator],
+                                                  conf_level, chunk, *[_p(b) for b in bufs])
+    if rows < 0:
+        raise MemoryError("streamed oracle: allocation failed")
+    res = fin()
+    res.rows = rows
+    return res
+
+
+class Stream:
+    """Incremental form: push column chunks of the SAME A/B the GPU path sees (e.g. copied back from the device), finish()."""
+
+    def __init__(self, model, params, d, N, order=(0, 1), nboot=1, Ei_estimator="Jansen1999"):
+        self.params = np.ascontiguousarray(np.asarray(params, dtype=np.float64).ravel(order="F"))
+        mid = MODELS[model]
+        self.d, self.N, self.nboot, self.second = d, N, nboot, 2 in order
+        self.nout = lib().ref_model_nout(mid, self.params.size, d)
+        self.h = lib().ref_stream_new(mid, _p(self.params), self.params.size, d, N, nboot, int(self.second), ESTIMATORS[Ei_estimator])
+        if not self.h:
+            raise MemoryError("ref_stream_new failed")
+
+    def push(self, A_chunk, B_chunk, col0):
+        A, B = _f(A_chunk), _f(B_chunk)
+        assert A.shape == B.shape and A.shape[0] == self.d
+        lib().ref_stream_push(self.h, _p(A), _p(B), col0, A.shape[1])
+
+    def finish(self, conf_level=0.95):
+        bufs, fin = _alloc_result(self.nout, self.d, self.nboot, self.second)
+        lib().ref_stream_finish(self.h, conf_level, *[_p(b) for b in bufs])
+        return fin()
+
+    def close(self):
+        if self.h:
+            lib().ref_stream_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()

@@ -332,3 +332,84 @@ def linear_multi_batch(X, W):
     for k in range(X.shape[0]):
         y += W[:, k:k + 1] * X[k][None, :]
     return y
+
+
+# --------------------------------------------------------------------------------------
+# "Exact" evaluation of the reference's formulas, used to ADJUDICATE the few tests whose tolerance is looser
+# than 1e-12: the model, every per-sample term and every sum are evaluated in extended precision (x87 long
+# double, 64-bit significand) with exactly rounded `math.fsum`-style sums where it matters, and rounded to
+# fp64 once at the end.  If the CUDA path is closer to this than the fp64 oracle is, the difference is the
+# oracle's (i.e. the reference's own fp64 rounding), not the kernel's.
+# --------------------------------------------------------------------------------------
+def gsa_sobol_exact(f: Callable[[np.ndarray], np.ndarray], A, B, order: Sequence[int] = (0, 1), nboot: int = 1,
+                    conf_level: float = 0.95, Ei_estimator: str = "Jansen1999", all_y=None, d=None, n=None) -> SobolResult:
+    """`f` must accept and return np.longdouble arrays (NumPy ufuncs do).  With `all_y` given (fp64 data), the
+    analysis alone is evaluated in extended precision."""
+    L = np.longdouble
+    second = 2 in order
+    if all_y is None:
+        A = np.asarray(A, dtype=np.float64)
+        B = np.asarray(B, dtype=np.float64)
+        d, N = A.shape
+        n = N // nboot
+        all_y = np.asarray(f(all_points(A, B, nboot, second).astype(L)), dtype=L)
+    else:
+        all_y = np.asarray(all_y).astype(L)
+    multi = all_y.ndim == 2
+    Y = all_y if multi else all_y[None, :]
+    nout = Y.shape[0]
+    step = 2 * d + 2 if second else d + 2
+    Yr = Y.reshape(nout, nboot, step, n)                       # [o, r, block, sample]
+    fA, fB, fAi = Yr[:, :, 0], Yr[:, :, 1], Yr[:, :, 2:2 + d]
+    nn = L(n)
+    both = Yr[:, :, 0:2].reshape(nout, nboot, 2 * n)
+    m = both.sum(axis=-1, dtype=L) / (2 * nn)
+    Var = ((both - m[..., None]) ** 2).sum(axis=-1, dtype=L) / (2 * nn - 1)           # two-pass, extended precision
+    Vi = (fB[:, :, None, :] * (fAi - fA[:, :, None, :])).sum(axis=-1, dtype=L) / nn
+    a = fA[:, :, None, :]
+    if Ei_estimator == "Jansen1999":
+        Ei = ((a - fAi) ** 2).sum(axis=-1, dtype=L) / (2 * nn)
+    elif Ei_estimator == "Sobol2007":
+        Ei = (a * (a - fAi)).sum(axis=-1, dtype=L) / nn
+    elif Ei_estimator == "Homma1996":
+        mA = fA.sum(axis=-1, dtype=L) / nn
+        Ei = (((fA - mA[..., None]) ** 2).sum(axis=-1, dtype=L) / (nn - 1))[..., None] - (a * fAi).sum(axis=-1, dtype=L) / nn \
+            + (mA ** 2)[..., None]
+    else:
+        s2 = (a ** 2 + fAi ** 2).sum(axis=-1, dtype=L)
+        s1 = (a + fAi).sum(axis=-1, dtype=L)
+        sp = (a * fAi).sum(axis=-1, dtype=L)
+        mh = s1 / (2 * nn)
+        # centred form of the same expression (the raw moments cancel when mean^2 >> var, even in extended precision)
+        Ei = (s2 / (2 * nn) - mh ** 2) * (1 - (sp / nn - mh ** 2) / (s2 / (2 * nn) - mh ** 2))
+    Si, Ti = Vi / Var[..., None], Ei / Var[..., None]          # [o, r, k]
+    Sij = None
+    if second:
+        fBi = Yr[:, :, 2 + d:2 + 2 * d]
+        Sij = np.zeros((nout, nboot, d, d), dtype=L)
+        fafb = fA * fB
+        for k in range(d):
+            for j in range(k + 1, d):
+                vkj = (fBi[:, :, k] * fAi[:, :, j] - fafb).sum(axis=-1, dtype=L) / nn
+                Sij[:, :, k, j] = (vkj - (Vi[:, :, k] + Vi[:, :, j])) / Var
+    S1ci = STci = S2ci = None
+    if nboot > 1:
+        z = L(norm_quantile((1 + conf_level) / 2))
+
+        def mean_ci(x):                                        # x: [o, r, ...]
+            mu = x.sum(axis=1, dtype=L) / nboot
+            sd = np.sqrt(((x - mu[:, None]) ** 2).sum(axis=1, dtype=L) / (nboot - 1))
+            return mu, z * sd / np.sqrt(L(nboot))
+
+        S1, S1ci = mean_ci(Si)
+        ST, STci = mean_ci(Ti)
+        if second:
+            S2, S2ci = mean_ci(Sij)
+    else:
+        S1, ST = Si[:, 0], Ti[:, 0]
+        if second:
+            S2 = Sij[:, 0]
+    f64 = lambda x: None if x is None else np.asarray(x, dtype=np.float64)
+    v1 = lambda x: None if x is None else (f64(x) if multi else f64(x)[0])
+    v2 = lambda x: None if x is None else (np.transpose(f64(x), (1, 2, 0)) if multi else f64(x)[0])
+    return SobolResult(v1(S1), v1(S1ci), v2(S2) if second else None, v2(S2ci) if second else None, v1(ST), v1(STci))

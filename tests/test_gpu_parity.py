@@ -28,6 +28,39 @@ def assert_parity(res, ref, tol=TOL, what=""):
             assert e <= tol, (f, what, e)
 
 
+def ulp_sensitivity(f, A, B, trials=8, **kw):
+    """How far +-1 ulp on every model value moves each index: max over `trials` random sign patterns of the distance between the
+    extended-precision evaluation (oracle/sobol_oracle.py gsa_sobol_exact) of the perturbed and of the unperturbed values."""
+    nboot, second = kw.get("nboot", 1), 2 in kw.get("order", (0, 1))
+    d, N = A.shape
+    n = N // nboot
+    y = np.asarray(f(so.all_points(np.asarray(A), np.asarray(B), nboot, second)), dtype=np.float64)
+    ex = so.gsa_sobol_exact(None, None, None, all_y=y, d=d, n=n, **kw)
+    rng = np.random.default_rng(0)
+    sens = {}
+    for _ in range(trials):
+        yp = np.where(rng.integers(0, 2, y.shape) == 1, np.nextafter(y, np.inf), np.nextafter(y, -np.inf))
+        pe = so.gsa_sobol_exact(None, None, None, all_y=yp, d=d, n=n, **kw)
+        for fld in FIELDS:
+            if getattr(ex, fld) is not None:
+                sens[fld] = max(sens.get(fld, 0.0), parity_err(getattr(pe, fld), getattr(ex, fld)))
+    return ex, sens
+
+
+def assert_parity_adjudicated(res, ref, f, A, B, what="", **kw):
+    """1e-12 against the oracle, or -- where the model values themselves differ by an ulp between CUDA's and glibc's libm --
+    within 4x what +-1 ulp on the model values does to the exact evaluation (and the oracle must be inside the same bound)."""
+    ex, sens = ulp_sensitivity(f, A, B, **kw)
+    for fld in FIELDS:
+        a, b = getattr(res, fld), getattr(ref, fld)
+        assert (a is None) == (b is None), (fld, what)
+        if a is None:
+            continue
+        bound = max(TOL, 4.0 * sens[fld])
+        e_gpu, e_orc = parity_err(a, getattr(ex, fld)), parity_err(b, getattr(ex, fld))
+        assert e_gpu <= bound and e_orc <= bound, (fld, what, e_gpu, e_orc, bound)
+
+
 # ------------------------------------------------------------------------------------------------ K1
 @pytest.mark.parametrize("n,d,num_mats", [(4, 4, 1), (8, 2, 1), (5, 3, 2), (1000, 3, 2), (600000, 4, 2), (4097, 100, 2),
                                            (300, 7, 40), (1, 2, 2), (65536, 1, 2)])
@@ -159,12 +192,14 @@ def test_edge_cases():
     ref = gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=(0, 1, 2), nboot=1000)
     res = g.gsa(ishi, g.Sobol(order=[0, 1, 2], nboot=1000), A, B, batch=True)
     assert_parity(res, ref)
-    # tiny designs
+    # tiny designs: a handful of values decide Var, so a 1-ulp difference between CUDA's and glibc's sin moves the indices by
+    # more than 1e-12.  Adjudicated: the bound is what +-1 ulp on the model values does to the
+    # extended-precision evaluation of the reference's formulas -- the kernel must stay within it, the oracle does too.
     for N, nboot in ((2, 1), (5, 2), (33, 1)):
         A, B = gsa_ref.sobol_design(N, lb, ub)
         ref = gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=(0, 1, 2), nboot=nboot)
         res = g.gsa(ishi, g.Sobol(order=[0, 1, 2], nboot=nboot), A, B, batch=True)
-        assert_parity(res, ref, tol=1e-11, what=(N, nboot))
+        assert_parity_adjudicated(res, ref, so.ishigami_batch, A, B, order=(0, 1, 2), nboot=nboot, what=(N, nboot))
     # nboot > N  =>  n = 0  =>  NaNs, as in the reference (SURVEY 8(b) "Errors")
     A, B = gsa_ref.sobol_design(3, lb, ub)
     res = g.gsa(ishi, g.Sobol(nboot=5), A, B, batch=True)
@@ -486,7 +521,12 @@ def test_linear_large_offset_inputs():
     A, B = gsa_ref.sobol_design(N, 1000.0 * np.ones(d), 1001.0 * np.ones(d))
     ref = gsa_ref.gsa_sobol("linear", W, A, B)
     res = g.gsa(g.DeviceModel("linear", W), g.Sobol(), A, B, batch=True)
-    assert parity_err(res.S1, ref.S1) < 1e-9 and parity_err(res.ST, ref.ST) < 1e-9      # the oracle's own fB*(fAB-fA) cancels here
+    # Adjudicated: y ~ 1e4 carries ~1e-12 of rounding, which the reference's fB*(fAB-fA) amplifies -- the fp64
+    # oracle is ~5e-11 off the extended-precision value of its own formula (tests/test_oracle_golden.py
+    # test_offset_inputs_fp64_model_rounding_dominates); the kernel's shifted moment form is not: 1e-12 against the exact value.
+    ex = so.gsa_sobol_exact(lambda X: W.astype(np.longdouble) @ X, A, B)
+    assert parity_err(res.S1, ex.S1) < TOL and parity_err(res.ST, ex.ST) < TOL, (parity_err(res.S1, ex.S1), parity_err(res.ST, ex.ST))
+    assert parity_err(ref.S1, ex.S1) < 1e-9 and parity_err(ref.ST, ex.ST) < TOL
 
 
 def test_linear_streamed_shards():
@@ -556,7 +596,7 @@ def test_user_device_model_from_fatbin(tmp_path):
     res = g.gsa(m, g.Sobol(order=[0, 1, 2], nboot=3), A, B, batch=True)
     ref = so.gsa_sobol(f2, A, B, order=(0, 1, 2), nboot=3)
     assert res.S1.shape == (2, d) and res.S2.shape == (d, d, 2)
-    assert_parity(res, ref, tol=1e-11)        # the model itself is evaluated by different libm's (sin): a few ulp per value
+    assert_parity_adjudicated(res, ref, f2, A, B, order=(0, 1, 2), nboot=3)     # sin: CUDA's and glibc's libm differ by an ulp
     # the default symbol name, one output, another estimator
     m1 = g.DeviceModel.from_fatbin(fat1.read_bytes(), "gsa_user_model", nout=1, params=[3.0])
     res = g.gsa(m1, g.Sobol(), A, B, batch=True, Ei_estimator="Sobol2007")
@@ -573,6 +613,8 @@ def test_multi_device_user_model(tmp_path):
     import shutil
     import subprocess
     import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2; evidence: profiles/r2_multi_gpu_tests.txt)")
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     src = tmp_path / "um.cu"
     src.write_text(USER_MODEL_CU)
@@ -584,16 +626,27 @@ def test_multi_device_user_model(tmp_path):
     m = g.GsaMulti(ndev=torch.cuda.device_count())
     model = m.model_from_fatbin(str(fat), "my_model", nout=1, params=p)
     res = m.gsa(model, g.Sobol(order=[0, 1, 2], nboot=2), A, B)
-    ref = so.gsa_sobol(lambda X: (p[:, None] * X * X).sum(axis=0) + X[0] * X[1], A, B, order=(0, 1, 2), nboot=2)
-    assert_parity(res, ref, tol=1e-11)
+    fm = lambda X: (p[:, None] * X * X).sum(axis=0) + X[0] * X[1]
+    ref = so.gsa_sobol(fm, A, B, order=(0, 1, 2), nboot=2)
+    assert_parity_adjudicated(res, ref, fm, A, B, order=(0, 1, 2), nboot=2)     # the sum over k is contracted to FMAs on the device
+    m.close()
+
+
+def test_multi_device_entry_on_one_device(ishigami_design):
+    """The gsa_multi entry (what a plain Julia ccall uses) with a single device: the same code path minus the peer gather."""
+    m = g.GsaMulti(ndev=1)
+    A, B = ishigami_design
+    ref = gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=(0, 1, 2), nboot=20)
+    assert_parity(m.gsa(g.DeviceModel("ishigami", [7.0, 0.1]), g.Sobol(order=[0, 1, 2], nboot=20), A, B), ref)
     m.close()
 
 
 def test_multi_device_single_process(ishigami_design):
-    """gsa_multi: one process, all visible GPUs, one gather-and-add kernel over NVLink peer memory for the partial sums.  Runs with
-    a single device too (then no collective is issued)."""
+    """gsa_multi: one process, all visible GPUs, one gather-and-add kernel over NVLink peer memory for the partial sums."""
     import torch
     ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2; evidence: profiles/r2_multi_gpu_tests.txt)")
     m = g.GsaMulti(ndev=ndev)
     A, B = ishigami_design
     ref = gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=(0, 1, 2), nboot=20)
@@ -648,9 +701,11 @@ def test_plain_c_client_of_the_abi(tmp_path):
 
 def test_peer_allreduce_two_ranks():
     """K5 over NVLink peer memory (csrc/peer.cu), one process per GPU under torchrun: sums equal NCCL's, are bit-identical on
-    every rank, and a sharded analysis equals the single-GPU one.  With one GPU the same protocol runs with world = 1."""
+    every rank, and a sharded analysis equals the single-GPU one."""
     import subprocess, sys, torch
-    nproc = min(2, torch.cuda.device_count())
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2; evidence: profiles/r2_multi_gpu_tests.txt)")
+    nproc = 2
     root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(root, "tools", "peer_probe.py")]
@@ -806,6 +861,89 @@ def test_config4_full_size_analytic():
     assert_parity(g.sobol_finalize(method, total, d, N), res)
 
 
+# ------------------------------------------------------------------------------------------------ BASELINE configs at FULL size
+# against the streamed exact-sum oracle (oracle/gsa_ref_streamed.c: full model per swapped coordinate, reference-formed terms,
+# exact sums; gated against the materialising oracle and the reference's literals in tests/test_oracle_golden.py).  The oracle
+# is fed the SAME A/B the kernels read, copied back from the device chunk by chunk.  Tolerance: the full 1e-12.
+def _stream_oracle_from_device(model, params, A, B, chunk, **kw):
+    d, N = A.shape
+    s = gsa_ref.Stream(model, params, d, N, **kw)
+    for c0 in range(0, N, chunk):
+        c1 = min(N, c0 + chunk)
+        s.push(A[:, c0:c1].t().cpu().numpy().T, B[:, c0:c1].t().cpu().numpy().T, c0)
+    res = s.finish()
+    s.close()
+    return res
+
+
+def test_config1_and_2_full_size_vs_both_oracles():
+    """BASELINE configs 1 (README example: Ishigami, Sobol(), N = 600000) and 2 (order=[0,1,2], nboot=1000, N = 2^20)."""
+    lb, ub = -np.pi * np.ones(3), np.pi * np.ones(3)
+    ishi = g.DeviceModel("ishigami", [7.0, 0.1])
+    for N, order, nboot in ((600000, (0, 1), 1), (1 << 20, (0, 1, 2), 1000)):
+        A, B = g.generate_design_matrices(N, lb, ub)
+        res = g.gsa(ishi, g.Sobol(order=list(order), nboot=nboot), A, B, batch=True)
+        assert_parity(res, gsa_ref.gsa_sobol("ishigami", [7.0, 0.1], A, B, order=order, nboot=nboot), what=("materialising", N))
+        assert_parity(res, gsa_ref.gsa_sobol_streamed("ishigami", [7.0, 0.1], A, B, order=order, nboot=nboot), what=("streamed", N))
+        gen = g.gsa(ishi, g.Sobol(order=list(order), nboot=1), [[-np.pi, np.pi]] * 3, samples=N, batch=True)     # p_range entry
+        exg = gsa_ref.gsa_sobol_streamed_generated("ishigami", [7.0, 0.1], lb, ub, N, order=order, nboot=1)
+        assert_parity(gen, exg, what=("generated", N))
+
+
+def test_config3_full_size_vs_streamed_oracle():
+    d, N = 8, 1 << 22
+    a = np.array([0.0, 1.0, 4.5, 9.0, 99.0, 99.0, 99.0, 99.0])
+    A, B = g.generate_design_matrices(N, np.zeros(d), np.ones(d), 2, device=True)
+    res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2]), A, B, batch=True)
+    ex = _stream_oracle_from_device("sobol_g", a, A, B, 1 << 20, order=(0, 1, 2))
+    assert_parity(res, ex)
+    for est in ("Sobol2007", "Homma1996", "Janon2014"):
+        res = g.gsa(g.DeviceModel("sobol_g", a), g.Sobol(order=[0, 1, 2], nboot=4), A, B, batch=True, Ei_estimator=est)
+        assert_parity(res, _stream_oracle_from_device("sobol_g", a, A, B, 1 << 20, order=(0, 1, 2), nboot=4, Ei_estimator=est), what=est)
+
+
+def test_config4_full_size_vs_streamed_oracle():
+    """BASELINE config 4 at FULL size (linear, d = 20, 256 outputs, N = 2^22; the reference's all_y would be 189 GB)."""
+    d, nout, N = 20, 256, 1 << int(os.environ.get("GSA_TEST_C4_LOG2N", "22"))
+    o, i = np.meshgrid(np.arange(1, nout + 1), np.arange(1, d + 1), indexing="ij")
+    W = 1.0 + ((o * 31 + i * 17) % 13) / 13.0
+    A, B = g.generate_design_matrices(N, np.zeros(d), np.ones(d), 2, device=True)
+    res = g.gsa(g.DeviceModel("linear", W), g.Sobol(), A, B, batch=True)
+    ex = _stream_oracle_from_device("linear", W, A, B, 1 << 20)
+    assert res.S1.shape == (nout, d)
+    assert_parity(res, ex)
+
+
+def test_config5_full_size_vs_streamed_oracle():
+    """BASELINE config 5 at FULL size (Sobol G, d = 100, S1/ST, N = 2^26: 107 GB of design in HBM): the resident fused kernel,
+    the 8-shard sum of partials (what 8 GPUs add up) and the design-generating kernel, each within 1e-12 of the oracle."""
+    import torch
+    d, N = 100, 1 << int(os.environ.get("GSA_TEST_C5_LOG2N", "26"))
+    a = np.array([0.0, 1.0, 4.5, 9.0] + [99.0] * 96)
+    model, method = g.DeviceModel("sobol_g", a), g.Sobol()
+    lb, ub = np.zeros(d), np.ones(d)
+    A, B = g.generate_design_matrices(N, lb, ub, 2, device=True)
+    whole = g.gsa(model, method, A, B, batch=True)
+    total = None
+    for rank in range(8):
+        c0, nc = g.shard_columns(N, rank, 8)
+        p = g.sobol_partials(model, method, A[:, c0:c0 + nc], B[:, c0:c0 + nc], N, c0)
+        total = p.clone() if total is None else total + p
+    torch.cuda.synchronize()
+    sharded = g.sobol_finalize(method, total, d, N)
+    gen = g.gsa(model, method, [[0.0, 1.0]] * d, samples=N, batch=True)
+    # spot-check that the oracle's own generator and K1 agree at this scale (a chunk at the far end of the sequence)
+    c0 = N - (1 << 12)
+    Ar, Br = gsa_ref.sobol_design(N, lb, ub, 2, col0=c0, ncols=1 << 12)
+    assert np.array_equal(A[:, c0:].t().cpu().numpy().T, Ar) and np.array_equal(B[:, c0:].t().cpu().numpy().T, Br)
+    ex = _stream_oracle_from_device("sobol_g", a, A, B, 1 << 19)
+    for name, r in (("resident", whole), ("8 shards", sharded), ("generated", gen)):
+        assert_parity(r, ex, what=name)
+    Vi = 1.0 / (3.0 * (1.0 + a) ** 2)
+    V = np.prod(1.0 + Vi) - 1.0
+    assert np.abs(whole.S1 - Vi / V).max() < 1e-4
+
+
 @pytest.mark.parametrize("d", [13, 16, 17, 24, 32, 33])
 def test_analyze_y_mid_d_first_order(d):
     """First-order estimator-on-Y for 12 < d <= 32 runs on the register kernel (Jansen) -- d = 33 and the three-term estimators
@@ -831,9 +969,13 @@ def test_variance_robust_when_mean_dominates(d, second):
     P = gsa_ref.all_points(A, B, nboot, second)
     Y = 1.0e5 + 1.0e-3 * gsa_ref.model_batch("sobol_g", a, P)
     ref = gsa_ref.analyze_y(Y, d, N // nboot, order=order, nboot=nboot)
+    ex = gsa_ref.analyze_y(Y, d, N // nboot, order=order, nboot=nboot, exact=True)
     res = g.gsa_sobol_all_y_analysis(g.Sobol(order=order, nboot=nboot), Y, d, N // nboot)
-    assert parity_err(res.ST, ref.ST) < 1e-10, parity_err(res.ST, ref.ST)
-    assert parity_err(res.ST_Conf_Int, ref.ST_Conf_Int) < 1e-10
+    # Adjudicated: the reference's two-pass var is exact here (fp64 oracle == exact-sum oracle to 1e-13,
+    # tests/test_oracle_golden.py test_mean_dominated_data_all_three_evaluations_agree_on_ST), so the full 1e-12 applies.
+    assert parity_err(ref.ST, ex.ST) < 1e-13
+    assert parity_err(res.ST, ex.ST) < TOL, parity_err(res.ST, ex.ST)
+    assert parity_err(res.ST_Conf_Int, ex.ST_Conf_Int) < TOL, parity_err(res.ST_Conf_Int, ex.ST_Conf_Int)
 
 
 def test_empty_and_degenerate_inputs():
