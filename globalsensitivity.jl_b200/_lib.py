@@ -56,6 +56,7 @@ SIGNATURES = {
     "gsa_sobol_run_generated": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
     "gsa_sobol_partials_generated": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _i64, _i64, _vp],
     "gsa_sobol_partials_y": [_vp, _op, _vp, _i, _i, _i64, _vp],
+    "gsa_sobol_combine": [_vp, _i, _sz, _i, _vp],
     "gsa_sobol_finalize": [_op, _vp, _i, _i, _i64, _rp],
     "gsa_sobol_analyze_y": [_vp, _op, _vp, _i, _i, _i64, _rp],
     "gsa_sobol_all_points": [_vp, _op, _vp, _vp, _i, _i64, _vp, _i],

@@ -97,19 +97,6 @@ void direction_numbers(int dim_first, int ndim, uint32_t* V) {
     }
 }
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-    }
-    ~DeviceGuard() {
-        int cur = -1;
-        cudaGetDevice(&cur);
-        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
-    }
-};
-
 static bool is_device_or_pinned(const void* p, bool* is_device) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -267,6 +254,13 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
 
     FusedPlan plan;
     if ((rc = plan_fused(h, model, d, nout, np, second, est, &plan, gen != nullptr))) return rc;
+    if (!gen && (plan.kind == PLAN_SMALL_ISHIGAMI || plan.kind == PLAN_SMALL_SOBOLG) && d % 2 == 0 && o->input_location == GSA_LOC_DEVICE &&
+        ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15)) {
+        // the register kernels read even-d rows with 16-byte vector loads; a device view that starts at an odd element takes
+        // the generic kernel instead of faulting (the C ABI accepts any device pointer)
+        plan.tiles_per_cta = 2;
+        if ((rc = plan_generic(h, &plan))) return rc;
+    }
     if (gen) {
         if ((int64_t)2 * o->nboot * d > 21201)
             return fail(GSA_ERR_INVALID, "2*nboot*d = %lld exceeds the 21201 dimensions of the Joe-Kuo table", (long long)2 * o->nboot * d);
@@ -405,10 +399,10 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
                 double* dB = dA + (size_t)d * (size_t)tiles_per_chunk * g.ts;
                 const double* hA = A + (size_t)d * (size_t)(c0 - col0);
                 const double* hB = B + (size_t)d * (size_t)(c0 - col0);
-                if (ci >= 2) {
-                    GSA_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));   // buffer free again?
-                    if (!pinned) GSA_CUDA(cudaEventSynchronize(h->ev_copy[b]));        // staging buffer drained?
-                }
+                // buffer b free again?  Also on the first two chunks: the previous (asynchronous) call on this handle may still be
+                // reading it.  Never-recorded events are complete, so the first call does not wait.
+                GSA_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));
+                if (!pinned) GSA_CUDA(cudaEventSynchronize(h->ev_copy[b]));            // staging buffer drained?
                 if (pinned) {
                     GSA_CUDA(cudaMemcpyAsync(dA, hA, bytes, cudaMemcpyHostToDevice, h->copy_stream));
                     GSA_CUDA(cudaMemcpyAsync(dB, hB, bytes, cudaMemcpyHostToDevice, h->copy_stream));
@@ -601,6 +595,7 @@ int gsa_create(int device, gsa_handle** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&h->evk0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->evk1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_params, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_switch, cudaEventDisableTiming);
     for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
         e = cudaEventCreateWithFlags(&h->ev_copy[b], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming);
@@ -635,6 +630,7 @@ int gsa_destroy(gsa_handle* h) {
         if (h->evk0) cudaEventDestroy(h->evk0);
         if (h->evk1) cudaEventDestroy(h->evk1);
         if (h->ev_params) cudaEventDestroy(h->ev_params);
+        if (h->ev_switch) cudaEventDestroy(h->ev_switch);
         if (h->own_stream) cudaStreamDestroy(h->own_stream);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     }
@@ -645,7 +641,15 @@ int gsa_destroy(gsa_handle* h) {
 int gsa_set_stream(gsa_handle* h, void* s, int external) {
     if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
     std::lock_guard<std::mutex> lk(h->mu);
-    h->stream = external ? static_cast<cudaStream_t>(s) : h->own_stream;
+    cudaStream_t next = external ? static_cast<cudaStream_t>(s) : h->own_stream;
+    if (next != h->stream) {
+        // the handle's scratch (tile records, staging buffers, Gram moments) is shared by everything it runs: whatever was issued
+        // on the old stream must finish before work on the new stream may reuse it
+        DeviceGuard guard(h->device);
+        GSA_CUDA(cudaEventRecord(h->ev_switch, h->stream));
+        GSA_CUDA(cudaStreamWaitEvent(next, h->ev_switch, 0));
+        h->stream = next;
+    }
     return GSA_OK;
 }
 
@@ -807,6 +811,25 @@ int gsa_sobol_partials_y(gsa_handle* h, const gsa_sobol_opts* opts, const double
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->device);
     return partials_y_impl(h, opts, Y, nout, d, n, partials_dev);
+}
+
+int gsa_sobol_combine(const double* parts_host, int nparts, size_t count, int nstat, double* out_host) {
+    if (!parts_host || !out_host || nparts < 1 || nstat < STAT_DD || count % (size_t)nstat) return fail(GSA_ERR_INVALID, "bad arguments to gsa_sobol_combine");
+    for (size_t i = 0; i < count; ++i) {
+        const int e = (int)(i % (size_t)nstat);
+        if (e < STAT_DD) {
+            if (e & 1) continue;
+            dd s{0.0, 0.0};
+            for (int g = 0; g < nparts; ++g) dd_add_dd(s, dd{parts_host[(size_t)g * count + i], parts_host[(size_t)g * count + i + 1]});
+            out_host[i] = s.hi;
+            out_host[i + 1] = s.lo;
+        } else {
+            double s = 0.0;
+            for (int g = 0; g < nparts; ++g) s += parts_host[(size_t)g * count + i];
+            out_host[i] = s;
+        }
+    }
+    return GSA_OK;
 }
 
 int gsa_sobol_finalize(const gsa_sobol_opts* opts, const double* partials_host, int nout, int d, int64_t n, gsa_sobol_result* out) {

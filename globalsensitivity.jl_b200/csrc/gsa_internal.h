@@ -32,6 +32,20 @@ struct DevBuf {
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 
+// sets the calling thread's current device for a scope and restores the previous one on every return path
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
 int finalize_host(const gsa_sobol_opts& o, const double* partials, int nout, int d, int64_t n, gsa_sobol_result* out);
 double host_norm_quantile(double p);
 
@@ -56,7 +70,7 @@ struct gsa_handle {
     int device = 0;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, ev_params = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, ev_params = nullptr, ev_switch = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     std::mutex mu;
     gsa::DevBuf tile_rec, partials, params, vtab, lbub, stage[2], dev_in[2], ybuf, aux, gram;
     void* pinned[2] = {nullptr, nullptr};

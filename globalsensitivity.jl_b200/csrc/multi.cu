@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <chrono>
 #include <thread>
 #include <vector>
@@ -68,8 +69,14 @@ struct gsa_multi {
 extern "C" {
 
 int gsa_multi_create(const int* devices, int ndev, gsa_multi** out) {
-    if (!out || ndev < 1 || ndev > 64) return fail(GSA_ERR_INVALID, "bad arguments to gsa_multi_create");
+    if (!out || ndev < 0 || ndev > 64) return fail(GSA_ERR_INVALID, "bad arguments to gsa_multi_create");
     *out = nullptr;
+    if (ndev == 0) {   // all visible devices
+        if (devices) return fail(GSA_ERR_INVALID, "gsa_multi_create: ndev == 0 (all devices) takes devices == NULL");
+        GSA_CUDA(cudaGetDeviceCount(&ndev));
+        if (ndev < 1) return fail(GSA_ERR_CUDA, "no CUDA device visible");
+        ndev = std::min(ndev, MULTI_MAX_DEV);
+    }
     gsa_multi* m = new (std::nothrow) gsa_multi();
     if (!m) return fail(GSA_ERR_NOMEM, "out of host memory");
     std::vector<int> devs(ndev);
@@ -157,6 +164,7 @@ static int multi_run(gsa_multi* m, const gsa_sobol_opts* opts, int model_id, con
     MDBG("run: enter");
     std::lock_guard<std::mutex> lk(m->mu);
     const int G = (int)m->h.size();
+    DeviceGuard guard(m->h[0]->device);   // the caller's current device is restored on every return path
     int nout = 0, rc;
     if (d < 1) return fail(GSA_ERR_INVALID, "d must be >= 1");
     if ((rc = model_nout_entry(m->h[0], model_id, nparams, d, &nout))) return rc;

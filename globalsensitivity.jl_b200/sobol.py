@@ -491,7 +491,7 @@ def gsa(f, method: Sobol, A, B=None, *, batch: bool = False, Ei_estimator="Janse
             # fused design generation: the kernel generates the points it evaluates (no A/B in memory at all)
             d = len(lb)
             nout = f.nout(d)
-            o = _opts(method, Ei_estimator, LOC_DEVICE)
+            o = _opts(method, Ei_estimator, LOC_HOST)
             rc, finish, _ = _alloc_result(nout, d, method.nboot, 2 in method.order, nout > 1)
             lbv, ubv = np.ascontiguousarray(lb, dtype=np.float64), np.ascontiguousarray(ub, dtype=np.float64)
             code = lib().gsa_sobol_run_generated(h.ptr, C.byref(o), f.model_id, f.params.ctypes.data, f.params.size,
@@ -619,12 +619,21 @@ def sobol_finalize(method: Sobol, partials, d: int, N: int, *, Ei_estimator="Jan
 
 
 def reduce_and_finalize(method: Sobol, partials, d: int, N: int, *, Ei_estimator="Jansen1999", group=None) -> SobolResult:
-    """K5: the single collective of the path.  Sums the per-rank partial sums (nboot, nout, nstat) over the ranks of
-    `group` with one `torch.distributed.all_reduce` (NCCL on GPUs; gloo in the CPU tests) -- a few KB -- and runs the
-    host epilogue.  Every rank returns the same SobolResult."""
+    """K5 through torch.distributed (NCCL on GPUs; gloo in the CPU tests): the per-rank partial sums (nboot, nout, nstat) -- a
+    few KB -- are all-gathered and added IN RANK ORDER by gsa_sobol_combine, which adds the (hi, lo) pairs of the
+    double-double entries error-free (a plain all_reduce(SUM) would add hi and lo words independently and lose the
+    mean^2 >> var robustness the single-GPU path has); then the host epilogue.  Every rank returns the same SobolResult."""
+    import torch
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(partials, op=dist.ReduceOp.SUM, group=group)
+        world = dist.get_world_size(group)
+        p = partials.contiguous()
+        parts = [torch.empty_like(p) for _ in range(world)]
+        dist.all_gather(parts, p, group=group)
+        stacked = np.ascontiguousarray(torch.stack(parts).cpu().numpy(), dtype=np.float64)
+        out = np.empty(p.shape, dtype=np.float64)
+        check(lib().gsa_sobol_combine(stacked.ctypes.data, world, int(p.numel()), int(p.shape[-1]), out.ctypes.data))
+        partials = out
     return sobol_finalize(method, partials, d, N, Ei_estimator=Ei_estimator)
 
 

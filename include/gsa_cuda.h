@@ -153,6 +153,12 @@ GSA_API int gsa_sobol_partials_generated(gsa_handle* h, const gsa_sobol_opts* op
 GSA_API int gsa_sobol_partials_y(gsa_handle* h, const gsa_sobol_opts* opts, const double* Y, int nout, int d,
                          int64_t n, double* partials_dev);
 
+/* Sum of `nparts` partial-sum vectors (HOST memory, parts[g*count + i], count = nboot*nout*nstat) in part order; the four
+ * double-double (hi, lo) pairs at the head of every record are added error-free, so the result does not depend on how the
+ * design was sharded beyond the last ulp.  What a caller that gathers the shards' sums itself (MPI, torch.distributed
+ * all_gather, Distributed.jl) calls before gsa_sobol_finalize. */
+GSA_API int gsa_sobol_combine(const double* parts_host, int nparts, size_t count, int nstat, double* out_host);
+
 /* (:318-404) partial sums (HOST memory, nboot*nout*nstat) -> SobolResult.  n = N / nboot. Pure host code. */
 GSA_API int gsa_sobol_finalize(const gsa_sobol_opts* opts, const double* partials_host, int nout, int d, int64_t n,
                        gsa_sobol_result* out);
@@ -193,7 +199,7 @@ GSA_API int gsa_peer_unmap(gsa_handle* h);
 GSA_API int gsa_peer_disconnect(gsa_handle* h);
 
 /* ---- single-process, multi-device form (a plain Julia `ccall` from one process) ------------------ */
-/* devices == NULL: devices 0..ndev-1.  Creates one gsa_handle per device and enables peer access from the first device to
+/* devices == NULL: devices 0..ndev-1; ndev == 0 (with devices == NULL): every visible device.  Creates one gsa_handle per device and enables peer access from the first device to
  * the others (up to 16 devices). */
 GSA_API int gsa_multi_create(const int* devices, int ndev, gsa_multi** out);
 GSA_API int gsa_multi_destroy(gsa_multi* m);

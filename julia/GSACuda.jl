@@ -128,7 +128,7 @@ function gsa(model::DeviceModel, method::Sobol, p_range::AbstractVector; samples
     lb = [float(p[1]) for p in p_range]; ub = [float(p[2]) for p in p_range]
     # first choice: the design is generated inside the fused kernel (no A/B in memory at all) ...
     d = length(lb); second = 2 in method.order
-    opts = Ref(GsaSobolOpts(second, method.nboot, method.conf_level, EI[Ei_estimator], 1))
+    opts = Ref(GsaSobolOpts(second, method.nboot, method.conf_level, EI[Ei_estimator], 0))   # lb, ub are host vectors
     res, finish, keep = alloc(nout(model, d), d, method.nboot, second)
     rc = GC.@preserve keep model lb ub ccall((:gsa_sobol_run_generated, libgsa), Cint,
         (Ptr{Cvoid}, Ref{GsaSobolOpts}, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Int64, Ref{GsaSobolResult}),
@@ -169,11 +169,12 @@ end
 # ---- one process, all GPUs (gsa_multi_*): contiguous column shards, one gather-and-add kernel over NVLink peer memory for the partial sums ----------------
 mutable struct Multi
     ptr::Ptr{Cvoid}
+    # Multi() drives ALL visible GPUs (ndev = 0 asks the library to enumerate them); Multi([0, 2]) the listed ones
     function Multi(devices::Vector{<:Integer} = Int[])
         r = Ref{Ptr{Cvoid}}(C_NULL)
         devs = Cint.(devices)
         check(ccall((:gsa_multi_create, libgsa), Cint, (Ptr{Cint}, Cint, Ref{Ptr{Cvoid}}),
-                    isempty(devs) ? C_NULL : devs, max(length(devs), 1), r))
+                    isempty(devs) ? C_NULL : devs, length(devs), r))
         m = new(r[])
         finalizer(x -> ccall((:gsa_multi_destroy, libgsa), Cint, (Ptr{Cvoid},), x.ptr), m)
         return m
@@ -196,7 +197,7 @@ end
 function gsa(m::Multi, model::DeviceModel, method::Sobol, p_range::AbstractVector; samples, Ei_estimator = :Jansen1999)
     lb = [float(p[1]) for p in p_range]; ub = [float(p[2]) for p in p_range]
     d = length(lb); second = 2 in method.order
-    opts = Ref(GsaSobolOpts(second, method.nboot, method.conf_level, EI[Ei_estimator], 1))
+    opts = Ref(GsaSobolOpts(second, method.nboot, method.conf_level, EI[Ei_estimator], 0))
     res, finish, keep = alloc(nout(model, d), d, method.nboot, second)
     GC.@preserve keep model lb ub begin
         check(ccall((:gsa_multi_sobol_run_generated, libgsa), Cint,

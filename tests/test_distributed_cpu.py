@@ -21,7 +21,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, nboot, est, out_q):
+def _offset_model(X):
+    """mean^2 / var ~ 1e16: the (hi, lo) pairs of the record matter"""
+    return 1.0e5 + 1.0e-3 * so.ishi_linear_batch(X)
+
+
+def _worker(rank, world, port, nboot, est, out_q, offset=False):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (root, os.path.join(root, "oracle"), os.path.join(root, "tests")):
         if p not in sys.path:
@@ -35,7 +40,7 @@ def _worker(rank, world, port, nboot, est, out_q):
     d, N = 4, 3001
     A, B = so.generate_design_matrices(N, -np.pi * np.ones(d), np.pi * np.ones(d))
     col0, ncols = g.shard_columns(N, rank, world)
-    P = sr.shard_records(so.ishi_linear_batch, A, B, nboot, True, est, col0, ncols)     # this rank's shard only
+    P = sr.shard_records(_offset_model if offset else so.ishi_linear_batch, A, B, nboot, True, est, col0, ncols)     # this rank's shard only
     res = g.reduce_and_finalize(g.Sobol(order=[0, 1, 2], nboot=nboot), torch.from_numpy(P), d, N, Ei_estimator=est)
     out_q.put((rank, {f: getattr(res, f) for f in ("S1", "ST", "S2", "S1_Conf_Int", "ST_Conf_Int", "S2_Conf_Int")}))
     dist.barrier()
@@ -66,3 +71,26 @@ def test_two_rank_allreduce_matches_oracle(nboot, est):
     for f in got[0]:
         if got[0][f] is not None:
             assert np.array_equal(got[0][f], got[1][f])          # every rank returns identical results
+
+
+def test_two_rank_reduce_keeps_double_double_pairs():
+    """mean^2 >> var across ranks: the all-gather + ordered double-double combine must reproduce the two-pass
+    variance of the whole design; adding hi and lo words independently (a plain all_reduce) would not."""
+    world, port, nboot, est = 2, _free_port(), 2, "Jansen1999"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nboot, est, q, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    d, N = 4, 3001
+    A, B = so.generate_design_matrices(N, -np.pi * np.ones(d), np.pi * np.ones(d))
+    Y = _offset_model(so.all_points(A, B, nboot, True))             # the fp64 model values the shards saw; their analysis is exact below
+    ex = so.gsa_sobol_exact(None, None, None, order=(0, 1, 2), nboot=nboot, Ei_estimator=est, all_y=Y, d=d, n=N // nboot)
+    for rank in range(world):
+        for f in ("ST", "ST_Conf_Int"):                        # ST (Jansen) isolates Var; S1 is noise in the reference's own formula here
+            v, r = got[rank][f], getattr(ex, f)
+            assert np.max(np.abs(v - r) / np.maximum(1.0, np.abs(r))) <= 1e-12, (rank, f)
