@@ -8,10 +8,10 @@ All numerics run in libgsa_cuda.so (hand-written sm_100a CUDA behind a C ABI, in
 """
 from .sobol import (DeviceModel, GsaHandle, GsaMulti, PeerGroup, Sobol, SobolResult, default_handle, generate_design_matrices, sample, gsa,
                     gsa_sobol_all_y_analysis, nstat, sobol_partials, sobol_partials_generated, sobol_finalize, shard_columns,
-                    reduce_and_finalize, gsa_sharded)
+                    reduce_and_finalize, gsa_sharded, ShardedStep)
 from . import sobol
 from ._lib import GsaError, LIB_PATH, lib
 
 __all__ = ["gsa", "Sobol", "SobolResult", "DeviceModel", "GsaHandle", "GsaMulti", "PeerGroup", "generate_design_matrices", "sample",
-           "gsa_sobol_all_y_analysis", "sobol_partials", "sobol_partials_generated", "sobol_finalize", "shard_columns", "nstat", "reduce_and_finalize", "gsa_sharded", "default_handle",
+           "gsa_sobol_all_y_analysis", "sobol_partials", "sobol_partials_generated", "sobol_finalize", "shard_columns", "nstat", "reduce_and_finalize", "gsa_sharded", "ShardedStep", "default_handle",
            "GsaError", "LIB_PATH", "lib"]

@@ -53,6 +53,8 @@ SIGNATURES = {
     "gsa_sobol_nstat": [_op, _i, _ip],
     "gsa_sobol_run": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
     "gsa_sobol_partials": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _i64, _i64, _vp],
+    "gsa_sobol_run_sharded": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _i64, _i64, _rp],
+    "gsa_sobol_run_sharded_generated": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _i64, _i64, _rp],
     "gsa_sobol_run_generated": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
     "gsa_sobol_partials_generated": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _i64, _i64, _vp],
     "gsa_sobol_partials_y": [_vp, _op, _vp, _i, _i, _i64, _vp],

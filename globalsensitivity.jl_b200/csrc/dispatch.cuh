@@ -38,6 +38,8 @@ struct FusedPlan {
     bool writes_partials() const { return kind == PLAN_LINEAR; }   // the plan adds its records to `out_partials` itself
     double* out_partials = nullptr;
     double* rec_base = nullptr;   // where the tile records go: h->tile_rec, or straight into `partials` when a replicate is one tile
+    TailArgs tail{};              // tail.counter != nullptr: the launch ends with stage 2 + exchange + host copy in its last CTA (tail.cuh)
+    bool supports_tail() const { return kind == PLAN_PRODUCT; }
 
     int prepare(gsa_handle* h, const double* params, int np);
     int launch(gsa_handle* h, const double* A, const double* B, const TileGeom& g, int t0, int t1);
@@ -341,6 +343,8 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = recs;
         a.g = g; a.d = d; a.nstat = nstat; a.t_begin = t0; a.t_end = t1; a.est = est;
         a.V = h->vtab.as<uint32_t>(); a.box = h->lbub.as<double2>(); a.first = gen_first; a.nboot = gen_nboot; a.unit_box = gen_unit_box;
+        a.tail = tail;
+        if (tail.counter) a.tail.target = (h->tail_arrived += (unsigned long long)grid);
         ((ProductKernel)kernel)<<<grid, threads, smem, h->stream>>>(a);
     }
     GSA_CUDA(cudaEventRecord(h->evk1, h->stream));

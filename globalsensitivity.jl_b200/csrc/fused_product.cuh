@@ -17,6 +17,7 @@
 // order (bitwise reproducible).  The AB_k matrices of fuse_designs (:94-108) never exist.
 #pragma once
 #include "gsa_common.cuh"
+#include "tail.cuh"
 
 namespace gsa {
 
@@ -33,6 +34,7 @@ struct ProductArgs {
     const double2* box;   // [d] (ub-lb, lb)
     uint64_t first;       // 0-based sequence index of sample 0 of every replicate: 2^floor(log2 samples)
     int nboot, unit_box;  // unit_box: lb = 0, ub = 1 for every coordinate (the affine map is the identity)
+    TailArgs tail;        // tail.counter != nullptr: stage 2, the all-reduce and the host copy run in this launch's last CTA
 };
 
 #ifndef PROD_GEN_MINBLOCKS
@@ -193,9 +195,18 @@ __global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fu
             if (T == 1) {
                 dd_add(sA1, yA); dd_add_sq(sA2, yA);
                 dd_add(sB1, yB); dd_add_sq(sB2, yB);
-            } else {
-                const double y = t == 0 ? yA : yB;  // lanes >= 2 accumulate a copy that is never used
+            } else if (T == 2) {
+                const double y = t == 0 ? yA : yB;
                 dd_add(sA1, y); dd_add_sq(sA2, y);
+            } else if (t < 4) {
+                // T >= 4: lanes 0..3 of the group own sum yA, sum yA^2, sum yB, sum yB^2 -- ONE double-double update per sample
+                // (x or x*x with its exact product error), and the other lanes of the group do none
+                const double y = (t & 2) ? yB : yA;
+                const double p = (t & 1) ? y * y : y;
+                const double pe = (t & 1) ? __fma_rn(y, y, -p) : 0.0;
+                dd s2 = two_sum(sA1.hi, p);
+                s2.lo += sA1.lo + pe;
+                sA1 = quick_two_sum(s2.hi, s2.lo);
             }
         }
 
@@ -213,13 +224,17 @@ __global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fu
         for (int o = (T > 1 ? T : 1); o < 32; o <<= 1) {
             dd w;
             w.hi = __shfl_xor_sync(0xffffffffu, sA1.hi, o); w.lo = __shfl_xor_sync(0xffffffffu, sA1.lo, o); dd_add_dd(sA1, w);
-            w.hi = __shfl_xor_sync(0xffffffffu, sA2.hi, o); w.lo = __shfl_xor_sync(0xffffffffu, sA2.lo, o); dd_add_dd(sA2, w);
+            if (T < 4) { w.hi = __shfl_xor_sync(0xffffffffu, sA2.hi, o); w.lo = __shfl_xor_sync(0xffffffffu, sA2.lo, o); dd_add_dd(sA2, w); }
             if (T == 1) {
                 w.hi = __shfl_xor_sync(0xffffffffu, sB1.hi, o); w.lo = __shfl_xor_sync(0xffffffffu, sB1.lo, o); dd_add_dd(sB1, w);
                 w.hi = __shfl_xor_sync(0xffffffffu, sB2.hi, o); w.lo = __shfl_xor_sync(0xffffffffu, sB2.lo, o); dd_add_dd(sB2, w);
             }
         }
-        if (T > 1) {  // bring lane 1's (yB) sums next to lane 0's
+        if (T >= 4) {  // lanes 0..3 hold sum yA, sum yA^2, sum yB, sum yB^2: bring them to lane 0
+            sA2.hi = __shfl_sync(0xffffffffu, sA1.hi, 1); sA2.lo = __shfl_sync(0xffffffffu, sA1.lo, 1);
+            sB1.hi = __shfl_sync(0xffffffffu, sA1.hi, 2); sB1.lo = __shfl_sync(0xffffffffu, sA1.lo, 2);
+            sB2.hi = __shfl_sync(0xffffffffu, sA1.hi, 3); sB2.lo = __shfl_sync(0xffffffffu, sA1.lo, 3);
+        } else if (T > 1) {  // bring lane 1's (yB) sums next to lane 0's
             sB1.hi = __shfl_sync(0xffffffffu, sA1.hi, 1); sB1.lo = __shfl_sync(0xffffffffu, sA1.lo, 1);
             sB2.hi = __shfl_sync(0xffffffffu, sA2.hi, 1); sB2.lo = __shfl_sync(0xffffffffu, sA2.lo, 1);
         }
@@ -260,6 +275,7 @@ __global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fu
         }
         __syncthreads();
     }
+    if (a.tail.counter) fused_tail(a.tail);
 }
 
 }  // namespace gsa

@@ -15,6 +15,8 @@
 #include "fused_generic.cuh"
 #include "reduce_tiles.cuh"
 #include "dispatch.cuh"
+#include "peer_state.h"
+#include <emmintrin.h>
 
 namespace gsa {
 
@@ -237,8 +239,68 @@ static int ensure_directions(gsa_handle* h, int dT) {
     return GSA_OK;
 }
 
+// What should happen to the partial sums at the end of the call (beyond landing in `partials`): an all-reduce over the handle's
+// peer group and / or a copy into the handle's result mailbox in pinned host memory.  Where the plan allows, the kernel's last
+// CTA does all of it (tail.cuh: one launch per step); otherwise the classic sequence of launches follows.
+struct TailRequest {
+    bool exchange = false;   // in: all-reduce over the peer group (gsa_peer_connect)
+    bool to_host = false;    // in: final sums -> h->tail_host
+    bool fused = false;      // out: done by the kernel's last CTA, h->tail_flag is raised to h->tail_flag_value at the end
+};
+
+int peer_allreduce_launch(gsa_handle* h, double* data_dev, size_t count, int nstat, double* host_out_mapped_dev);   // peer.cu
+
+static int ensure_tail(gsa_handle* h, size_t count) {
+    if (!h->tail_counter) {
+        GSA_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->tail_counter), sizeof(unsigned long long)));
+        GSA_CUDA(cudaMemset(h->tail_counter, 0, sizeof(unsigned long long)));
+        h->tail_arrived = 0;
+        GSA_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->tail_flag), sizeof(unsigned long long), cudaHostAllocMapped));
+        *h->tail_flag = 0;
+        h->tail_flag_value = 0;
+        GSA_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->tail_flag_dev), h->tail_flag, 0));
+    }
+    if (h->tail_host_cap < count) {
+        GSA_CUDA(cudaStreamSynchronize(h->stream));   // nothing in flight may still write the old mailbox
+        if (h->tail_host) cudaFreeHost(h->tail_host);
+        h->tail_host = nullptr;
+        h->tail_host_cap = 0;
+        const size_t cap = count + count / 4 + 64;
+        GSA_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->tail_host), sizeof(double) * cap, cudaHostAllocMapped));
+        GSA_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->tail_host_dev), h->tail_host, 0));
+        h->tail_host_cap = cap;
+    }
+    return GSA_OK;
+}
+
+// Block until the result mailbox of the last call holds the final sums.  Fused tail: spin on the flag the kernel's last CTA
+// raises (the host sees the result ~2 us after it is written, without waiting for the stream to drain); otherwise synchronise.
+static int wait_tail(gsa_handle* h, const TailRequest& tr) {
+    if (tr.fused) {
+        volatile unsigned long long* f = h->tail_flag;
+        const unsigned long long want = h->tail_flag_value;
+        for (unsigned spins = 0; *f < want; ++spins) {
+            if ((spins & 0x3fff) == 0x3fff) {   // a failed launch / timed-out exchange never raises the flag: look at the stream now and then
+                const cudaError_t q = cudaStreamQuery(h->stream);
+                if (q != cudaErrorNotReady) {
+                    if (q != cudaSuccess) return cuda_fail(q, "fused kernel");
+                    break;
+                }
+            }
+            _mm_pause();
+        }
+        if (*f < want) GSA_CUDA(cudaStreamSynchronize(h->stream));
+    } else {
+        GSA_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    if (tr.exchange && h->peer && h->peer->status_host && *h->peer->status_host)
+        return fail(GSA_ERR_CUDA, "peer all-reduce timed out waiting for a rank");
+    return GSA_OK;
+}
+
 static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, const double* params, int np, const double* A,
-                         const double* B, int d, int64_t N, int64_t col0, int64_t ncols, double* partials, const GenSpec* gen = nullptr) {
+                         const double* B, int d, int64_t N, int64_t col0, int64_t ncols, double* partials, const GenSpec* gen = nullptr,
+                         TailRequest* tr = nullptr) {
     int rc = check_opts(o);
     if (rc) return rc;
     if (d < 1) return fail(GSA_ERR_INVALID, "d must be >= 1");
@@ -285,7 +347,10 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
     h->last_launches = 0;
     h->kernel_timed = false;
     GSA_CUDA(cudaEventRecord(h->ev0, h->stream));
-    GSA_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (size_t)o->nboot * recsz, h->stream));
+    const size_t count = (size_t)o->nboot * recsz;
+    const bool want_tail = tr && (tr->exchange || tr->to_host);
+    if (want_tail && (rc = ensure_tail(h, count))) return rc;
+    bool zeroed = false;
     const int64_t valid_hi = std::min<int64_t>(col0 + ncols, (int64_t)o->nboot * n);
     if (n > 0 && valid_hi > col0) {
         if ((rc = upload_params(h, params, np))) return rc;
@@ -356,6 +421,31 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         // tiles that intersect the shard form one contiguous index range [t_lo, t_hi); the others are all-zero records
         const int t_lo = (int)((col0 - (int64_t)g.rep_first * n) / g.ts);
         const int t_hi = (rep_last - g.rep_first) * g.tpr + (int)((valid_hi - 1 - (int64_t)rep_last * n) / g.ts) + 1;
+        // one launch per step: stage 2, the exchange and the host copy run in the kernel's last CTA (tail.cuh)
+        const bool fuse = want_tail && plan.supports_tail() && !host_in && t_hi > t_lo && !getenv("GSA_NO_TAIL");
+        if (fuse) {
+            TailArgs& t = plan.tail;
+            t.counter = h->tail_counter;
+            t.tile_rec = direct ? nullptr : h->tile_rec.as<double>();
+            t.partials = partials;
+            t.reduce = direct ? 0 : 1;
+            t.recsz = recsz; t.nstat = nstat; t.tpr = g.tpr; t.rep_first = g.rep_first; t.nrep = nrep; t.nboot = o->nboot;
+            t.exchange = 0;
+            t.host_out = nullptr;
+            if (tr->exchange) {
+                if ((rc = peer_next_exchange(h, partials, count, nstat, h->tail_host_dev, &t.peer))) return rc;
+                t.exchange = 1;
+            } else {
+                t.host_out = h->tail_host_dev;
+            }
+            t.host_flag = h->tail_flag_dev;
+            t.flag_value = ++h->tail_flag_value;
+            tr->fused = true;
+        }
+        if (!fuse || direct) {   // (the fused stage 2 writes every element of `partials` itself)
+            GSA_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * count, h->stream));
+            zeroed = true;
+        }
         if (!direct && t_lo > 0) GSA_CUDA(cudaMemsetAsync(h->tile_rec.p, 0, sizeof(double) * (size_t)t_lo * recsz, h->stream));
         if (!direct && t_hi < g.ntiles)
             GSA_CUDA(cudaMemsetAsync(h->tile_rec.as<double>() + (size_t)t_hi * recsz, 0, sizeof(double) * (size_t)(g.ntiles - t_hi) * recsz, h->stream));
@@ -421,7 +511,17 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
                 GSA_CUDA(cudaEventRecord(h->ev_done[b], h->stream));
             }
         }
-        if (!direct && (rc = run_reduce(h, recsz, nstat, g.tpr, g.rep_first, nrep, partials))) return rc;
+        if (!direct && !(tr && tr->fused) && (rc = run_reduce(h, recsz, nstat, g.tpr, g.rep_first, nrep, partials))) return rc;
+    }
+    if (!(tr && tr->fused)) {
+        if (!zeroed && !(n > 0 && valid_hi > col0)) GSA_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * count, h->stream));   // empty shard
+        if (want_tail) {
+            if (tr->exchange) {
+                if ((rc = peer_allreduce_launch(h, partials, count, nstat, h->tail_host_dev))) return rc;
+            } else {
+                GSA_CUDA(cudaMemcpyAsync(h->tail_host, partials, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+            }
+        }
     }
     GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
     return GSA_OK;
@@ -616,6 +716,9 @@ int gsa_destroy(gsa_handle* h) {
         if (h->stream) cudaStreamSynchronize(h->stream);
         if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
         peer_release_handle(h);
+        if (h->tail_counter) cudaFree(h->tail_counter);
+        if (h->tail_host) cudaFreeHost(h->tail_host);
+        if (h->tail_flag) cudaFreeHost(h->tail_flag);
         DevBuf* bufs[] = {&h->tile_rec, &h->partials, &h->params, &h->vtab, &h->lbub, &h->stage[0], &h->stage[1], &h->dev_in[0], &h->dev_in[1], &h->ybuf, &h->aux, &h->gram};
         for (DevBuf* b : bufs) b->release();
         for (auto& um : h->user_models)
@@ -802,8 +905,11 @@ int gsa_sobol_run_generated(gsa_handle* h, const gsa_sobol_opts* opts, int model
     if ((rc = h->partials.reserve(sizeof(double) * (size_t)opts->nboot * nout * nstat))) return rc;
     GenSpec gs{lb, ub, samples};
     const int64_t N = (int64_t)opts->nboot * samples;
-    if ((rc = partials_impl(h, opts, model_id, params, nparams, nullptr, nullptr, d, N, 0, N, h->partials.as<double>(), &gs))) return rc;
-    return fetch_and_finalize(h, opts, nout, d, samples, out);
+    TailRequest tr;
+    tr.to_host = true;
+    if ((rc = partials_impl(h, opts, model_id, params, nparams, nullptr, nullptr, d, N, 0, N, h->partials.as<double>(), &gs, &tr))) return rc;
+    if ((rc = wait_tail(h, tr))) return rc;
+    return finalize_host(*opts, h->tail_host, nout, d, samples, out);
 }
 
 int gsa_sobol_partials_y(gsa_handle* h, const gsa_sobol_opts* opts, const double* Y, int nout, int d, int64_t n, double* partials_dev) {
@@ -860,8 +966,46 @@ int gsa_sobol_run(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const
     if ((rc = model_nout(h, model_id, nparams, d, &nout))) return rc;
     const int nstat = stat_count(d, opts->ei_estimator, opts->second_order != 0);
     if ((rc = h->partials.reserve(sizeof(double) * (size_t)opts->nboot * nout * nstat))) return rc;
-    if ((rc = partials_impl(h, opts, model_id, params, nparams, A, B, d, N, 0, N, h->partials.as<double>()))) return rc;
-    return fetch_and_finalize(h, opts, nout, d, N / opts->nboot, out);
+    TailRequest tr;
+    tr.to_host = true;
+    if ((rc = partials_impl(h, opts, model_id, params, nparams, A, B, d, N, 0, N, h->partials.as<double>(), nullptr, &tr))) return rc;
+    if ((rc = wait_tail(h, tr))) return rc;
+    return finalize_host(*opts, h->tail_host, nout, d, N / opts->nboot, out);
+}
+
+// One call per step of the sharded form (one process per GPU): partial sums of this rank's column shard, all-reduce over the
+// peer group of the handle, epilogue.  One kernel launch where the plan has a fused tail (tail.cuh).
+static int run_sharded(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams, const double* A,
+                       const double* B, const GenSpec* gen, int d, int64_t N, int64_t col0, int64_t ncols, gsa_sobol_result* out) {
+    int rc = check_opts(opts);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    int nout = 0;
+    if (d < 1) return fail(GSA_ERR_INVALID, "d must be >= 1");
+    if ((rc = model_nout(h, model_id, nparams, d, &nout))) return rc;
+    const int nstat = stat_count(d, opts->ei_estimator, opts->second_order != 0);
+    if ((rc = h->partials.reserve(sizeof(double) * (size_t)opts->nboot * nout * nstat))) return rc;
+    TailRequest tr;
+    tr.exchange = peer_connected(h);   // a group of one (or no group): the shard is the whole design
+    tr.to_host = true;
+    if ((rc = partials_impl(h, opts, model_id, params, nparams, A, B, d, N, col0, ncols, h->partials.as<double>(), gen, &tr))) return rc;
+    if ((rc = wait_tail(h, tr))) return rc;
+    return finalize_host(*opts, h->tail_host, nout, d, N / opts->nboot, out);
+}
+
+int gsa_sobol_run_sharded(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams, const double* A,
+                          const double* B, int d, int64_t N, int64_t col0, int64_t ncols, gsa_sobol_result* out) {
+    if (!h || !out) return fail(GSA_ERR_INVALID, "handle or result is NULL");
+    return run_sharded(h, opts, model_id, params, nparams, A, B, nullptr, d, N, col0, ncols, out);
+}
+
+int gsa_sobol_run_sharded_generated(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams,
+                                    const double* lb, const double* ub, int d, int64_t samples, int64_t col0, int64_t ncols,
+                                    gsa_sobol_result* out) {
+    if (!h || !out || !lb || !ub || !opts) return fail(GSA_ERR_INVALID, "handle, result, lb, ub or opts is NULL");
+    GenSpec gs{lb, ub, samples};
+    return run_sharded(h, opts, model_id, params, nparams, nullptr, nullptr, &gs, d, (int64_t)opts->nboot * samples, col0, ncols, out);
 }
 
 int gsa_sobol_analyze_y(gsa_handle* h, const gsa_sobol_opts* opts, const double* Y, int nout, int d, int64_t n, gsa_sobol_result* out) {

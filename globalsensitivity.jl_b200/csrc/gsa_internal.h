@@ -83,4 +83,14 @@ struct gsa_handle {
     bool kernel_timed = false;   // evk0/evk1 bracket the dominant kernel of the last call
     int last_launches = 0;
     gsa::PeerState* peer = nullptr;
+    // fused tail (tail.cuh): device counter of arrived CTAs (monotonic over launches; tail_arrived = its value once everything
+    // issued so far has run), and the result mailbox in mapped pinned host memory: sums + a flag the last CTA raises
+    unsigned long long* tail_counter = nullptr;
+    unsigned long long tail_arrived = 0;
+    double* tail_host = nullptr;            // [tail_host_cap] sums, host view
+    double* tail_host_dev = nullptr;        // device view of the same memory
+    size_t tail_host_cap = 0;
+    unsigned long long* tail_flag = nullptr;      // host view
+    unsigned long long* tail_flag_dev = nullptr;
+    unsigned long long tail_flag_value = 0;       // value the last fused launch raises
 };

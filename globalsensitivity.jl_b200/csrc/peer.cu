@@ -21,59 +21,13 @@
 
 #include "gsa_common.cuh"
 #include "gsa_internal.h"
+#include "peer.cuh"
+#include "peer_state.h"
 
 namespace gsa {
 
-struct PeerState {
-    int rank = -1, world = 0;
-    size_t max_doubles = 0;
-    void* mailbox = nullptr;                 // this rank's: [2][world_max][max_doubles] doubles, then flags [2][world_max] u64
-    std::vector<void*> peer;                 // mapped mailboxes, peer[rank] = own
-    void** peer_dev = nullptr;               // device copy of `peer`
-    unsigned long long epoch = 0, ctas_launched = 0;
-    unsigned long long* counter_dev = nullptr;
-    int* status_host = nullptr;              // pinned + mapped: 0 ok, 1 timeout
-    int* status_dev = nullptr;
-};
-
-constexpr int PEER_WORLD_MAX = 16;
 constexpr int PEER_THREADS = 256;
 constexpr int PEER_CTAS_MAX = 64;
-
-__host__ __device__ inline size_t peer_flags_offset(size_t max_doubles) { return sizeof(double) * 2 * PEER_WORLD_MAX * max_doubles; }
-inline size_t peer_mailbox_bytes(size_t max_doubles) { return peer_flags_offset(max_doubles) + sizeof(unsigned long long) * 2 * PEER_WORLD_MAX; }
-
-struct PeerArgs {
-    void* const* peer;          // [world] mailboxes
-    double* data;               // in: this rank's vector, out: the sum
-    double* host_out;           // optional mapped host copy of the sum
-    int* status;
-    unsigned long long* counter;   // CTAs of this rank that have finished pushing (monotonic over calls)
-    unsigned long long counter_base;
-    size_t count, max_doubles;
-    unsigned long long epoch;
-    long long timeout_ns;
-    int rank, world, nstat;
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ long long global_ns() {
-    long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 // grid = min(records, PEER_CTAS_MAX) CTAs (always co-resident); every CTA owns a contiguous range of whole records
 __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(PeerArgs a) {
@@ -98,44 +52,8 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(PeerArgs a
         unsigned long long* f = reinterpret_cast<unsigned long long*>(static_cast<char*>(a.peer[tid]) + peer_flags_offset(a.max_doubles));
         st_release_sys(f + par * PEER_WORLD_MAX + a.rank, a.epoch);
     }
-    // 3. wait for everybody's vector of this epoch
-    if (tid < a.world) {
-        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(static_cast<const char*>(a.peer[a.rank]) + peer_flags_offset(a.max_doubles));
-        const long long t0 = global_ns();
-        while (ld_acquire_sys(f + par * PEER_WORLD_MAX + tid) != a.epoch) {
-            if (global_ns() - t0 > a.timeout_ns) {
-                timed_out = 1;
-                break;
-            }
-            __nanosleep(100);
-        }
-    }
-    __syncthreads();
-    if (timed_out) {
-        if (tid == 0) *a.status = 1;
-        return;
-    }
-    // 4. add in rank order
-    const double* own = static_cast<const double*>(a.peer[a.rank]) + (size_t)par * PEER_WORLD_MAX * a.max_doubles;
-    for (size_t i = lo + tid; i < hi; i += PEER_THREADS) {
-        const int e = (int)(i % a.nstat);
-        if (e < STAT_DD) {
-            if (e & 1) continue;   // the lo word is handled with its hi word
-            dd s{0.0, 0.0};
-            for (int q = 0; q < a.world; ++q) {
-                const double* v = own + (size_t)q * a.max_doubles + i;
-                dd_add_dd(s, dd{ld_relaxed_sys(v), ld_relaxed_sys(v + 1)});
-            }
-            a.data[i] = s.hi;
-            a.data[i + 1] = s.lo;
-            if (a.host_out) { a.host_out[i] = s.hi; a.host_out[i + 1] = s.lo; }
-        } else {
-            double s = 0.0;
-            for (int q = 0; q < a.world; ++q) s += ld_relaxed_sys(own + (size_t)q * a.max_doubles + i);
-            a.data[i] = s;
-            if (a.host_out) a.host_out[i] = s;
-        }
-    }
+    // 3. wait for everybody's vector of this epoch, 4. add in rank order
+    peer_wait_and_add(a, lo, hi, &timed_out);
 }
 
 // unmap the peers' mailboxes (this rank's own mailbox stays allocated: peers may still have it mapped)
@@ -159,6 +77,51 @@ static void peer_release(gsa_handle* h) {
 }
 
 void peer_release_handle(gsa_handle* h) { peer_release(h); }
+
+int peer_next_exchange(gsa_handle* h, double* data_dev, size_t count, int nstat, double* host_out_mapped_dev, PeerArgs* out);
+
+// the stand-alone exchange: one launch on the handle's stream (the caller holds the handle's lock and has set the device)
+int peer_allreduce_launch(gsa_handle* h, double* data_dev, size_t count, int nstat, double* host_out_mapped_dev) {
+    PeerArgs a;
+    int rc = peer_next_exchange(h, data_dev, count, nstat, host_out_mapped_dev, &a);
+    if (rc) return rc;
+    PeerState* ps = h->peer;
+    const int grid = (int)std::min<size_t>(count / (size_t)nstat, (size_t)PEER_CTAS_MAX);
+    a.counter = ps->counter_dev;
+    a.counter_base = ps->ctas_launched;
+    ps->ctas_launched += (unsigned long long)grid;
+    peer_allreduce_kernel<<<grid, PEER_THREADS, 0, h->stream>>>(a);
+    h->last_launches++;
+    GSA_CUDA(cudaGetLastError());
+    return GSA_OK;
+}
+
+bool peer_connected(const gsa_handle* h) { return h->peer && h->peer->peer_dev && h->peer->world > 1; }
+
+int peer_next_exchange(gsa_handle* h, double* data_dev, size_t count, int nstat, double* host_out_mapped_dev, PeerArgs* out) {
+    PeerState* ps = h->peer;
+    if (!ps || !ps->peer_dev) return fail(GSA_ERR_INVALID, "peer exchange: peers are not connected (gsa_peer_export / gsa_peer_connect)");
+    if (count > ps->max_doubles) return fail(GSA_ERR_INVALID, "peer exchange: %zu doubles exceed the mailbox (%zu)", count, ps->max_doubles);
+    if (nstat < STAT_DD || count == 0 || count % (size_t)nstat) return fail(GSA_ERR_INVALID, "peer exchange: count %zu is not a multiple of nstat %d", count, nstat);
+    if (*ps->status_host) return fail(GSA_ERR_CUDA, "peer exchange: an earlier exchange timed out waiting for a peer");
+    PeerArgs a;
+    a.peer = ps->peer_dev;
+    a.data = data_dev;
+    a.host_out = host_out_mapped_dev;
+    a.status = ps->status_dev;
+    a.counter = ps->counter_dev;
+    a.counter_base = 0;
+    a.count = count;
+    a.max_doubles = ps->max_doubles;
+    a.epoch = ++ps->epoch;
+    const char* t = getenv("GSA_PEER_TIMEOUT_MS");
+    a.timeout_ns = (long long)(t && atoi(t) > 0 ? atoi(t) : 10000) * 1000000LL;
+    a.rank = ps->rank;
+    a.world = ps->world;
+    a.nstat = nstat;
+    *out = a;
+    return GSA_OK;
+}
 
 }  // namespace gsa
 
@@ -232,39 +195,15 @@ int gsa_peer_connect(gsa_handle* h, int rank, int world, const void* handles) {
 
 int gsa_peer_allreduce(gsa_handle* h, double* data_dev, size_t count, int nstat, double* host_out) {
     if (!h || !data_dev) return fail(GSA_ERR_INVALID, "bad arguments to gsa_peer_allreduce");
-    PeerState* ps = h->peer;
-    if (!ps || !ps->peer_dev) return fail(GSA_ERR_INVALID, "gsa_peer_allreduce: peers are not connected");
-    if (count > ps->max_doubles) return fail(GSA_ERR_INVALID, "gsa_peer_allreduce: %zu doubles exceed the mailbox (%zu)", count, ps->max_doubles);
-    if (nstat < STAT_DD || count == 0 || count % (size_t)nstat) return fail(GSA_ERR_INVALID, "gsa_peer_allreduce: count %zu is not a multiple of nstat %d", count, nstat);
     std::lock_guard<std::mutex> lk(h->mu);
     DevGuard guard(h->device);
-    if (*ps->status_host) return fail(GSA_ERR_CUDA, "gsa_peer_allreduce: an earlier exchange timed out waiting for a peer");
-    PeerArgs a;
-    a.peer = ps->peer_dev;
-    a.data = data_dev;
-    a.host_out = nullptr;
+    double* host_dev = nullptr;
     if (host_out) {
         void* dp = nullptr;
         GSA_CUDA(cudaHostGetDevicePointer(&dp, host_out, 0));   // fails for pageable memory: the caller must pass pinned memory
-        a.host_out = static_cast<double*>(dp);
+        host_dev = static_cast<double*>(dp);
     }
-    a.status = ps->status_dev;
-    a.count = count;
-    a.max_doubles = ps->max_doubles;
-    a.epoch = ++ps->epoch;
-    const char* t = getenv("GSA_PEER_TIMEOUT_MS");
-    a.timeout_ns = (long long)(t && atoi(t) > 0 ? atoi(t) : 10000) * 1000000LL;
-    a.rank = ps->rank;
-    a.world = ps->world;
-    a.nstat = nstat;
-    const int grid = (int)std::min<size_t>(count / (size_t)nstat, (size_t)PEER_CTAS_MAX);
-    a.counter = ps->counter_dev;
-    a.counter_base = ps->ctas_launched;
-    ps->ctas_launched += (unsigned long long)grid;
-    peer_allreduce_kernel<<<grid, PEER_THREADS, 0, h->stream>>>(a);
-    h->last_launches++;
-    GSA_CUDA(cudaGetLastError());
-    return GSA_OK;
+    return peer_allreduce_launch(h, data_dev, count, nstat, host_dev);
 }
 
 int gsa_peer_status(gsa_handle* h, int* status) {

@@ -637,20 +637,67 @@ def reduce_and_finalize(method: Sobol, partials, d: int, N: int, *, Ei_estimator
     return sobol_finalize(method, partials, d, N, Ei_estimator=Ei_estimator)
 
 
+class ShardedStep:
+    """A prepared `gsa_sobol_run_sharded` call (one process per GPU): everything that does not change from step to step --
+    options, pointers, result buffers -- is built once, `run()` is ONE ctypes call that launches the fused kernel on this rank's
+    shard, all-reduces the partial sums over the handle's peer group (for product-form models inside the same kernel: its last
+    CTA pushes them over NVLink) and runs the epilogue.  Without a connected peer group the shard is the whole design.
+
+        pg = PeerGroup(handle, nboot * nout * nstat)              # once, collective
+        step = ShardedStep(model, method, A_local, B_local, N, col0, handle=handle)
+        res = step.run()                                          # collective: every rank, same arguments
+
+    `p_range=(lb, ub)` instead of A_local/B_local: the shard's points are generated inside the kernel (columns
+    [col0, col0 + ncols) of the nboot*samples-column design of gsa(f, ::Sobol, p_range; samples), N = nboot*samples)."""
+
+    def __init__(self, f: DeviceModel, method: Sobol, A_local, B_local, N: int, col0: int, *, Ei_estimator="Jansen1999",
+                 handle: Optional[GsaHandle] = None, p_range=None, ncols: Optional[int] = None, torch_stream: bool = True):
+        self.h = handle or getattr(f, "handle", None) or default_handle()
+        self.f, self.method = f, method
+        if p_range is None:
+            self.Am, self.Bm = _Mat(A_local), _Mat(B_local)
+            if (self.Am.d, self.Am.N) != (self.Bm.d, self.Bm.N) or self.Am.loc != self.Bm.loc:
+                raise ValueError("A_local and B_local must have the same shape and location")
+            d, ncols, loc = self.Am.d, self.Am.N, self.Am.loc
+        else:
+            self.lb = np.ascontiguousarray(p_range[0], dtype=np.float64)
+            self.ub = np.ascontiguousarray(p_range[1], dtype=np.float64)
+            d, loc = self.lb.size, LOC_HOST
+            if ncols is None:
+                raise ValueError("ncols is required with p_range")
+        nout = f.nout(d)
+        self.o = _opts(method, Ei_estimator, loc)
+        self.rc, self.finish, self._keep = _alloc_result(nout, d, method.nboot, 2 in method.order, nout > 1)
+        L = lib()
+        if p_range is None:
+            self._call = lambda: L.gsa_sobol_run_sharded(self.h.ptr, C.byref(self.o), f.model_id, f.params.ctypes.data, f.params.size,
+                                                         self.Am.ptr, self.Bm.ptr, d, N, col0, ncols, C.byref(self.rc))
+        else:
+            samples = N // method.nboot
+            self._call = lambda: L.gsa_sobol_run_sharded_generated(self.h.ptr, C.byref(self.o), f.model_id, f.params.ctypes.data,
+                                                                   f.params.size, self.lb.ctypes.data, self.ub.ctypes.data, d,
+                                                                   samples, col0, ncols, C.byref(self.rc))
+        if torch_stream and (loc == LOC_DEVICE or p_range is not None):
+            import torch
+            self.h.set_stream(torch.cuda.current_stream().cuda_stream)     # ordered after whatever produced the tensors
+
+    def run(self) -> SobolResult:
+        check(self._call())
+        return self.finish()
+
+
 def gsa_sharded(f: DeviceModel, method: Sobol, A_local, B_local, N: int, col0: int, *, Ei_estimator="Jansen1999",
                 group=None, handle: Optional[GsaHandle] = None, peers: Optional["PeerGroup"] = None) -> SobolResult:
     """gsa(f, Sobol(...), A, B; batch=true) with the d x N design sharded by contiguous column ranges over the ranks of a
     torch.distributed group (one process per GPU): local fused kernel -> one all-reduce -> epilogue.
-    `peers` (a PeerGroup built once on the same handle) runs the all-reduce as one kernel per rank over NVLink peer memory
-    (csrc/peer.cu) instead of torch.distributed's collective."""
+    `peers` (a PeerGroup built once on the same handle) runs the whole step as one `gsa_sobol_run_sharded` call: the all-reduce
+    goes over NVLink peer memory (csrc/peer.cu, fused into the kernel's tail where possible) instead of torch.distributed."""
     h = handle or (peers.h if peers is not None else None)
-    p = sobol_partials(f, method, A_local, B_local, N, col0, Ei_estimator=Ei_estimator, handle=h)
     if peers is None:
+        p = sobol_partials(f, method, A_local, B_local, N, col0, Ei_estimator=Ei_estimator, handle=h)
         return reduce_and_finalize(method, p, _Mat(A_local).d, N, Ei_estimator=Ei_estimator, group=group)
-    import torch
-    host = torch.empty(p.shape, dtype=torch.float64).pin_memory()
-    peers.allreduce(p, p.shape[-1], host_out=host)
-    torch.cuda.current_stream().synchronize()
-    if peers.status() != 0:
-        raise GsaError(2, "peer all-reduce timed out waiting for a rank")
-    return sobol_finalize(method, host.numpy(), _Mat(A_local).d, N, Ei_estimator=Ei_estimator)
+    step = ShardedStep(f, method, A_local, B_local, N, col0, Ei_estimator=Ei_estimator, handle=h)
+    try:
+        return step.run()
+    finally:
+        h.set_stream(None)

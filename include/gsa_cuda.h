@@ -136,6 +136,17 @@ GSA_API int gsa_sobol_partials(gsa_handle* h, const gsa_sobol_opts* opts, int mo
                        int nparams, const double* A, const double* B, int d, int64_t N, int64_t col0,
                        int64_t ncols, double* partials_dev);
 
+/* The sharded form in ONE call per rank: partial sums of the rank's shard, all-reduce over the peer group the handle is connected
+ * to (gsa_peer_export / gsa_peer_connect below; no group or a group of one: the shard is the whole design) and the epilogue, so
+ * every rank returns the same SobolResult.  Collective: every rank of the group calls it with the same options.  Where the
+ * kernel has a fused tail (product-form models) the whole step is ONE kernel launch: its last CTA sums the tile records, pushes
+ * them to the peers over NVLink, adds the peers' in rank order and writes the result to pinned host memory. */
+GSA_API int gsa_sobol_run_sharded(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams,
+                          const double* A, const double* B, int d, int64_t N, int64_t col0, int64_t ncols, gsa_sobol_result* out);
+GSA_API int gsa_sobol_run_sharded_generated(gsa_handle* h, const gsa_sobol_opts* opts, int model_id, const double* params, int nparams,
+                                    const double* lb, const double* ub, int d, int64_t samples, int64_t col0, int64_t ncols,
+                                    gsa_sobol_result* out);
+
 /* gsa(model, Sobol(...), p_range; samples) (:407-417) WITHOUT materialising A and B: the fused kernel generates the Sobol points
  * of the samples it evaluates (K1 fused into K2+K3), so the path has no HBM reads and no design memory at all.  The design is
  * the reference's: one 2*nboot*d-dimensional sequence, replicate r = dimensions [r*d, (r+1)*d) (A) and [(nboot+r)*d, ...) (B)

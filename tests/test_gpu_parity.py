@@ -714,6 +714,48 @@ def test_peer_allreduce_two_ranks():
     assert '"e2e_max_abs_diff_vs_single_gpu"' in r.stdout
 
 
+def test_one_call_step_with_fused_tail(monkeypatch):
+    """gsa_sobol_run_sharded without a peer group (the shard is the whole design or a slice of it): for product-form models the
+    kernel's last CTA does stage 2 and the host copy (tail.cuh) -- same numbers as the classic launch sequence, one launch."""
+    import torch
+    d, N = 100, 100003
+    a = np.array([0.0, 1.0, 4.5, 9.0] + [99.0] * 96)
+    model = g.DeviceModel("sobol_g", a)
+    A, B = g.generate_design_matrices(N, np.zeros(d), np.ones(d), 2, device=True)
+    An, Bn = A.cpu().numpy(), B.cpu().numpy()
+    h = g.default_handle()
+    for nboot, est in ((1, "Jansen1999"), (3, "Jansen1999"), (7, "Sobol2007"), (1000, "Homma1996")):
+        method = g.Sobol(nboot=nboot)
+        ref = gsa_ref.gsa_sobol("sobol_g", a, An, Bn, nboot=nboot, Ei_estimator=est)
+        step = g.ShardedStep(model, method, A, B, N, 0, Ei_estimator=est)
+        fused = step.run()
+        fused2 = step.run()                                 # the counters and the flag are monotonic over launches
+        launches = h.last_timing()[2]
+        assert launches == 1, launches
+        h.set_stream(None)
+        monkeypatch.setenv("GSA_NO_TAIL", "1")
+        classic = g.gsa(model, method, A, B, batch=True, Ei_estimator=est)
+        assert h.last_timing()[2] >= 1
+        monkeypatch.delenv("GSA_NO_TAIL")
+        assert_parity(fused, ref, what=("fused", nboot, est))
+        assert_parity(classic, ref, what=("classic", nboot, est))
+        for f in ("S1", "ST"):
+            assert np.array_equal(getattr(fused, f), getattr(fused2, f))
+    # the generated design, and a shard that is a slice (untouched replicates are written as zeros by the tail)
+    method = g.Sobol(nboot=3)
+    gen = g.ShardedStep(model, method, None, None, 3 * 20011, 0, p_range=(np.zeros(d), np.ones(d)), ncols=3 * 20011).run()
+    g.default_handle().set_stream(None)
+    assert_parity(gen, g.gsa(model, method, [[0.0, 1.0]] * d, samples=20011, batch=True))
+    n = N // 3
+    sl = g.ShardedStep(model, method, A[:, n + 5:2 * n - 7], B[:, n + 5:2 * n - 7], N, n + 5).run()      # inside replicate 1 only
+    g.default_handle().set_stream(None)
+    p = g.sobol_partials(model, method, A[:, n + 5:2 * n - 7], B[:, n + 5:2 * n - 7], N, n + 5)
+    torch.cuda.synchronize()
+    want = g.sobol_finalize(method, p, d, N)
+    for f in ("S1", "ST"):                                   # replicates 0 and 2 are empty: NaN in both
+        assert np.array_equal(np.isnan(getattr(sl, f)), np.isnan(getattr(want, f)))
+
+
 def test_streamed_host_inputs_large():
     """Host designs larger than one streaming chunk (pinned: 256 MB per matrix; pageable: 64 MB): many chunk kernels."""
     import torch

@@ -75,6 +75,62 @@ whole = g.gsa(model, method, Aw, Bw, batch=True, handle=h)
 err = max(float(np.abs(res.S1 - whole.S1).max()), float(np.abs(res.ST - whole.ST).max()), float(np.abs(res.ST_Conf_Int - whole.ST_Conf_Int).max()))
 assert err <= 1e-12, err
 out["e2e_max_abs_diff_vs_single_gpu"] = err
+# the whole step as ONE call / ONE kernel (gsa_sobol_run_sharded: the fused kernel's last CTA reduces the tiles, exchanges the
+# sums over NVLink and writes them to pinned host memory), with a resident and with a generated design; second order (no fused
+# tail: the classic launches follow) as well
+step = g.ShardedStep(model, method, A, B, N, c0, handle=h)
+for _ in range(3):
+    r1 = step.run()
+launches = h.last_timing()[2]
+err = max(float(np.abs(r1.S1 - whole.S1).max()), float(np.abs(r1.ST - whole.ST).max()), float(np.abs(r1.ST_Conf_Int - whole.ST_Conf_Int).max()))
+assert err <= 1e-12, ("fused sharded step", err)
+out["sharded_step_max_abs_diff_vs_single_gpu"] = err
+out["sharded_step_launches"] = launches
+allr = [None] * world
+dist.all_gather_object(allr, (r1.S1.tobytes(), r1.ST.tobytes(), r1.ST_Conf_Int.tobytes()))
+assert all(x == allr[0] for x in allr), "ranks disagree on the fused sharded step"
+# (generated: N = nboot * samples columns, replicate r uses its own dimension block -- compare with the single-GPU generated run)
+gw = g.gsa(model, method, [[0.0, 1.0]] * d, samples=N // 3, batch=True, handle=h)
+sg = g.ShardedStep(model, method, None, None, (N // 3) * 3, *g.shard_columns((N // 3) * 3, rank, world)[:1], handle=h,
+                   p_range=(np.zeros(d), np.ones(d)), ncols=g.shard_columns((N // 3) * 3, rank, world)[1])
+r2 = sg.run()
+err = max(float(np.abs(r2.S1 - gw.S1).max()), float(np.abs(r2.ST - gw.ST).max()))
+assert err <= 1e-12, ("generated sharded step", err)
+out["sharded_generated_step_max_abs_diff_vs_single_gpu"] = err
+a8 = [0.0, 1.0, 4.5, 9.0, 99.0, 99.0, 99.0, 99.0]
+m8, me8 = g.DeviceModel("sobol_g", a8), g.Sobol(order=[0, 1, 2], nboot=2)
+pg.close()
+pg = g.PeerGroup(h, 2 * g.nstat(me8, 8))
+N8 = 1 << 16
+c8, n8 = g.shard_columns(N8, rank, world)
+A8, B8 = g.generate_design_matrices(N8, np.zeros(8), np.ones(8), 2, device=True, handle=h)
+w8 = g.gsa(m8, me8, A8, B8, batch=True, handle=h)
+r8 = g.ShardedStep(m8, me8, A8[:, c8:c8 + n8], B8[:, c8:c8 + n8], N8, c8, handle=h).run()
+err = max(float(np.abs(r8.S1 - w8.S1).max()), float(np.abs(r8.S2 - w8.S2).max()), float(np.abs(r8.S2_Conf_Int - w8.S2_Conf_Int).max()))
+assert err <= 1e-12, ("unfused sharded step", err)
+out["sharded_step_second_order_max_abs_diff"] = err
+# timing of the one-call step against partials + allreduce + finalize (small shard: the overhead is what shows)
+step = g.ShardedStep(model, method, A, B, N, c0, handle=h)
+pg.close()
+pg = g.PeerGroup(h, 3 * ns)
+for _ in range(10):
+    step.run()
+dist.barrier(); torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(100):
+    step.run()
+t_step = (time.perf_counter() - t0) / 100
+kms = h.last_timing()[1]
+dist.barrier(); torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(100):
+    p = g.sobol_partials(model, method, A, B, N, c0, handle=h, out=p)
+    pg.allreduce(p, ns, host_out=host)
+    torch.cuda.current_stream().synchronize()
+    g.sobol_finalize(method, host.numpy(), d, N)
+t_old = (time.perf_counter() - t0) / 100
+out["step_us"] = {"one_call_fused": round(1e6 * t_step, 1), "three_calls": round(1e6 * t_old, 1), "kernel_us": round(1e3 * kms, 1)}
+h.set_stream(None)
 pg.close()
 if rank == 0:
     print(json.dumps(out), flush=True)
