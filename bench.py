@@ -5,9 +5,10 @@
     on  gsa(sobol_g, Sobol(order=[0,1]), A, B; batch=true)  with d = 100, N = 2^26  (config 5),
     strong-scaled over 1/2/4/8 B200 (contiguous column shards, ONE all-reduce of the partial sums).
 
-A "step" is one full pass of the path over the design: fused design-swap + model + estimator kernel on this
-rank's shard, tile reduction, (N>1) all-reduce of nboot*nout*nstat doubles (one kernel per rank over NVLink peer memory that also writes the sums to pinned host memory; NCCL + a D2H copy as fallback)
-and the host epilogue that yields S1/ST.
+A "step" is one full pass of the path over the design through ONE public call per rank (gsa_sobol_run_sharded): fused
+design-swap + model + estimator kernel on this rank's shard whose last CTA also sums the tile records, (N>1) all-reduces the
+nboot*nout*nstat partial sums over NVLink peer memory and writes them to pinned host memory (one kernel launch per step), and
+the host epilogue that yields S1/ST.
 
   value      inputs (A, B shards) resident in HBM before the timed region; CUDA events, max over ranks
   e2e        the same metric through the public API with HOST (pinned) A and B: the chunked H2D copy of the
@@ -15,6 +16,9 @@ and the host epilogue that yields S1/ST.
   roofline   the fused kernel alone: 16*d bytes per sample / its CUDA-event time, against MEASURED_PEAKS.json
   cpu_baseline   the CPU restatement of the reference (oracle/gsa_ref.c, OpenMP, all host cores) on a bounded
              sample of the same workload (Julia is not in the image, so the reference itself cannot run)
+
+  configs    (N = 1) BASELINE configs 1-4, K1 in steady state and the estimator-only kernel, each with its own kernel time,
+             algorithmic bytes and fraction of the measured HBM peak -- measured inside this run, with its clocks
 
 `--impl reference` times only that CPU restatement and prints a line of the same shape.
 """
@@ -76,7 +80,9 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = workload(args.log2n)
+    w = workload(args.cpu_log2n)          # the config this arm really runs: a bounded sample of the headline workload
+    w["sampled_from"] = f"N=2^{args.log2n} (the reference's all_points for the full config would be 5.5 TB)"
+    w["extrapolated"] = True
     times, rows = [], 0
     import gsa_ref
     gsa_ref.build()
@@ -163,6 +169,112 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# host memory placement: a rank's host shard lives on the NUMA node its GPU hangs off
+# ------------------------------------------------------------------------------------------------------------------
+def gpu_numa_node(idx: int):
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(idx)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            n = int(f.read())
+        return n if n >= 0 else None
+    except Exception:                                   # noqa: BLE001 - best effort
+        return None
+
+
+def bind_to_node(addr: int, nbytes: int, node) -> str:
+    """mbind(MPOL_BIND) of the page range BEFORE it is first touched; returns how the memory ended up placed"""
+    if node is None or node >= 64:
+        return "default (GPU NUMA node unknown)"
+    import ctypes
+    libc = ctypes.CDLL(None, use_errno=True)
+    page = 4096
+    start = addr & ~(page - 1)
+    length = ((addr + nbytes + page - 1) & ~(page - 1)) - start
+    mask = ctypes.c_ulong(1 << node)
+    rc = libc.syscall(237, ctypes.c_void_p(start), ctypes.c_ulong(length), ctypes.c_int(2), ctypes.byref(mask), ctypes.c_ulong(65),
+                      ctypes.c_uint(0))
+    return f"mbind to node {node}" if rc == 0 else f"default (mbind failed, errno {ctypes.get_errno()})"
+
+
+def W_c4(nout=256, d=20):
+    o, i = np.meshgrid(np.arange(1, nout + 1), np.arange(1, d + 1), indexing="ij")
+    return 1.0 + ((o * 31 + i * 17) % 13) / 13.0
+
+
+def configs_block(g, h, peak, reps=5):
+    """BASELINE configs 1-4 (fused path), K1 in steady state, the estimator-only kernel: device-resident inputs, kernel time from
+    CUDA events around the dominant kernel (gsa_last_timing), the public call's wall time beside it."""
+    import torch
+    out = {}
+    cfgs = {
+        "c1_ishigami_d3_N600000": dict(model=("ishigami", [7.0, 0.1]), d=3, N=600000, order=[0, 1], nboot=1, lb=-np.pi, ub=np.pi),
+        "c2_ishigami_d3_N2^20_order2_nboot1000": dict(model=("ishigami", [7.0, 0.1]), d=3, N=1 << 20, order=[0, 1, 2], nboot=1000, lb=-np.pi, ub=np.pi),
+        "c3_sobolg_d8_N2^22_order2": dict(model=("sobol_g", [0, 1, 4.5, 9, 99, 99, 99, 99]), d=8, N=1 << 22, order=[0, 1, 2], nboot=1, lb=0.0, ub=1.0),
+        "c4_linear_d20_256out_N2^22": dict(model=("linear", W_c4()), d=20, N=1 << 22, order=[0, 1], nboot=1, lb=0.0, ub=1.0),
+    }
+    for name, c in cfgs.items():
+        d, N = c["d"], c["N"]
+        model, method = g.DeviceModel(*c["model"]), g.Sobol(order=c["order"], nboot=c["nboot"])
+        step = 2 * d + 2 if 2 in c["order"] else d + 2
+        n = N // c["nboot"]
+        rows = c["nboot"] * n * step
+        A, B = g.generate_design_matrices(N, np.full(d, c["lb"]), np.full(d, c["ub"]), 2, device=True, handle=h)
+        torch.cuda.synchronize()
+        ks, ts, ws = [], [], []
+        for i in range(reps + 2):
+            t0 = time.perf_counter()
+            res = g.gsa(model, method, A, B, batch=True, handle=h)          # the public call, result on the host
+            w = time.perf_counter() - t0
+            t, k, nl = h.last_timing()
+            if i >= 2:
+                ks.append(k); ts.append(t); ws.append(w)
+        k, t, w = float(np.median(ks)), float(np.median(ts)), float(np.median(ws))
+        alg = 16.0 * d * c["nboot"] * n
+        out[name] = {"rows": rows, "kernel_ms": k, "device_ms": t, "call_wall_ms": 1e3 * w, "launches": nl, "algorithmic_bytes": alg,
+                     "achieved_gbs": alg / (k * 1e-3) / 1e9, "frac": alg / (k * 1e-3) / 1e9 / peak, "rows_per_s_call": rows / w,
+                     "S1_head": np.ravel(res.S1)[:3].tolist()}
+        del A, B
+        torch.cuda.empty_cache()
+    # K1: first touch of fresh memory vs steady state (the second and later calls into the same buffers)
+    for d, N in ((100, 1 << 22), (8, 1 << 24)):
+        mats = g.generate_design_matrices(N, np.zeros(d), np.ones(d), 2, device=True, handle=h)
+        torch.cuda.synchronize()
+        first = h.last_timing()[0]
+        import ctypes as C
+        ptrs = (C.c_void_p * 2)(*[m.t().data_ptr() for m in mats])
+        lbv, ubv = np.zeros(d), np.ones(d)
+        ts = []
+        for _ in range(reps):
+            g.sobol.check(g.lib().gsa_sobol_design(h.ptr, N, d, 2, lbv.ctypes.data, ubv.ctypes.data, 0, N, ptrs, 1))
+            h.synchronize()
+            ts.append(h.last_timing()[0])
+        t = float(np.median(ts))
+        alg = 16.0 * d * N
+        out[f"k1_design_d{d}_N2^{N.bit_length() - 1}"] = {"first_touch_ms": first, "steady_ms": t, "algorithmic_bytes": alg,
+                                                          "achieved_gbs": alg / (t * 1e-3) / 1e9, "frac": alg / (t * 1e-3) / 1e9 / peak}
+        del mats
+        torch.cuda.empty_cache()
+    # estimator-only kernel on a precomputed Y (random values: only the timing matters here; parity is in tests/)
+    for name, d, n, order in (("y_c3_shape_d8_order2", 8, 1 << 22, [0, 1, 2]), ("y_c5_shape_d100", 100, 1 << 22, [0, 1]), ("y_d20_order2", 20, 1 << 21, [0, 1, 2])):
+        step = 2 * d + 2 if 2 in order else d + 2
+        Y = torch.rand(step * n, dtype=torch.float64, device="cuda")
+        ks = []
+        for i in range(reps + 1):
+            g.gsa_sobol_all_y_analysis(g.Sobol(order=order), Y, d, n, handle=h)
+            if i >= 1:
+                ks.append(h.last_timing()[1])
+        k = float(np.median(ks))
+        alg = 8.0 * step * n
+        out[name] = {"rows": step * n, "kernel_ms": k, "algorithmic_bytes": alg, "achieved_gbs": alg / (k * 1e-3) / 1e9,
+                     "frac": alg / (k * 1e-3) / 1e9 / peak}
+        del Y
+        torch.cuda.empty_cache()
+    return out
+
+
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -192,17 +304,15 @@ def gpu_arm(args):
     torch.cuda.synchronize()
     k1_ms = h.last_timing()[0]
     ns = g.nstat(method, d)
-    partials = torch.empty((1, 1, ns), dtype=torch.float64, device="cuda")
-    host_part = torch.empty(partials.shape, dtype=torch.float64).pin_memory()
 
-    # the single collective of the path (a few KB): one kernel per rank over NVLink peer memory (csrc/peer.cu) that also
-    # writes the sums into pinned host memory; torch.distributed's NCCL all-reduce + a D2H copy if the mailboxes cannot be mapped
+    # the single collective of the path (a few KB) runs over NVLink peer memory (csrc/peer.cu), inside the fused kernel's last CTA;
+    # if the mailboxes cannot be mapped every rank falls back to partials + torch.distributed (NCCL) + finalize
     pg, collective = None, "none"
     if world > 1:
         collective = "nccl"
         if args.collective == "peer":
             try:
-                pg = g.PeerGroup(h, partials.numel())
+                pg = g.PeerGroup(h, ns)
                 okf = torch.ones(1, device="cuda")
             except Exception as e:                          # noqa: BLE001 - any rank failing sends every rank to NCCL
                 sys.stderr.write(f"[bench rank {rank}] peer mailboxes unavailable ({e}); using NCCL\n")
@@ -211,21 +321,14 @@ def gpu_arm(args):
             if float(okf) < 1.0:
                 pg = None
             else:
-                collective = "peer-memory kernel (gsa_peer_allreduce)"
-
-    def reduce_to_host():
-        if pg is not None:
-            pg.allreduce(partials, ns, host_out=host_part)
-        else:
-            if world > 1:
-                dist.all_reduce(partials)
-            host_part.copy_(partials, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return g.sobol_finalize(method, host_part.numpy(), d, N)
-
-    def step():
-        g.sobol_partials(model, method, A, B, N, col0, handle=h, out=partials)
-        return reduce_to_host()
+                collective = "peer-memory exchange fused into the kernel's last CTA (gsa_sobol_run_sharded)"
+    one_call = world == 1 or pg is not None
+    if one_call:
+        sstep = g.ShardedStep(model, method, A, B, N, col0, handle=h)
+        step = sstep.run                                    # ONE public call: kernel (+ exchange) + epilogue
+    else:
+        def step():
+            return g.gsa_sharded(model, method, A, B, N, col0, handle=h)
 
     def barrier():
         if world > 1:
@@ -247,7 +350,7 @@ def gpu_arm(args):
     ev0.record()
     for _ in range(args.steps):
         res = step()
-        kernel_ms.append(h.last_timing()[1])               # events already complete: the step synchronised
+        kernel_ms.append(h.last_timing()[1])               # (waits for the step's closing event: the result is already on the host)
     ev1.record()
     barrier()
     tw1 = time.perf_counter()
@@ -266,19 +369,16 @@ def gpu_arm(args):
 
     # ---- extra: the same analysis with the design GENERATED inside the fused kernel (gsa(model, Sobol(), p_range; samples)):
     #      no A/B in memory, no HBM reads.  Reported beside the headline, not instead of it. --------------------------------
-    gen = None
-    if not args.no_gen:
-        def gen_step():
-            g.sobol_partials_generated(model, method, lb, ub, N, col0, ncols, handle=h, out=partials)
-            return reduce_to_host()
-
+    gen, res_g = None, None
+    if not args.no_gen and one_call:
+        gstep = g.ShardedStep(model, method, None, None, N, col0, handle=h, p_range=(lb, ub), ncols=ncols)
         for _ in range(args.warmup):
-            res_g = gen_step()
+            res_g = gstep.run()
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(args.steps):
-            res_g = gen_step()
+            res_g = gstep.run()
         g1.record()
         barrier()
         tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
@@ -286,76 +386,137 @@ def gpu_arm(args):
             dist.all_reduce(tg, op=dist.ReduceOp.MAX)
         gen = {"value": w["rows"] * args.steps / (float(tg[0]) * 1e-3), "unit": UNIT, "ms_per_step": float(tg[0]) / args.steps,
                "hbm_bytes_read": 0, "note": "K1 fused into the product kernel: the Sobol points are generated in registers "
-               "(bit-identical to the materialised design), gsa_sobol_partials_generated",
+               "(bit-identical to the materialised design), gsa_sobol_run_sharded_generated",
                "max_abs_diff_vs_resident": float(max(np.abs(res_g.S1 - res.S1).max(), np.abs(res_g.ST - res.ST).max()))}
 
-    # ---- e2e: public API with HOST (pinned) inputs; H2D of the whole shard inside the timed region ---------------
+    # ---- N > 1: the single-process entry (gsa_multi_*: what a plain Julia ccall uses) on ALL devices, checked against the
+    #      one-process-per-GPU result of this run -------------------------------------------------------
+    multi = None
+    if world > 1 and not args.no_multi:
+        barrier()
+        if rank == 0:
+            try:
+                m = g.GsaMulti(list(range(world)))
+                t0 = time.perf_counter()
+                rm = m.gsa_p_range(model, method, [[0.0, 1.0]] * d, N)
+                dtm = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                rm = m.gsa_p_range(model, method, [[0.0, 1.0]] * d, N)
+                dtm = min(dtm, time.perf_counter() - t0)
+                ref_r = res_g if res_g is not None else res
+                diff = float(max(np.abs(rm.S1 - ref_r.S1).max(), np.abs(rm.ST - ref_r.ST).max()))
+                multi = {"entry": "gsa_multi_sobol_run_generated over %d devices from ONE process (rank 0)" % world,
+                         "max_abs_diff_vs_sharded": diff, "ok": bool(diff <= 1e-12), "rows_per_s": w["rows"] / dtm, "ms": 1e3 * dtm}
+                m.close()
+            except Exception as e:                          # noqa: BLE001 - reported, not fatal for the headline
+                multi = {"error": str(e), "ok": False}
+        barrier()
+
+    # ---- e2e: the public call with HOST inputs; H2D of the whole shard inside the timed region --------------------------
     e2e = None
     if not args.no_e2e:
         cudart = torch.cuda.cudart()
         nbytes = 8 * d * ncols
         hostA = np.empty((ncols, d), dtype=np.float64)
         hostB = np.empty((ncols, d), dtype=np.float64)
+        node = gpu_numa_node(local)
+        placement = [bind_to_node(arr.ctypes.data, nbytes, node) for arr in (hostA, hostB)][0]
+        tA, tB = torch.from_numpy(hostA), torch.from_numpy(hostB)
+        tA.copy_(A.t())                                     # fill the host copies (untimed; first touch under the policy above)
+        tB.copy_(B.t())
+        torch.cuda.synchronize()
         for arr in (hostA, hostB):
             rc = cudart.cudaHostRegister(arr.ctypes.data, nbytes, 0)
             if int(rc) != 0:
                 raise RuntimeError(f"cudaHostRegister failed: {rc}")
-        tA, tB = torch.from_numpy(hostA), torch.from_numpy(hostB)
-        tA.copy_(A.t())                                     # fill the host copies (untimed)
-        tB.copy_(B.t())
-        torch.cuda.synchronize()
         del A, B
+        if one_call:
+            del sstep
         torch.cuda.empty_cache()
         hA, hB = tA.t(), tB.t()                             # (d, ncols) views in Julia layout
+        h.set_stream(None)
+        if world == 1:
+            e2e_step = lambda: g.gsa(model, method, hA, hB, batch=True, handle=h)          # the call a user makes
+        elif pg is not None:
+            e2e_step = g.ShardedStep(model, method, hA, hB, N, col0, handle=h, torch_stream=False).run     # gsa_sobol_run_sharded
+        else:
+            e2e_step = lambda: g.gsa_sharded(model, method, hA, hB, N, col0, handle=h)
 
-        def e2e_step():
-            if world == 1:
-                return g.gsa(model, method, hA, hB, batch=True, handle=h)          # the call a user makes
-            g.sobol_partials(model, method, hA, hB, N, col0, handle=h, out=partials)
-            return reduce_to_host()
+        def timed(nsteps, nwarm):
+            for _ in range(nwarm):
+                r = e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(nsteps):
+                r = e2e_step()
+            mine = time.perf_counter() - t0
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t0, mine], dtype=torch.float64, device="cuda")
+            allr = [tt.clone() for _ in range(world)]
+            if world > 1:
+                dist.all_gather(allr, tt)
+            return r, max(float(x[0]) for x in allr), [float(x[1]) for x in allr]
 
-        for _ in range(args.e2e_warmup):
-            res_e = e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            res_e = e2e_step()
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": w["rows"] * args.e2e_steps / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * d * N,
-               "d2h_bytes_per_step": int(partials.numel() * 8 * world), "steps": args.e2e_steps, "warmup": args.e2e_warmup,
-               "ms_per_step": 1e3 * float(dt[0]) / args.e2e_steps, "host_memory": "pinned (cudaHostRegister)",
+        res_e, dt, per = timed(args.e2e_steps, args.e2e_warmup)
+        e2e = {"value": w["rows"] * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * d * N,
+               "d2h_bytes_per_step": int(ns * 8 * world), "steps": args.e2e_steps, "warmup": args.e2e_warmup,
+               "ms_per_step": 1e3 * dt / args.e2e_steps, "host_memory": "pinned (cudaHostRegister), " + placement,
+               "aggregate_h2d_gbs": 2 * 8 * d * N * args.e2e_steps / dt / 1e9,
+               "per_gpu_h2d_gbs": [round(2 * nbytes * args.e2e_steps / p / 1e9, 1) for p in per],
+               "entry": "gsa_sobol_run" if world == 1 else "gsa_sobol_run_sharded (one call per rank)",
                "max_abs_diff_vs_resident": float(max(np.abs(res_e.S1 - res.S1).max(), np.abs(res_e.ST - res.ST).max()))}
         for arr in (hostA, hostB):
             cudart.cudaHostUnregister(arr.ctypes.data)
+        # the same call on PAGEABLE memory (what a plain Julia Matrix{Float64} is): staged through the library's pinned buffers
+        res_p, dtp, _ = timed(1, 0)
+        e2e["pageable"] = {"value": w["rows"] / dtp, "unit": UNIT, "ms_per_step": 1e3 * dtp, "aggregate_h2d_gbs": 2 * 8 * d * N / dtp / 1e9,
+                           "host_memory": "pageable (numpy), staged by the library",
+                           "max_abs_diff_vs_resident": float(max(np.abs(res_p.S1 - res.S1).max(), np.abs(res_p.ST - res.ST).max()))}
+        del hA, hB, tA, tB, hostA, hostB
 
     if rank == 0:
         peak, peak_src = peaks()
         alg_bytes = 16.0 * d * ncols                          # per launch on one GPU: A and B shards read once
         achieved = alg_bytes / (kms * 1e-3) / 1e9
         traffic, traffic_src = None, None
-        try:   # DRAM bytes per launch from the committed ncu capture (measured at N=2^22, scaled by the algorithmic bytes)
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        try:   # DRAM bytes per launch from the committed ncu capture of the SHIPPED kernel (same binary: checked by its hash)
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
                 tr = json.load(f)["fused_product_kernel"]
-            traffic, traffic_src = tr["dram_bytes_per_algorithmic_byte"] * alg_bytes, tr["source"]
+            import hashlib
+            with open(g.LIB_PATH, "rb") as f:
+                sha = hashlib.sha256(f.read()).hexdigest()[:16]
+            if tr.get("lib_sha256_16") in (None, sha):
+                traffic, traffic_src = tr["dram_bytes_per_algorithmic_byte"] * alg_bytes, tr["source"]
+            else:
+                traffic_src = "profiles/r2_traffic.json was captured from another build of libgsa_cuda.so: not reported"
         except (OSError, KeyError, ValueError):
             pass
-        roofline = {"bound": "hbm", "kernel": "fused_product_kernel<T,CPL> (design swap + Sobol-G + Jansen sums)",
+        roofline = {"bound": "hbm", "kernel": "fused_product_kernel<T,CPL> (design swap + Sobol-G + Jansen sums; its last CTA also "
+                    "does stage 2, the exchange and the host copy)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_source": traffic_src,
                     "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes,
-                    "per_rank_kernel_ms": per_rank_kernel_ms, "k1_design_ms": k1_ms, "k1_design_gbs": 16.0 * d * ncols / (k1_ms * 1e-3) / 1e9}
+                    "per_rank_kernel_ms": per_rank_kernel_ms, "k1_design_first_touch_ms": k1_ms,
+                    "k1_design_first_touch_gbs": 16.0 * d * ncols / (k1_ms * 1e-3) / 1e9,
+                    "host_overhead_ms_per_step": ms_total / args.steps - kms}
+        configs = None
+        if world == 1 and not args.no_configs:
+            try:
+                configs = configs_block(g, h, peak)
+            except Exception as e:                          # noqa: BLE001 - the headline line must still be printed
+                configs = {"error": str(e)}
         cb = None if args.no_cpu else cpu_sample(args.cpu_log2n, 2)
         Vi = 1.0 / (3.0 * (1.0 + np.array(SOBOL_G_A)) ** 2)
         V = np.prod(1.0 + Vi) - 1.0
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": w, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-                "collective": collective, "roofline": roofline, "generated_design": gen, "cpu_baseline": cb, "clocks": clocks,
+                "launches_per_step": launches_per_step,
+                "collective": collective, "roofline": roofline, "generated_design": gen, "multi_single_process": multi,
+                "configs": configs, "cpu_baseline": cb, "clocks": clocks,
                 "check": {"S1_0": float(res.S1[0]), "S1_0_analytic": float(Vi[0] / V), "ST_0": float(res.ST[0]),
-                          "ST_0_analytic": float(Vi[0] * np.prod(1 + Vi) / (1 + Vi[0]) / V)}}
+                          "ST_0_analytic": float(Vi[0] * np.prod(1 + Vi) / (1 + Vi[0]) / V),
+                          "parity": "tests/test_gpu_parity.py::test_config5_full_size_vs_streamed_oracle (1e-12 at N=2^26)"}}
         emit(line)
     if pg is not None:
         if pg.status() != 0:
@@ -400,6 +561,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gen", action="store_true")
+    ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the single-process (gsa_multi) cross-check")
+    ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the per-config block (BASELINE configs 1-4, K1, estimator on Y)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"], help="N > 1: how the partial sums are all-reduced")
     args = ap.parse_args()
     if args.impl == "reference":
