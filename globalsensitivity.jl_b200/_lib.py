@@ -49,6 +49,7 @@ SIGNATURES = {
     "gsa_model_lookup": [C.c_char_p, _ip],
     "gsa_model_nout": [_vp, _i, _i, _i, _ip],
     "gsa_model_register_fatbin": [_vp, _vp, _sz, C.c_char_p, _i, _ip],
+    "gsa_model_register_separable": [_vp, _vp, _sz, C.c_char_p, _i, _ip],
     "gsa_sobol_design": [_vp, _i64, _i, _i, _vp, _vp, _i64, _i64, C.POINTER(_vp), _i],
     "gsa_sobol_nstat": [_op, _i, _ip],
     "gsa_sobol_run": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
@@ -67,6 +68,7 @@ SIGNATURES = {
     "gsa_multi_device_count": [_vp, _ip],
     "gsa_multi_handle": [_vp, _i, C.POINTER(_vp)],
     "gsa_multi_model_register_fatbin": [_vp, _vp, _sz, C.c_char_p, _i, _ip],
+    "gsa_multi_model_register_separable": [_vp, _vp, _sz, C.c_char_p, _i, _ip],
     "gsa_multi_sobol_run": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
     "gsa_multi_sobol_run_generated": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
     "gsa_last_timing": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _ip],

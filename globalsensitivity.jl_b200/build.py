@@ -53,20 +53,34 @@ def build(force: bool = False, verbose: bool = False) -> str:
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     blob = os.path.join(obj_dir, "directions_blob.o")
     subprocess.check_call(["/usr/bin/gcc", "-c", os.path.join(CSRC, "directions_blob.S"), f'-DGSA_TABLE_PATH="{TABLE}"', "-o", blob])
-    # the generic kernel with an unresolved model, as a relocatable cubin that gsa_model_register_fatbin links at run time
-    ucu = os.path.join(obj_dir, "user_kernel.cu")
-    shutil.copyfile(os.path.join(CSRC, "user_kernel.cu.in"), ucu)
-    ucubin = os.path.join(obj_dir, "user_kernel.cubin")
-    subprocess.check_call([nvcc(), "-ccbin", HOST_CXX, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-rdc=true", "-cubin", "-I", CSRC, "-o", ucubin, ucu])
-    ublob = os.path.join(obj_dir, "user_blob.o")
-    subprocess.check_call(["/usr/bin/gcc", "-c", os.path.join(CSRC, "user_blob.S"), f'-DGSA_USER_CUBIN_PATH="{ucubin}"', "-o", ublob])
+    # the fused kernels with an UNRESOLVED user model, as relocatable cubins that gsa_model_register_* link at run time:
+    # generic (gsa_user_model), product form (gsa_user_factor), additive (gsa_user_term)
+    user_procs, user_blobs = [], []
+    for tag, src_in, defs in (("kernel", "user_kernel.cu.in", []), ("product", "user_kernel_separable.cu.in", ["-DGSA_USER_KIND=1"]),
+                              ("additive", "user_kernel_separable.cu.in", ["-DGSA_USER_KIND=2"])):
+        ucu = os.path.join(obj_dir, f"user_{tag}.cu")
+        shutil.copyfile(os.path.join(CSRC, src_in), ucu)
+        ucubin = os.path.join(obj_dir, f"user_{tag}.cubin")
+        cmd = [nvcc(), "-ccbin", HOST_CXX, "-std=c++17", "-O3", "-lineinfo", *ARCH, "-rdc=true", "-cubin", "-I", CSRC, *defs, "-o", ucubin, ucu]
+        user_procs.append((ucu, ucubin, tag, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for ucu, ucubin, tag, p in user_procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError(f"nvcc failed on {ucu}")
+        ublob = os.path.join(obj_dir, f"user_blob_{tag}.o")
+        sym = f"gsa_user_{tag}_blob"
+        subprocess.check_call(["/usr/bin/gcc", "-c", os.path.join(CSRC, "user_blob.S"), f"-DGSA_BLOB_SYM={sym}", f"-DGSA_BLOB_END={sym}_end",
+                               f'-DGSA_USER_CUBIN_PATH="{ucubin}"', "-o", ublob])
+        user_blobs.append(ublob)
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [nvcc(), "-ccbin", HOST_CXX, "-shared", *ARCH, "-o", OUT, *objs, blob, ublob, "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    link = [nvcc(), "-ccbin", HOST_CXX, "-shared", *ARCH, "-o", OUT, *objs, blob, *user_blobs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     subprocess.check_call(link)
     return OUT
 

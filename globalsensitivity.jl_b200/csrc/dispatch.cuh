@@ -27,6 +27,7 @@ struct FusedPlan {
     const void* kernel = nullptr;
 
     int prod_T = 0, prod_CPL = 0;
+    bool user_sep = false;       // product kernel linked against a user's per-coordinate function (gsa_model_register_separable)
     bool gen = false;            // the design is generated inside the kernel (gsa_sobol_*_generated)
     uint64_t gen_first = 0;
     int gen_nboot = 1, gen_unit_box = 0;
@@ -38,7 +39,7 @@ struct FusedPlan {
     bool writes_partials() const { return kind == PLAN_LINEAR; }   // the plan adds its records to `out_partials` itself
     double* out_partials = nullptr;
     double* rec_base = nullptr;   // where the tile records go: h->tile_rec, or straight into `partials` when a replicate is one tile
-    TailArgs tail{};              // tail.counter != nullptr: the launch ends with stage 2 + exchange + host copy in its last CTA (tail.cuh)
+    TailArgs tail{};              // tail.counters != nullptr: stage 2 + exchange + host copy happen inside the launch (tail.cuh)
     bool supports_tail() const { return kind == PLAN_PRODUCT; }
 
     int prepare(gsa_handle* h, const double* params, int np);
@@ -47,13 +48,13 @@ struct FusedPlan {
 
 using GenericKernel = void (*)(GenericArgs);
 
-template <bool SECOND>
+template <bool SECOND, bool LARGE>
 static GenericKernel generic_kernel_for(int model) {
     switch (model) {
-        case GSA_MODEL_ISHIGAMI: return fused_generic_kernel<IshigamiModel, SECOND>;
-        case GSA_MODEL_SOBOL_G: return fused_generic_kernel<SobolGModel, SECOND>;
-        case GSA_MODEL_LINEAR: return fused_generic_kernel<LinearModel, SECOND>;
-        case GSA_MODEL_ISHI_LINEAR: return fused_generic_kernel<IshiLinearModel, SECOND>;
+        case GSA_MODEL_ISHIGAMI: return fused_generic_kernel<IshigamiModel, SECOND, LARGE>;
+        case GSA_MODEL_SOBOL_G: return fused_generic_kernel<SobolGModel, SECOND, LARGE>;
+        case GSA_MODEL_LINEAR: return fused_generic_kernel<LinearModel, SECOND, LARGE>;
+        case GSA_MODEL_ISHI_LINEAR: return fused_generic_kernel<IshiLinearModel, SECOND, LARGE>;
         default: return nullptr;
     }
 }
@@ -63,25 +64,30 @@ static int plan_generic(gsa_handle* h, FusedPlan* p) {
         return fail(GSA_ERR_UNSUPPORTED, "generic fused kernel supports d <= %d (got %d)", GENERIC_DMAX, p->d);
     if (p->nout > GENERIC_NOMAX)
         return fail(GSA_ERR_UNSUPPORTED, "generic fused kernel supports nout <= %d (got %d)", GENERIC_NOMAX, p->nout);
+    if (p->d * p->nout > GENERIC_ACC_L)
+        return fail(GSA_ERR_UNSUPPORTED, "generic fused kernel supports d*nout <= %d (got %d)", GENERIC_ACC_L, p->d * p->nout);
     if (p->second && p->d * p->nout > GENERIC_YMAX)
         return fail(GSA_ERR_UNSUPPORTED, "generic second-order kernel supports d*nout <= %d (got %d)", GENERIC_YMAX, p->d * p->nout);
+    const bool large = p->d > 32 || p->d * p->nout > GENERIC_ACC_S;   // which instantiation: capacity of the per-thread arrays
     const void* k = nullptr;
     const bool user = p->model >= GSA_MODEL_USER_BASE;
     if (user) {
         const int idx = p->model - GSA_MODEL_USER_BASE;
         if (idx >= (int)h->user_models.size()) return fail(GSA_ERR_INVALID, "unknown user model id %d for this handle", p->model);
-        k = (const void*)(p->second ? h->user_models[idx].k_second : h->user_models[idx].k_first);
+        k = (const void*)h->user_models[idx].k_generic[p->second ? 1 : 0][large ? 1 : 0];
+    } else if (p->second) {
+        k = large ? (const void*)generic_kernel_for<true, true>(p->model) : (const void*)generic_kernel_for<true, false>(p->model);
     } else {
-        k = (const void*)(p->second ? generic_kernel_for<true>(p->model) : generic_kernel_for<false>(p->model));
+        k = large ? (const void*)generic_kernel_for<false, true>(p->model) : (const void*)generic_kernel_for<false, false>(p->model);
     }
     if (!k) return fail(GSA_ERR_INVALID, "unknown model id %d", p->model);
-    const size_t rec_bytes = sizeof(double) * (size_t)p->nstat * p->nout;
-    int warps = (int)std::min<size_t>(8, ((user ? 48u : 160u) << 10) / rec_bytes);   // linked kernels: stay within the default 48 KB
+    const size_t rec_bytes = sizeof(double) * (size_t)p->nstat * p->nout, per_warp = rec_bytes + sizeof(double) * GENERIC_TILE_DOUBLES;
+    int warps = (int)std::min<size_t>(8, ((user ? 48u : 160u) << 10) / per_warp);   // linked kernels: stay within the default 48 KB
     if (warps < 1) return fail(GSA_ERR_UNSUPPORTED, "statistics record of %zu bytes does not fit in shared memory", rec_bytes);
     p->kind = PLAN_GENERIC;
     p->kernel = k;
     p->threads = 32 * warps;
-    p->smem = rec_bytes * warps;
+    p->smem = per_warp * warps;
     int nb = 2;
     if (!user) {
         if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
@@ -150,13 +156,23 @@ static bool product_shape(int d, int* T, int* cpl) {
 
 static int plan_product(gsa_handle* h, FusedPlan* p) {
     p->kind = PLAN_PRODUCT;
-    p->kernel = (const void*)product_kernel_for(p->prod_T, p->prod_CPL, p->gen, p->est == GSA_EI_JANSEN1999);
     p->threads = PROD_THREADS;
     const int slots = p->prod_T * p->prod_CPL;
     p->smem = sizeof(double) * (2 * slots + (PROD_THREADS / 32) * (2 * slots + 8) + (p->gen ? 2 * slots + (32 * (2 * slots + 1) + 1) / 2 : 0));
-    if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
     int nb = 0;
-    GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));
+    if (p->user_sep) {
+        int rc = user_separable_kernel(h, p->model, p->prod_T, p->prod_CPL, p->est == GSA_EI_JANSEN1999, &p->kernel);
+        if (rc) return rc;
+        if (p->smem > (48u << 10)) return fail(GSA_ERR_UNSUPPORTED, "separable user kernel: d = %d needs %zu bytes of shared memory (max 48 KB)", p->d, p->smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem) != cudaSuccess) {
+            cudaGetLastError();
+            nb = 2;
+        }
+    } else {
+        p->kernel = (const void*)product_kernel_for(p->prod_T, p->prod_CPL, p->gen, p->est == GSA_EI_JANSEN1999);
+        if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+        GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));
+    }
     p->resident = std::max(1, nb) * h->sm_count;
     p->ts_min = p->ts_gran = PROD_THREADS / p->prod_T;
     return GSA_OK;
@@ -218,6 +234,11 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
     const bool one_term = est == GSA_EI_JANSEN1999 || (!gen && (est == GSA_EI_SOBOL2007 || est == GSA_EI_HOMMA1996));
     if (!generic_only && model == GSA_MODEL_SOBOL_G && !second && one_term && product_shape(d, &p->prod_T, &p->prod_CPL))
         return plan_product(h, p);
+    if (!generic_only && !gen && model >= GSA_MODEL_USER_BASE && model - GSA_MODEL_USER_BASE < (int)h->user_models.size() &&
+        h->user_models[model - GSA_MODEL_USER_BASE].kind != GSA_USER_GENERIC && !second && one_term && product_shape(d, &p->prod_T, &p->prod_CPL)) {
+        p->user_sep = true;   // product-form / additive user model: the O(d) kernel linked against its per-coordinate function
+        return plan_product(h, p);
+    }
     if (gen)
         return fail(GSA_ERR_UNSUPPORTED, "fused design generation is implemented for product-form models (sobol_g), S1/ST, Jansen1999, d <= 416; "
                                          "use gsa_sobol_design + gsa_sobol_run for this request");
@@ -341,11 +362,12 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
     else if (kind == PLAN_PRODUCT) {
         ProductArgs a;
         a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = recs;
+        a.params = h->params.as<double>(); a.np = np;
         a.g = g; a.d = d; a.nstat = nstat; a.t_begin = t0; a.t_end = t1; a.est = est;
         a.V = h->vtab.as<uint32_t>(); a.box = h->lbub.as<double2>(); a.first = gen_first; a.nboot = gen_nboot; a.unit_box = gen_unit_box;
         a.tail = tail;
-        if (tail.counter) a.tail.target = (h->tail_arrived += (unsigned long long)grid);
-        ((ProductKernel)kernel)<<<grid, threads, smem, h->stream>>>(a);
+        void* kargs[] = {&a};
+        GSA_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, h->stream));   // (also takes the cudaKernel_t of a linked user kernel)
     }
     GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
     h->kernel_timed = true;
@@ -359,7 +381,7 @@ inline int FusedPlan::prepare(gsa_handle* h, const double* params, int np_) {
         pa = params[0];
         pb = params[1];
     }
-    if ((kind == PLAN_PRODUCT || kind == PLAN_SMALL_SOBOLG || kind == PLAN_PAIRS_MMA) && h->aux_kind != PLAN_PRODUCT) {
+    if ((kind == PLAN_PRODUCT || kind == PLAN_SMALL_SOBOLG || kind == PLAN_PAIRS_MMA) && !user_sep && h->aux_kind != PLAN_PRODUCT) {
         // (upload_params resets aux_kind whenever the parameters change)
         // g_k(x) = (|4x-2| + a_k)/(1 + a_k) = |x - 0.5| * 4/(1+a_k) + a_k/(1+a_k)
         std::vector<double> c(2 * (size_t)d);

@@ -21,9 +21,33 @@
 
 namespace gsa {
 
+// ---- the per-coordinate function g_k of a separable model ------------------------------------------------------------------
+// built in: Sobol G, coefficients staged in shared memory
+struct SobolGFactor {
+    static constexpr bool kUser = false;
+    __device__ __forceinline__ static double eval(int k, double x, const double2* scoef, const double*, int) {
+        const double2 c = scoef[k];
+        return fma(fabs(x - 0.5), c.x, c.y);
+    }
+};
+// supplied by the user as relocatable device code (gsa_model_register_separable), resolved by nvJitLink:
+//   product form  f(x) = prod_k gsa_user_factor(k, x_k, p, np)        additive  f(x) = sum_k gsa_user_term(k, x_k, p, np)
+extern "C" __device__ double gsa_user_factor(int k, double x, const double* p, int np);
+extern "C" __device__ double gsa_user_term(int k, double x, const double* p, int np);
+struct UserFactor {
+    static constexpr bool kUser = true;
+    __device__ __forceinline__ static double eval(int k, double x, const double2*, const double* p, int np) { return gsa_user_factor(k, x, p, np); }
+};
+struct UserTerm {
+    static constexpr bool kUser = true;
+    __device__ __forceinline__ static double eval(int k, double x, const double2*, const double* p, int np) { return gsa_user_term(k, x, p, np); }
+};
+
 struct ProductArgs {
     const double* A;
     const double* B;
+    const double* params; // user factors / terms: the model's parameter vector (device memory)
+    int np;
     const double2* coef;  // [d] (c1_k, c0_k): g_k(x) = |x - 0.5| * c1_k + c0_k,  c1 = 4/(1+a_k), c0 = a_k/(1+a_k)
     double* tile_rec;     // [ntiles][nstat]
     TileGeom g;
@@ -34,7 +58,7 @@ struct ProductArgs {
     const double2* box;   // [d] (ub-lb, lb)
     uint64_t first;       // 0-based sequence index of sample 0 of every replicate: 2^floor(log2 samples)
     int nboot, unit_box;  // unit_box: lb = 0, ub = 1 for every coordinate (the affine map is the identity)
-    TailArgs tail;        // tail.counter != nullptr: stage 2, the all-reduce and the host copy run in this launch's last CTA
+    TailArgs tail;        // tail.counters != nullptr: stage 2, the all-reduce and the host copy run inside this launch (tail.cuh)
 };
 
 #ifndef PROD_GEN_MINBLOCKS
@@ -56,8 +80,10 @@ constexpr size_t product_smem_doubles() {
 // JANSEN = false: the total-order term is sum yA (yA - yAB_k) (Sobol2007, :211) or sum yA yAB_k (Homma1996, :207) instead of
 // sum (yA - yAB_k)^2 (:213) -- one accumulator per coordinate either way, so the same kernel serves all three (the headline
 // instantiation keeps its code unchanged; Janon2014 needs three terms per coordinate and stays on the generic kernel).
-template <int T, int CPL, bool GEN, bool JANSEN = true>
-__global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fused_product_kernel(ProductArgs a) {
+// F: the per-coordinate function (SobolGFactor, UserFactor, UserTerm).  ADD = true: the model is the SUM of its terms instead of
+// the product of its factors -- f(AB_k) = yA + (g_k(B_k) - g_k(A_k)) -- same mapping, same accumulators, no prefix/suffix sweeps.
+template <int T, int CPL, bool GEN, bool JANSEN, class F, bool ADD>
+__device__ __forceinline__ void fused_product_body(const ProductArgs& a) {
     const bool sobol2007 = a.est == GSA_EI_SOBOL2007;   // (only read when !JANSEN)
     constexpr int NW = PROD_THREADS / 32;
     constexpr int NG = PROD_THREADS / T;  // sample groups per CTA
@@ -78,7 +104,7 @@ __global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fu
     // group that has already left the loop (found the hard way: a hang on N = 100003, nboot = 3).
     const unsigned gmask = T >= 32 ? 0xffffffffu : (((1u << (T & 31)) - 1u) << (lane & ~(T - 1)));
     for (int i = threadIdx.x; i < SLOTS; i += PROD_THREADS) {
-        scoef[i] = i < d ? a.coef[i] : make_double2(0.0, 1.0);
+        if (!F::kUser) scoef[i] = i < d ? a.coef[i] : make_double2(0.0, 1.0);
         if (GEN) sbox[i] = i < d ? a.box[i] : make_double2(0.0, 0.0);
     }
     int vs_rep = -1;  // replicate whose direction numbers are in Vs
@@ -156,14 +182,19 @@ __global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fu
                     gB[i] = ldg_stream(bs + off);
                 }
             }
-            double LA = 1.0, LB = 1.0;
+            double LA = ADD ? 0.0 : 1.0, LB = ADD ? 0.0 : 1.0;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
-                const double2 c = scoef[t + T * i];
-                gA[i] = fma(fabs(gA[i] - 0.5), c.x, c.y);
-                gB[i] = fma(fabs(gB[i] - 0.5), c.x, c.y);
-                LA *= gA[i];
-                LB *= gB[i];
+                const int k = t + T * i;
+                if constexpr (F::kUser) {   // padded coordinates (k >= d) contribute the neutral element
+                    gA[i] = k < d ? F::eval(k, gA[i], scoef, a.params, a.np) : (ADD ? 0.0 : 1.0);
+                    gB[i] = k < d ? F::eval(k, gB[i], scoef, a.params, a.np) : (ADD ? 0.0 : 1.0);
+                } else {
+                    gA[i] = F::eval(k, gA[i], scoef, a.params, a.np);
+                    gB[i] = F::eval(k, gB[i], scoef, a.params, a.np);
+                }
+                if constexpr (ADD) { LA += gA[i]; LB += gB[i]; }
+                else { LA *= gA[i]; LB *= gB[i]; }
             }
             // butterfly over the T lanes of the group: product of the others (A) and the totals (A, B)
             double others = 1.0, yA = LA, yB = LB;
@@ -171,26 +202,36 @@ __global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fu
             for (int o = 1; o < T; o <<= 1) {
                 const double pa = __shfl_xor_sync(gmask, yA, o);
                 const double pb = __shfl_xor_sync(gmask, yB, o);
-                others *= pa;
-                yA *= pa;
-                yB *= pb;
+                if constexpr (ADD) { yA += pa; yB += pb; }
+                else { others *= pa; yA *= pa; yB *= pb; }
             }
-            // prefix products seeded with the other lanes' product, then the suffix sweep
-            double run = others;
+            if constexpr (ADD) {
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-                P[i] = run;
-                run *= gA[i];
-            }
-            double suf = 1.0;
+                for (int i = 0; i < CPL; ++i) {
+                    const double df = gB[i] - gA[i];   // f(AB_k) - f(A): only term k changes
+                    const double yAB = yA + df;
+                    V[i] = fma(yB, df, V[i]);  // :192
+                    if constexpr (JANSEN) E[i] = fma(df, df, E[i]);  // :213
+                    else E[i] = fma(yA, sobol2007 ? -df : yAB, E[i]);  // :211 / :207
+                }
+            } else {
+                // prefix products seeded with the other lanes' product, then the suffix sweep
+                double run = others;
 #pragma unroll
-            for (int i = CPL - 1; i >= 0; --i) {
-                const double yAB = P[i] * (gB[i] * suf);
-                suf *= gA[i];
-                const double df = yAB - yA;
-                V[i] = fma(yB, df, V[i]);  // :192
-                if constexpr (JANSEN) E[i] = fma(df, df, E[i]);  // :213
-                else E[i] = fma(yA, sobol2007 ? -df : yAB, E[i]);  // :211 / :207
+                for (int i = 0; i < CPL; ++i) {
+                    P[i] = run;
+                    run *= gA[i];
+                }
+                double suf = 1.0;
+#pragma unroll
+                for (int i = CPL - 1; i >= 0; --i) {
+                    const double yAB = P[i] * (gB[i] * suf);
+                    suf *= gA[i];
+                    const double df = yAB - yA;
+                    V[i] = fma(yB, df, V[i]);  // :192
+                    if constexpr (JANSEN) E[i] = fma(df, df, E[i]);  // :213
+                    else E[i] = fma(yA, sobol2007 ? -df : yAB, E[i]);  // :211 / :207
+                }
             }
             if (T == 1) {
                 dd_add(sA1, yA); dd_add_sq(sA2, yA);
@@ -274,8 +315,13 @@ __global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fu
             rec[0] = a1.hi; rec[1] = a1.lo; rec[2] = a2.hi; rec[3] = a2.lo;   // over [yA; yB]
         }
         __syncthreads();
+        if (a.tail.counters) fused_tail_tile_done(a.tail, tile);   // sign off: group -> replicate -> exchange (tail.cuh)
     }
-    if (a.tail.counter) fused_tail(a.tail);
+}
+
+template <int T, int CPL, bool GEN, bool JANSEN = true>
+__global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fused_product_kernel(ProductArgs a) {
+    fused_product_body<T, CPL, GEN, JANSEN, SobolGFactor, false>(a);
 }
 
 }  // namespace gsa

@@ -251,10 +251,7 @@ struct TailRequest {
 int peer_allreduce_launch(gsa_handle* h, double* data_dev, size_t count, int nstat, double* host_out_mapped_dev);   // peer.cu
 
 static int ensure_tail(gsa_handle* h, size_t count) {
-    if (!h->tail_counter) {
-        GSA_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->tail_counter), sizeof(unsigned long long)));
-        GSA_CUDA(cudaMemset(h->tail_counter, 0, sizeof(unsigned long long)));
-        h->tail_arrived = 0;
+    if (!h->tail_flag) {
         GSA_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->tail_flag), sizeof(unsigned long long), cudaHostAllocMapped));
         *h->tail_flag = 0;
         h->tail_flag_value = 0;
@@ -425,11 +422,22 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         const bool fuse = want_tail && plan.supports_tail() && !host_in && t_hi > t_lo && !getenv("GSA_NO_TAIL");
         if (fuse) {
             TailArgs& t = plan.tail;
-            t.counter = h->tail_counter;
+            const size_t cbytes = sizeof(unsigned int) * tail_counter_count(nrep, g.tpr);
+            if (h->tail_counters.cap < cbytes) h->tail_counters_zeroed = 0;
+            if ((rc = h->tail_counters.reserve(cbytes))) return rc;
+            if (h->tail_counters_zeroed < cbytes) {   // the counters clean up after themselves: zeroed once per (re)allocation
+                GSA_CUDA(cudaMemsetAsync(h->tail_counters.p, 0, h->tail_counters.cap, h->stream));
+                h->tail_counters_zeroed = h->tail_counters.cap;
+            }
+            t.ngr = tail_groups_per_replicate(g.tpr);
+            if (!direct && (rc = h->tail_grec.reserve(sizeof(double) * (size_t)nrep * t.ngr * recsz))) return rc;
+            t.counters = h->tail_counters.as<unsigned int>();
             t.tile_rec = direct ? nullptr : h->tile_rec.as<double>();
+            t.grec = direct ? nullptr : h->tail_grec.as<double>();
             t.partials = partials;
             t.reduce = direct ? 0 : 1;
             t.recsz = recsz; t.nstat = nstat; t.tpr = g.tpr; t.rep_first = g.rep_first; t.nrep = nrep; t.nboot = o->nboot;
+            t.t_lo = t_lo; t.t_hi = t_hi;
             t.exchange = 0;
             t.host_out = nullptr;
             if (tr->exchange) {
@@ -716,10 +724,9 @@ int gsa_destroy(gsa_handle* h) {
         if (h->stream) cudaStreamSynchronize(h->stream);
         if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
         peer_release_handle(h);
-        if (h->tail_counter) cudaFree(h->tail_counter);
         if (h->tail_host) cudaFreeHost(h->tail_host);
         if (h->tail_flag) cudaFreeHost(h->tail_flag);
-        DevBuf* bufs[] = {&h->tile_rec, &h->partials, &h->params, &h->vtab, &h->lbub, &h->stage[0], &h->stage[1], &h->dev_in[0], &h->dev_in[1], &h->ybuf, &h->aux, &h->gram};
+        DevBuf* bufs[] = {&h->tile_rec, &h->partials, &h->params, &h->vtab, &h->lbub, &h->stage[0], &h->stage[1], &h->dev_in[0], &h->dev_in[1], &h->ybuf, &h->aux, &h->gram, &h->tail_counters, &h->tail_grec};
         for (DevBuf* b : bufs) b->release();
         for (auto& um : h->user_models)
             if (um.lib) cudaLibraryUnload(um.lib);
@@ -785,7 +792,14 @@ int gsa_model_register_fatbin(gsa_handle* h, const void* image, size_t len, cons
     if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->device);
-    return register_user_model(h, image, len, symbol, nout, model_id);
+    return register_user_model(h, image, len, symbol, GSA_USER_GENERIC, nout, model_id);
+}
+
+int gsa_model_register_separable(gsa_handle* h, const void* image, size_t len, const char* symbol, int kind, int* model_id) {
+    if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->device);
+    return register_user_model(h, image, len, symbol, kind, 1, model_id);
 }
 
 int gsa_sobol_nstat(const gsa_sobol_opts* o, int d, int* nstat) {

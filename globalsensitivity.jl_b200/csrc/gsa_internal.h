@@ -58,10 +58,12 @@ void direction_numbers(int dim_first, int ndim, uint32_t* V /* ndim x 32 */);
 namespace gsa {
 struct UserModelEntry {
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t k_first = nullptr, k_second = nullptr;
+    cudaKernel_t k_generic[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [second order][large instantiation]
     int nout = 1;
+    int kind = 0;   // GSA_USER_GENERIC | GSA_USER_PRODUCT | GSA_USER_ADDITIVE
 };
-int register_user_model(gsa_handle* h, const void* image, size_t len, const char* symbol, int nout, int* model_id);
+int register_user_model(gsa_handle* h, const void* image, size_t len, const char* symbol, int kind, int nout, int* model_id);
+int user_separable_kernel(gsa_handle* h, int model_id, int T, int cpl, bool jansen, const void** kernel);
 struct PeerState;                          // peer.cu: mailboxes of the NVLink all-reduce
 void peer_release_handle(gsa_handle* h);   // frees h->peer (no-op when absent)
 }  // namespace gsa
@@ -83,10 +85,10 @@ struct gsa_handle {
     bool kernel_timed = false;   // evk0/evk1 bracket the dominant kernel of the last call
     int last_launches = 0;
     gsa::PeerState* peer = nullptr;
-    // fused tail (tail.cuh): device counter of arrived CTAs (monotonic over launches; tail_arrived = its value once everything
-    // issued so far has run), and the result mailbox in mapped pinned host memory: sums + a flag the last CTA raises
-    unsigned long long* tail_counter = nullptr;
-    unsigned long long tail_arrived = 0;
+    // fused tail (tail.cuh): self-cleaning arrival counters and group records in device memory, and the result mailbox in mapped
+    // pinned host memory: sums + a flag the last CTA raises
+    gsa::DevBuf tail_counters, tail_grec;
+    size_t tail_counters_zeroed = 0;        // bytes of tail_counters known to be zero
     double* tail_host = nullptr;            // [tail_host_cap] sums, host view
     double* tail_host_dev = nullptr;        // device view of the same memory
     size_t tail_host_cap = 0;

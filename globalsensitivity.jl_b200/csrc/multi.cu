@@ -148,6 +148,22 @@ int gsa_multi_model_register_fatbin(gsa_multi* m, const void* image, size_t len,
     return GSA_OK;
 }
 
+int gsa_multi_model_register_separable(gsa_multi* m, const void* image, size_t len, const char* symbol, int kind, int* model_id) {
+    if (!m || !model_id) return fail(GSA_ERR_INVALID, "NULL argument to gsa_multi_model_register_separable");
+    std::lock_guard<std::mutex> lk(m->mu);
+    int first = -1;
+    for (gsa_handle* hh : m->h) {
+        int id = -1;
+        const int rc = gsa_model_register_separable(hh, image, len, symbol, kind, &id);
+        if (rc != GSA_OK) return rc;
+        if (first < 0) first = id;
+        else if (id != first)
+            return fail(GSA_ERR_INVALID, "user model got id %d on device %d but %d on the first device: register models through gsa_multi only", id, hh->device, first);
+    }
+    *model_id = first;
+    return GSA_OK;
+}
+
 int gsa_multi_handle(gsa_multi* m, int i, gsa_handle** out) {
     if (!m || !out || i < 0 || i >= (int)m->h.size()) return fail(GSA_ERR_INVALID, "bad arguments to gsa_multi_handle");
     *out = m->h[i];

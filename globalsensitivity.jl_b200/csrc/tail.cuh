@@ -1,11 +1,18 @@
 // tail.cuh -- the end of a K2+K3 launch, fused into the kernel itself (one launch per step):
 //
-// The CTA that finishes LAST (a device-wide counter, monotonic over launches) does what used to be two more launches and a copy:
-//   1. stage 2: sums the tile records of every replicate in tile order (fixed order: bitwise reproducible) into `partials`
-//      (replicates this shard does not touch are written as zeros, so no memset precedes the launch);
-//   2. K5: pushes the partial sums into every peer's mailbox over NVLink, publishes, waits for the peers' and adds them in
-//      rank order (peer.cuh) -- or, on a single GPU, copies them into mapped pinned host memory;
-//   3. raises a flag in mapped pinned host memory: the host sees the result without waiting for the stream to drain.
+// What used to follow the fused kernel -- a stage-2 launch that sums the tile records, a launch for the all-reduce, a copy to
+// the host -- is done by the kernel's own CTAs as they finish, in a FIXED-ORDER TREE (results do not depend on who arrives when):
+//   tile    a CTA that has written the record of tile t signs off at the tile's GROUP (TAIL_G consecutive tiles of a replicate);
+//   group   the CTA whose arrival completes a group sums the group's tile records in tile order into a group record -- while the
+//           other CTAs are still computing -- and signs off at the REPLICATE;
+//   repl.   the CTA that completes a replicate sums its group records in group order into `partials` and signs off at the top;
+//   top     the CTA that completes the launch zeroes the replicates this shard does not touch, runs K5 -- pushes the partial sums
+//           into every peer's mailbox over NVLink, publishes, waits for the peers' and adds them in rank order (peer.cuh) -- or,
+//           on a single GPU, copies them into mapped pinned host memory, and finally raises a flag in mapped pinned host memory:
+//           the host sees the result without waiting for the stream to drain.
+// Only the last group, the last replicate and the exchange are on the critical path (~10 us + the exchange); a single last CTA
+// that summed all 888 x 208 doubles of config 5 itself took ~100 us (profiles/r2_peer_probe_n2_first.json).
+// Counters are self-cleaning (whoever completes a level resets its counter), so nothing is memset between launches.
 // (SURVEY 5 / VERDICT r1 #3: "fold reduce_tiles and the peer push into the last-arriving CTA of the fused kernel".)
 #pragma once
 #include "gsa_common.cuh"
@@ -13,63 +20,97 @@
 
 namespace gsa {
 
+constexpr int TAIL_G = 32;   // tiles per group
+
 struct TailArgs {
-    unsigned long long* counter;   // nullptr: no fused tail (the launch is followed by reduce_tiles etc.)
-    unsigned long long target;     // value of the counter after the last CTA of THIS launch has arrived
+    unsigned int* counters;        // nullptr: no fused tail.  [nrep*ngr] groups, then [nrep] replicates, then [1] top
     const double* tile_rec;        // [nrep*tpr][recsz]   (reduce != 0)
+    double* grec;                  // [nrep*ngr][recsz] group records (reduce != 0)
     double* partials;              // [nboot][recsz]
     double* host_out;              // mapped pinned host copy of the final sums (may be null)
     unsigned long long* host_flag; // mapped pinned: set to flag_value after host_out is complete (may be null)
     unsigned long long flag_value;
-    int reduce;                    // 1: stage 2 here; 0: the tiles were written straight into `partials`
+    int reduce;                    // 1: tile records -> partials here; 0: the tiles were written straight into `partials` (tpr == 1)
     int exchange;                  // 1: peer all-reduce of `partials`
-    int recsz, nstat, tpr, rep_first, nrep, nboot;
+    int recsz, nstat, tpr, ngr, rep_first, nrep, nboot, t_lo, t_hi;   // launched tiles: [t_lo, t_hi) of the nrep*tpr local tiles
     PeerArgs peer;
 };
 
+inline int tail_groups_per_replicate(int tpr) { return (tpr + TAIL_G - 1) / TAIL_G; }
+inline size_t tail_counter_count(int nrep, int tpr) { return (size_t)nrep * tail_groups_per_replicate(tpr) + nrep + 1; }
+
 #ifdef __CUDACC__
-__device__ __forceinline__ void fused_tail(const TailArgs& t) {
-    __shared__ int s_last, s_timed_out;
-    __threadfence();    // this thread's tile records are visible device-wide before the CTA signs off
+// sum of `cnt` records (stride `stride` doubles, element i of record j at base[j*stride + i]) in record order -> out[0..recsz)
+__device__ __forceinline__ void tail_sum_records(const double* base, int cnt, size_t stride, int recsz, int nstat, double* out) {
+    for (int i = threadIdx.x; i < recsz; i += blockDim.x) {
+        const int e = i % nstat;
+        const bool is_dd = e < STAT_DD;
+        if (is_dd && (e & 1)) continue;
+        const double* b = base + i;
+        if (is_dd) {
+            dd s{0.0, 0.0};
+            for (int j = 0; j < cnt; ++j) dd_add_dd(s, dd{__ldcg(b + (size_t)j * stride), __ldcg(b + (size_t)j * stride + 1)});
+            out[i] = s.hi;
+            out[i + 1] = s.lo;
+        } else {
+            double s = 0.0;
+            int j = 0;
+            for (; j + 7 < cnt; j += 8) {   // eight loads in flight (one L2 round trip per iteration otherwise)
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(b + (size_t)(j + u) * stride);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += v[u];
+            }
+            for (; j < cnt; ++j) s += __ldcg(b + (size_t)j * stride);
+            out[i] = s;
+        }
+    }
+}
+
+// arrival at a counter: true for the CTA whose arrival makes it `expected` (which then also resets it).  Every thread of the
+// CTA calls this after its global writes; the winner may read what ALL earlier arrivals wrote.
+__device__ __forceinline__ bool tail_arrive(unsigned int* counter, unsigned int expected, int* s_flag) {
+    __threadfence();   // this thread's writes are visible device-wide before the CTA signs off
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(t.counter, 1ull) == t.target - 1;
+    if (threadIdx.x == 0) {
+        const bool last = atomicAdd(counter, 1u) == expected - 1;
+        if (last) *counter = 0u;   // self-cleaning: nobody else touches this counter any more in this launch
+        *s_flag = last;
+    }
     __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    const bool last = *s_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+// called by ALL threads of a CTA right after the record of `tile` has been written
+__device__ __forceinline__ void fused_tail_tile_done(const TailArgs& t, int tile) {
+    __shared__ int s_flag, s_timed_out;
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t count = (size_t)t.nboot * t.recsz;
     if (t.reduce) {
+        const int rl = tile / t.tpr, tr0 = rl * t.tpr, g = (tile - tr0) / TAIL_G;
+        const int g0 = tr0 + g * TAIL_G, g1 = min(g0 + TAIL_G, tr0 + t.tpr);                   // the group's tiles
+        const unsigned in_group = (unsigned)(min(g1, t.t_hi) - max(g0, t.t_lo));             // ... of which launched
+        if (!tail_arrive(t.counters + (size_t)rl * t.ngr + g, in_group, &s_flag)) return;
+        // tiles of the group outside [t_lo, t_hi) hold zero records (memset by the host): summed like the others
+        tail_sum_records(t.tile_rec + (size_t)g0 * t.recsz, g1 - g0, t.recsz, t.recsz, t.nstat, t.grec + ((size_t)rl * t.ngr + g) * t.recsz);
+        const int lo = max(tr0, t.t_lo), hi = min(tr0 + t.tpr, t.t_hi);                        // launched tiles of the replicate
+        const int gf = (lo - tr0) / TAIL_G, gl = (hi - 1 - tr0) / TAIL_G;                        // its groups with launched tiles
+        if (!tail_arrive(t.counters + (size_t)t.nrep * t.ngr + rl, (unsigned)(gl - gf + 1), &s_flag)) return;
+        tail_sum_records(t.grec + ((size_t)rl * t.ngr + gf) * t.recsz, gl - gf + 1, t.recsz, t.recsz, t.nstat,
+                         t.partials + (size_t)(t.rep_first + rl) * t.recsz);
+        if (!tail_arrive(t.counters + (size_t)t.nrep * t.ngr + t.nrep, (unsigned)t.nrep, &s_flag)) return;
+        // replicates this shard does not touch
         for (size_t idx = tid; idx < count; idx += nt) {
-            const int rep = (int)(idx / t.recsz), i = (int)(idx - (size_t)rep * t.recsz), e = i % t.nstat;
-            const bool is_dd = e < STAT_DD;
-            if (is_dd && (e & 1)) continue;
-            const int rl = rep - t.rep_first;
-            if (rl < 0 || rl >= t.nrep) {
-                t.partials[idx] = 0.0;
-                if (is_dd) t.partials[idx + 1] = 0.0;
-                continue;
-            }
-            const double* base = t.tile_rec + (size_t)rl * t.tpr * t.recsz + i;
-            if (is_dd) {
-                dd s{0.0, 0.0};
-                for (int j = 0; j < t.tpr; ++j) dd_add_dd(s, dd{__ldcg(base + (size_t)j * t.recsz), __ldcg(base + (size_t)j * t.recsz + 1)});
-                t.partials[idx] = s.hi;
-                t.partials[idx + 1] = s.lo;
-            } else {
-                double s = 0.0;
-                int j = 0;
-                for (; j + 7 < t.tpr; j += 8) {   // eight loads in flight (one L2 round trip per iteration otherwise)
-                    double v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = __ldcg(base + (size_t)(j + u) * t.recsz);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) s += v[u];
-                }
-                for (; j < t.tpr; ++j) s += __ldcg(base + (size_t)j * t.recsz);
-                t.partials[idx] = s;
-            }
+            const int rep = (int)(idx / t.recsz);
+            if (rep < t.rep_first || rep >= t.rep_first + t.nrep) t.partials[idx] = 0.0;
         }
-        __syncthreads();   // the sums are complete (and visible to the CTA) before they are pushed / copied
+        __threadfence_block();
+        __syncthreads();
+    } else {
+        if (!tail_arrive(t.counters + (size_t)t.nrep * t.ngr + t.nrep, (unsigned)(t.t_hi - t.t_lo), &s_flag)) return;
     }
     if (t.exchange) {
         peer_exchange_one_cta(t.peer, &s_timed_out);   // writes the world's sums to partials and host_out

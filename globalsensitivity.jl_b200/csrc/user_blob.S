@@ -1,10 +1,12 @@
-/* Embeds the relocatable cubin of the generic fused kernel with an unresolved model (user_kernel.cu.in, built by
- * build.py with nvcc -rdc=true -cubin) into libgsa_cuda.so; gsa_model_register_fatbin links it with nvJitLink. */
+/* Embeds the relocatable cubins of the fused kernels with an UNRESOLVED user model (user_kernel.cu.in and
+ * user_kernel_separable.cu.in, built by build.py with nvcc -rdc=true -cubin) into libgsa_cuda.so;
+ * gsa_model_register_fatbin / gsa_model_register_separable link them with nvJitLink.
+ * Assembled once per cubin: -DGSA_BLOB_SYM=<symbol> -DGSA_BLOB_END=<symbol>_end -DGSA_USER_CUBIN_PATH="..." */
     .section .rodata
-    .global gsa_user_kernel_blob
-    .global gsa_user_kernel_blob_end
+    .global GSA_BLOB_SYM
+    .global GSA_BLOB_END
     .balign 16
-gsa_user_kernel_blob:
+GSA_BLOB_SYM:
     .incbin GSA_USER_CUBIN_PATH
-gsa_user_kernel_blob_end:
+GSA_BLOB_END:
     .section .note.GNU-stack,"",@progbits

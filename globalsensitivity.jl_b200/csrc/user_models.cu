@@ -16,6 +16,10 @@
 
 extern "C" const unsigned char gsa_user_kernel_blob[];
 extern "C" const unsigned char gsa_user_kernel_blob_end[];
+extern "C" const unsigned char gsa_user_product_blob[];
+extern "C" const unsigned char gsa_user_product_blob_end[];
+extern "C" const unsigned char gsa_user_additive_blob[];
+extern "C" const unsigned char gsa_user_additive_blob_end[];
 
 namespace gsa {
 
@@ -88,17 +92,44 @@ std::string trampoline_ptx(const char* symbol) {
            "  call.uni " + s + ", (c0, c1, c2, c3, c4, c5);\n  }\n  ret;\n}\n";
 }
 
+// the same for a per-coordinate function  double <symbol>(int k, double x, const double* p, int np)
+std::string trampoline_ptx_separable(const char* symbol, const char* target) {
+    const std::string s(symbol), t(target);
+    return std::string(".version 8.8\n.target sm_100a\n.address_size 64\n") +
+           ".extern .func (.param .b64 r0) " + s + "(.param .b32 a0, .param .b64 a1, .param .b64 a2, .param .b32 a3);\n" +
+           ".visible .func (.param .b64 rr) " + t + "(.param .b32 b0, .param .b64 b1, .param .b64 b2, .param .b32 b3)\n{\n"
+           "  .reg .b64 %rd<4>;\n  .reg .b32 %r<2>;\n"
+           "  ld.param.u32 %r0, [b0];\n  ld.param.u64 %rd0, [b1];\n  ld.param.u64 %rd1, [b2];\n  ld.param.u32 %r1, [b3];\n"
+           "  {\n  .param .b32 c0;\n  .param .b64 c1;\n  .param .b64 c2;\n  .param .b32 c3;\n  .param .b64 cr;\n"
+           "  st.param.b32 [c0], %r0;\n  st.param.b64 [c1], %rd0;\n  st.param.b64 [c2], %rd1;\n  st.param.b32 [c3], %r1;\n"
+           "  call.uni (cr), " + s + ", (c0, c1, c2, c3);\n  ld.param.b64 %rd2, [cr];\n  }\n"
+           "  st.param.b64 [rr], %rd2;\n  ret;\n}\n";
+}
+
 JitLinkApi g_api;
 std::mutex g_api_mu;
 
+// linked cubins, keyed by (kind, symbol, image): a model registered on several devices (gsa_multi) or handles is linked once
+struct LinkedCubin {
+    int kind;
+    std::string symbol;
+    uint64_t hash;
+    size_t len;
+    std::vector<char> cubin;
+};
+std::vector<LinkedCubin> g_linked;
+std::mutex g_linked_mu;
+
+uint64_t fnv1a(const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+}
+
 }  // namespace
 
-int register_user_model(gsa_handle* h, const void* image, size_t len, const char* symbol, int nout, int* model_id) {
-    if (!image || len == 0 || !symbol || !*symbol || !model_id) return fail(GSA_ERR_INVALID, "image, symbol or model_id is NULL/empty");
-    if (nout < 1 || nout > 4) return fail(GSA_ERR_UNSUPPORTED, "user models support 1..4 outputs (got %d)", nout);
-    for (const char* c = symbol; *c; ++c)
-        if (!((*c >= 'a' && *c <= 'z') || (*c >= 'A' && *c <= 'Z') || (*c >= '0' && *c <= '9') || *c == '_' || *c == '$'))
-            return fail(GSA_ERR_INVALID, "symbol '%s' is not a plain C identifier (declare the model extern \"C\")", symbol);
+static int link_user_image(const void* image, size_t len, const char* symbol, int kind, std::vector<char>* cubin_out) {
     {
         std::lock_guard<std::mutex> lk(g_api_mu);
         int rc = load_api(g_api);
@@ -119,12 +150,15 @@ int register_user_model(gsa_handle* h, const void* image, size_t len, const char
         a.Destroy(&jl);
         return fail(GSA_ERR_INVALID, "%s failed (%d): %.380s", what, code, log.c_str());
     };
-    const size_t blob_len = (size_t)(gsa_user_kernel_blob_end - gsa_user_kernel_blob);
-    if ((e = a.AddData(jl, NVJL_INPUT_CUBIN, gsa_user_kernel_blob, blob_len, "gsa_user_kernel"))) return log_and_fail("nvJitLinkAddData(kernel)", e);
+    const unsigned char *blob = gsa_user_kernel_blob, *blob_end = gsa_user_kernel_blob_end;
+    const char* target = "gsa_user_model";
+    if (kind == GSA_USER_PRODUCT) { blob = gsa_user_product_blob; blob_end = gsa_user_product_blob_end; target = "gsa_user_factor"; }
+    if (kind == GSA_USER_ADDITIVE) { blob = gsa_user_additive_blob; blob_end = gsa_user_additive_blob_end; target = "gsa_user_term"; }
+    if ((e = a.AddData(jl, NVJL_INPUT_CUBIN, blob, (size_t)(blob_end - blob), "gsa_user_kernel"))) return log_and_fail("nvJitLinkAddData(kernel)", e);
     if ((e = a.AddData(jl, NVJL_INPUT_ANY, image, len, "user_model"))) return log_and_fail("nvJitLinkAddData(user image)", e);
     std::string ptx;
-    if (strcmp(symbol, "gsa_user_model") != 0) {
-        ptx = trampoline_ptx(symbol);
+    if (strcmp(symbol, target) != 0) {
+        ptx = kind == GSA_USER_GENERIC ? trampoline_ptx(symbol) : trampoline_ptx_separable(symbol, target);
         if ((e = a.AddData(jl, NVJL_INPUT_PTX, ptx.c_str(), ptx.size() + 1, "gsa_trampoline"))) return log_and_fail("nvJitLinkAddData(trampoline)", e);
     }
     if ((e = a.Complete(jl))) return log_and_fail("nvJitLinkComplete (is the model built with -rdc=true for sm_100a, with the expected signature?)", e);
@@ -139,21 +173,64 @@ int register_user_model(gsa_handle* h, const void* image, size_t len, const char
     }
     size_t cs = 0;
     if ((e = a.GetLinkedCubinSize(jl, &cs))) return log_and_fail("nvJitLinkGetLinkedCubinSize", e);
-    std::vector<char> cubin(cs);
-    if ((e = a.GetLinkedCubin(jl, cubin.data()))) return log_and_fail("nvJitLinkGetLinkedCubin", e);
+    cubin_out->resize(cs);
+    if ((e = a.GetLinkedCubin(jl, cubin_out->data()))) return log_and_fail("nvJitLinkGetLinkedCubin", e);
     a.Destroy(&jl);
+    return GSA_OK;
+}
 
-    UserModelEntry um;
-    um.nout = nout;
-    GSA_CUDA(cudaLibraryLoadData(&um.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-    cudaError_t ce = cudaLibraryGetKernel(&um.k_first, um.lib, "gsa_user_fused_first");
-    if (ce == cudaSuccess) ce = cudaLibraryGetKernel(&um.k_second, um.lib, "gsa_user_fused_second");
-    if (ce != cudaSuccess) {
-        cudaLibraryUnload(um.lib);
-        return cuda_fail(ce, "cudaLibraryGetKernel");
+int register_user_model(gsa_handle* h, const void* image, size_t len, const char* symbol, int kind, int nout, int* model_id) {
+    if (!image || len == 0 || !symbol || !*symbol || !model_id) return fail(GSA_ERR_INVALID, "image, symbol or model_id is NULL/empty");
+    if (kind != GSA_USER_GENERIC && kind != GSA_USER_PRODUCT && kind != GSA_USER_ADDITIVE) return fail(GSA_ERR_INVALID, "unknown user model kind %d", kind);
+    if (nout < 1 || nout > 4) return fail(GSA_ERR_UNSUPPORTED, "user models support 1..4 outputs (got %d)", nout);
+    if (kind != GSA_USER_GENERIC && nout != 1) return fail(GSA_ERR_INVALID, "separable user models have one output (got %d)", nout);
+    for (const char* c = symbol; *c; ++c)
+        if (!((*c >= 'a' && *c <= 'z') || (*c >= 'A' && *c <= 'Z') || (*c >= '0' && *c <= '9') || *c == '_' || *c == '$'))
+            return fail(GSA_ERR_INVALID, "symbol '%s' is not a plain C identifier (declare the model extern \"C\")", symbol);
+    // link once per (kind, symbol, image); every handle / device loads the cached cubin
+    const uint64_t hash = fnv1a(image, len);
+    const std::vector<char>* cubin = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_linked_mu);
+        for (const LinkedCubin& c : g_linked)
+            if (c.kind == kind && c.hash == hash && c.len == len && c.symbol == symbol) cubin = &c.cubin;
+        if (!cubin) {
+            LinkedCubin c;
+            c.kind = kind; c.symbol = symbol; c.hash = hash; c.len = len;
+            int rc = link_user_image(image, len, symbol, kind, &c.cubin);
+            if (rc) return rc;
+            g_linked.push_back(std::move(c));
+            cubin = &g_linked.back().cubin;
+        }
+        UserModelEntry um;
+        um.nout = nout;
+        um.kind = kind;
+        GSA_CUDA(cudaLibraryLoadData(&um.lib, cubin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+        cudaError_t ce = cudaSuccess;
+        static const char* const names[2][2] = {{"gsa_user_fused_first_s", "gsa_user_fused_first_l"}, {"gsa_user_fused_second_s", "gsa_user_fused_second_l"}};
+        for (int s2 = 0; s2 < 2 && ce == cudaSuccess; ++s2)
+            for (int lg = 0; lg < 2 && ce == cudaSuccess; ++lg) ce = cudaLibraryGetKernel(&um.k_generic[s2][lg], um.lib, names[s2][lg]);
+        if (ce != cudaSuccess) {
+            cudaLibraryUnload(um.lib);
+            return cuda_fail(ce, "cudaLibraryGetKernel");
+        }
+        h->user_models.push_back(um);
     }
-    h->user_models.push_back(um);
     *model_id = GSA_MODEL_USER_BASE + (int)h->user_models.size() - 1;
+    return GSA_OK;
+}
+
+// the O(d) kernel of a separable user model for (lanes per sample, coordinates per lane, Jansen | other one-term estimators)
+int user_separable_kernel(gsa_handle* h, int model_id, int T, int cpl, bool jansen, const void** kernel) {
+    const int idx = model_id - GSA_MODEL_USER_BASE;
+    if (idx < 0 || idx >= (int)h->user_models.size()) return fail(GSA_ERR_INVALID, "unknown user model id %d for this handle", model_id);
+    UserModelEntry& um = h->user_models[idx];
+    if (um.kind == GSA_USER_GENERIC) return fail(GSA_ERR_INVALID, "user model %d is not separable", model_id);
+    char name[64];
+    snprintf(name, sizeof(name), "gsa_user_sep_T%d_C%d_J%d", T, cpl, jansen ? 1 : 0);
+    cudaKernel_t k = nullptr;
+    GSA_CUDA(cudaLibraryGetKernel(&k, um.lib, name));
+    *kernel = (const void*)k;
     return GSA_OK;
 }
 

@@ -69,14 +69,20 @@ class DeviceModel:
         check(lib().gsa_model_lookup(self.name.encode(), C.byref(mid)))
         self.model_id = mid.value
 
+    USER_KINDS = {"generic": 0, "product": 1, "additive": 2}
+
     @classmethod
-    def from_fatbin(cls, image, symbol: str, nout: int = 1, params=(), handle: "Optional[GsaHandle]" = None) -> "DeviceModel":
-        """A user-supplied model: `image` (bytes or a path) is a fatbin / cubin / PTX / LTO-IR built with
+    def from_fatbin(cls, image, symbol: str, nout: int = 1, params=(), handle: "Optional[GsaHandle]" = None,
+                    kind: str = "generic") -> "DeviceModel":
+        """A user-supplied model: `image` (bytes or a path) is a fatbin / cubin / PTX built with
         `nvcc -rdc=true -gencode arch=compute_100a,code=sm_100a` that defines
 
-            extern "C" __device__ void <symbol>(const double* x, int d, const double* p, int np, double* y, int nout);
+            kind="generic"   extern "C" __device__ void   <symbol>(const double* x, int d, const double* p, int np, double* y, int nout);
+            kind="product"   extern "C" __device__ double <symbol>(int k, double x_k, const double* p, int np);   f(x) = prod_k of it
+            kind="additive"  extern "C" __device__ double <symbol>(int k, double x_k, const double* p, int np);   f(x) = sum_k of it
 
-        It is linked into the generic fused kernel with nvJitLink (gsa_model_register_fatbin)."""
+        It is linked into the fused kernels with nvJitLink (gsa_model_register_fatbin / gsa_model_register_separable).  Separable
+        kinds run first/total order on the O(d)-per-sample product kernel instead of the O(d^2) generic one."""
         if isinstance(image, (str, bytes)) and not isinstance(image, bytes):
             with open(image, "rb") as f:
                 image = f.read()
@@ -84,7 +90,10 @@ class DeviceModel:
         m = cls("user:" + symbol, params)
         mid = C.c_int()
         buf = C.create_string_buffer(bytes(image), len(image))
-        check(lib().gsa_model_register_fatbin(h.ptr, buf, len(image), symbol.encode(), int(nout), C.byref(mid)))
+        if kind == "generic":
+            check(lib().gsa_model_register_fatbin(h.ptr, buf, len(image), symbol.encode(), int(nout), C.byref(mid)))
+        else:
+            check(lib().gsa_model_register_separable(h.ptr, buf, len(image), symbol.encode(), cls.USER_KINDS[kind], C.byref(mid)))
         m.model_id, m.handle = mid.value, h
         return m
 
@@ -251,16 +260,19 @@ class GsaMulti:
         except Exception:
             pass
 
-    def model_from_fatbin(self, image, symbol: str, nout: int = 1, params=()) -> "DeviceModel":
-        """A user `__device__` model linked on every device of this object (gsa_multi_model_register_fatbin); see
-        DeviceModel.from_fatbin for the image format."""
+    def model_from_fatbin(self, image, symbol: str, nout: int = 1, params=(), kind: str = "generic") -> "DeviceModel":
+        """A user `__device__` model linked once and loaded on every device of this object (gsa_multi_model_register_*); see
+        DeviceModel.from_fatbin for the image format and the kinds."""
         if isinstance(image, str):
             with open(image, "rb") as f:
                 image = f.read()
         m = DeviceModel("user:" + symbol, params)
         mid = C.c_int()
         buf = C.create_string_buffer(bytes(image), len(image))
-        check(lib().gsa_multi_model_register_fatbin(self._m, buf, len(image), symbol.encode(), int(nout), C.byref(mid)))
+        if kind == "generic":
+            check(lib().gsa_multi_model_register_fatbin(self._m, buf, len(image), symbol.encode(), int(nout), C.byref(mid)))
+        else:
+            check(lib().gsa_multi_model_register_separable(self._m, buf, len(image), symbol.encode(), DeviceModel.USER_KINDS[kind], C.byref(mid)))
         h = C.c_void_p()
         check(lib().gsa_multi_handle(self._m, 0, C.byref(h)))
         m.model_id, m.handle = mid.value, _BorrowedHandle(h)

@@ -109,6 +109,19 @@ GSA_API int gsa_model_nout(gsa_handle* h, int model_id, int nparams, int d, int*
 GSA_API int gsa_model_register_fatbin(gsa_handle* h, const void* image, size_t len, const char* symbol, int nout,
                               int* model_id);
 
+/* Structured user models (SURVEY 7 "separable-model registry hook").  The reference's `f` is arbitrary (:143), so the generic
+ * kernel evaluates it d+2 (2d+2) times per sample at O(d) each.  A model that is a PRODUCT or a SUM of per-coordinate functions
+ * can say so and gets the O(d)-per-sample kernel that makes BASELINE config 5 HBM-bound:
+ *     GSA_USER_PRODUCT    f(x) = prod_k g(k, x_k)     extern "C" __device__ double <symbol>(int k, double x, const double* p, int np);
+ *     GSA_USER_ADDITIVE   f(x) = sum_k  g(k, x_k)     same signature
+ *     GSA_USER_GENERIC    the full-vector form of gsa_model_register_fatbin
+ * (default symbols: gsa_user_factor / gsa_user_term / gsa_user_model; other names go through a PTX trampoline).  One output.
+ * First/total order with Jansen1999, Sobol2007 or Homma1996 run on the separable kernel; second order and Janon2014 run on the
+ * generic kernel, which evaluates the whole model through the same per-coordinate function.  Linked cubins are cached per
+ * (kind, symbol, image): registering the same image on several handles / devices links once. */
+enum { GSA_USER_GENERIC = 0, GSA_USER_PRODUCT = 1, GSA_USER_ADDITIVE = 2 };
+GSA_API int gsa_model_register_separable(gsa_handle* h, const void* image, size_t len, const char* symbol, int kind, int* model_id);
+
 /* ---- K1: unrandomised Sobol A/B design --------------------------------------------------------- */
 /* Replaces QuasiMonteCarlo.generate_design_matrices(n, lb, ub, SobolSample(), num_mats) (reference
  * call sites src/sobol_sensitivity.jl:408-413, README.md:55-56, test/sobol_method.jl:29-30): one
@@ -220,6 +233,7 @@ GSA_API int gsa_multi_handle(gsa_multi* m, int i, gsa_handle** out);
 /* gsa_model_register_fatbin on every device of `m`: the same image is linked once per device and gets the same id on all */
 GSA_API int gsa_multi_model_register_fatbin(gsa_multi* m, const void* image, size_t len, const char* symbol, int nout,
                                     int* model_id);
+GSA_API int gsa_multi_model_register_separable(gsa_multi* m, const void* image, size_t len, const char* symbol, int kind, int* model_id);
 /* gsa(model, Sobol(...), A, B; batch=true) (:110-149 + :169-405) with the HOST design sharded by contiguous column ranges
  * over the devices: every device streams and reduces its shard, ONE kernel on the first device gathers and adds the
  * nboot*nout*nstat partial sums of all devices over NVLink peer memory (error-free for the double-double entries) and

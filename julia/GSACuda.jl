@@ -217,6 +217,43 @@ function DeviceModel(image::Vector{UInt8}, symbol::AbstractString, params = Floa
     end
     return DeviceModel(id[], vec(Float64.(params)), Int(nout))
 end
+# Separable user models: kind = :product (f(x) = prod_k g(k, x_k)) or :additive (f(x) = sum_k g(k, x_k)), with
+#      extern "C" __device__ double <symbol>(int k, double x_k, const double* p, int np)
+# run first/total order on the O(d)-per-sample kernel (gsa_model_register_separable).
+const USER_KIND = Dict(:generic => 0, :product => 1, :additive => 2)
+function SeparableModel(image::Vector{UInt8}, symbol::AbstractString, kind::Symbol, params = Float64[]; handle::Handle = default_handle())
+    id = Ref{Cint}(0)
+    GC.@preserve image begin
+        check(ccall((:gsa_model_register_separable, libgsa), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Csize_t, Cstring, Cint, Ref{Cint}),
+                    handle.ptr, image, length(image), symbol, USER_KIND[kind], id))
+    end
+    return DeviceModel(id[], vec(Float64.(params)), 1)
+end
+function SeparableModel(m::Multi, image::Vector{UInt8}, symbol::AbstractString, kind::Symbol, params = Float64[])
+    id = Ref{Cint}(0)
+    GC.@preserve image begin
+        check(ccall((:gsa_multi_model_register_separable, libgsa), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Csize_t, Cstring, Cint, Ref{Cint}),
+                    m.ptr, image, length(image), symbol, USER_KIND[kind], id))
+    end
+    return DeviceModel(id[], vec(Float64.(params)), 1)
+end
+
+# ---- the sharded form, one process per GPU (Distributed.jl / MPI.jl workers): ONE call per rank and step -----------------
+# (the ranks exchange the 64-byte mailbox handles of gsa_peer_export once, e.g. with MPI.Allgather, then gsa_peer_connect)
+function gsa_sharded(model::DeviceModel, method::Sobol, A_local::Matrix{Float64}, B_local::Matrix{Float64}, N::Integer, col0::Integer;
+                     Ei_estimator = :Jansen1999, handle::Handle = default_handle())
+    d, ncols = size(A_local); second = 2 in method.order
+    opts = Ref(GsaSobolOpts(second, method.nboot, method.conf_level, EI[Ei_estimator], 0))
+    res, finish, keep = alloc(nout(model, d), d, method.nboot, second)
+    GC.@preserve A_local B_local keep model begin
+        check(ccall((:gsa_sobol_run_sharded, libgsa), Cint,
+                    (Ptr{Cvoid}, Ref{GsaSobolOpts}, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Int64, Int64, Int64,
+                     Ref{GsaSobolResult}),
+                    handle.ptr, opts, model.id, model.params, length(model.params), A_local, B_local, d, N, col0, ncols, Ref(res)))
+    end
+    return finish()
+end
+
 function DeviceModel(m::Multi, image::Vector{UInt8}, symbol::AbstractString, params = Float64[]; nout::Integer = 1)
     id = Ref{Cint}(0)
     GC.@preserve image begin
