@@ -27,6 +27,7 @@ struct FusedPlan {
     const void* kernel = nullptr;
 
     int prod_T = 0, prod_CPL = 0;
+    const void* kernel_v2 = nullptr;   // pair-load variant of the product kernel (even d, 16-byte aligned rows; chosen at launch)
     bool user_sep = false;       // product kernel linked against a user's per-coordinate function (gsa_model_register_separable)
     bool gen = false;            // the design is generated inside the kernel (gsa_sobol_*_generated)
     uint64_t gen_first = 0;
@@ -172,6 +173,15 @@ static int plan_product(gsa_handle* h, FusedPlan* p) {
         p->kernel = (const void*)product_kernel_for(p->prod_T, p->prod_CPL, p->gen, p->est == GSA_EI_JANSEN1999);
         if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
         GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));
+        // pair loads: T = 8, 14 slots per lane covers 96 < d <= 112 (config 5: d = 100)   [GSA_PRODUCT_VEC2=0 turns it off]
+        const char* ev = getenv("GSA_PRODUCT_VEC2");
+        if (!p->gen && p->d % 2 == 0 && p->d > 96 && p->d <= 112 && p->est == GSA_EI_JANSEN1999 && !(ev && atoi(ev) == 0)) {
+            p->kernel_v2 = (const void*)fused_product_kernel_v2<8, 14, true>;
+            int nb2 = 0;
+            const size_t smem2 = sizeof(double) * (2 * 112 + (PROD_THREADS / 32) * (2 * 112 + 8));
+            GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, p->kernel_v2, p->threads, smem2));
+            if (nb2 < nb) p->kernel_v2 = nullptr;   // (must not cost residency)
+        }
     }
     p->resident = std::max(1, nb) * h->sm_count;
     p->ts_min = p->ts_gran = PROD_THREADS / p->prod_T;
@@ -367,7 +377,11 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         a.V = h->vtab.as<uint32_t>(); a.box = h->lbub.as<double2>(); a.first = gen_first; a.nboot = gen_nboot; a.unit_box = gen_unit_box;
         a.tail = tail;
         void* kargs[] = {&a};
-        GSA_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, h->stream));   // (also takes the cudaKernel_t of a linked user kernel)
+        const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
+        if (kernel_v2 && aligned)
+            GSA_CUDA(cudaLaunchKernel(kernel_v2, dim3(grid), dim3(threads), kargs, sizeof(double) * (2 * 112 + (PROD_THREADS / 32) * (2 * 112 + 8)), h->stream));
+        else
+            GSA_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, h->stream));   // (also takes the cudaKernel_t of a linked user kernel)
     }
     GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
     h->kernel_timed = true;

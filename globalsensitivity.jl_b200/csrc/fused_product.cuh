@@ -82,8 +82,13 @@ constexpr size_t product_smem_doubles() {
 // instantiation keeps its code unchanged; Janon2014 needs three terms per coordinate and stays on the generic kernel).
 // F: the per-coordinate function (SobolGFactor, UserFactor, UserTerm).  ADD = true: the model is the SUM of its terms instead of
 // the product of its factors -- f(AB_k) = yA + (g_k(B_k) - g_k(A_k)) -- same mapping, same accumulators, no prefix/suffix sweeps.
-template <int T, int CPL, bool GEN, bool JANSEN, class F, bool ADD>
+// VW = 2 (even d, 16-byte aligned rows, not GEN): a lane owns PAIRS of adjacent coordinates, k = 2t + 2T*(i/2) + (i & 1), and reads
+// each pair with one 16-byte load -- half the load instructions and half the L1 wavefronts of the 8-byte mapping (the T lanes of
+// a group then cover one full 128-byte line per request).
+template <int T, int CPL, bool GEN, bool JANSEN, class F, bool ADD, int VW = 1>
 __device__ __forceinline__ void fused_product_body(const ProductArgs& a) {
+    static_assert(VW == 1 || (VW == 2 && CPL % 2 == 0 && !GEN), "pair loads need an even number of slots per lane");
+    auto kc = [](int t, int i) { return VW == 1 ? t + T * i : 2 * t + 2 * T * (i >> 1) + (i & 1); };   // coordinate of slot i of lane t
     const bool sobol2007 = a.est == GSA_EI_SOBOL2007;   // (only read when !JANSEN)
     constexpr int NW = PROD_THREADS / 32;
     constexpr int NG = PROD_THREADS / T;  // sample groups per CTA
@@ -172,20 +177,33 @@ __device__ __forceinline__ void fused_product_body(const ProductArgs& a) {
 #pragma unroll
                 for (int i = 0; i < CPL; ++i) { xa[i] ^= row[T * i]; xb[i] ^= row[SLOTS + T * i]; }
             } else {
-                const double* as = a.A + (size_t)(s - a.g.buf_col0) * d + t;
-                const double* bs = a.B + (size_t)(s - a.g.buf_col0) * d + t;
+                if constexpr (VW == 2) {
+                    const double* as = a.A + (size_t)(s - a.g.buf_col0) * d;
+                    const double* bs = a.B + (size_t)(s - a.g.buf_col0) * d;
 #pragma unroll
-                for (int i = 0; i < CPL; ++i) {
-                    // padded coordinates (k >= d) re-read coordinate 0 of the row and get coef (0, 1), i.e. g = 1
-                    const int off = (t + T * i) < d ? T * i : -t;
-                    gA[i] = ldg_stream(as + off);
-                    gB[i] = ldg_stream(bs + off);
+                    for (int i = 0; i < CPL; i += 2) {
+                        // padded pairs (k >= d; d is even) re-read coordinates 0, 1 of the row and get coef (0, 1), i.e. g = 1
+                        const int k = kc(t, i), off = k < d ? k : 0;
+                        const double2 va = ldg_stream2(as + off), vb = ldg_stream2(bs + off);
+                        gA[i] = va.x; gA[i + 1] = va.y;
+                        gB[i] = vb.x; gB[i + 1] = vb.y;
+                    }
+                } else {
+                    const double* as = a.A + (size_t)(s - a.g.buf_col0) * d + t;
+                    const double* bs = a.B + (size_t)(s - a.g.buf_col0) * d + t;
+#pragma unroll
+                    for (int i = 0; i < CPL; ++i) {
+                        // padded coordinates (k >= d) re-read coordinate 0 of the row and get coef (0, 1), i.e. g = 1
+                        const int off = (t + T * i) < d ? T * i : -t;
+                        gA[i] = ldg_stream(as + off);
+                        gB[i] = ldg_stream(bs + off);
+                    }
                 }
             }
             double LA = ADD ? 0.0 : 1.0, LB = ADD ? 0.0 : 1.0;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
-                const int k = t + T * i;
+                const int k = kc(t, i);
                 if constexpr (F::kUser) {   // padded coordinates (k >= d) contribute the neutral element
                     gA[i] = k < d ? F::eval(k, gA[i], scoef, a.params, a.np) : (ADD ? 0.0 : 1.0);
                     gB[i] = k < d ? F::eval(k, gB[i], scoef, a.params, a.np) : (ADD ? 0.0 : 1.0);
@@ -283,8 +301,8 @@ __device__ __forceinline__ void fused_product_body(const ProductArgs& a) {
         if (lane < T) {
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
-                wr[t + T * i] = V[i];
-                wr[SLOTS + t + T * i] = E[i];
+                wr[kc(t, i)] = V[i];
+                wr[SLOTS + kc(t, i)] = E[i];
             }
         }
         if (lane == 0) {
@@ -322,6 +340,11 @@ __device__ __forceinline__ void fused_product_body(const ProductArgs& a) {
 template <int T, int CPL, bool GEN, bool JANSEN = true>
 __global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fused_product_kernel(ProductArgs a) {
     fused_product_body<T, CPL, GEN, JANSEN, SobolGFactor, false>(a);
+}
+// pair-load variant (even d, aligned rows)
+template <int T, int CPL, bool JANSEN = true>
+__global__ void __launch_bounds__(PROD_THREADS, 3) fused_product_kernel_v2(ProductArgs a) {
+    fused_product_body<T, CPL, false, JANSEN, SobolGFactor, false, 2>(a);
 }
 
 }  // namespace gsa

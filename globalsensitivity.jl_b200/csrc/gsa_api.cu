@@ -228,6 +228,38 @@ struct GenSpec {
     int64_t samples;
 };
 
+// K1 launch: `nm` matrices (<= 8) of d x ncols starting at sequence index `first`; matrix m takes the dimensions
+// [voff[m], voff[m] + d) of the table.  scale/lb: device vectors [d] (ub - lb, lb).
+static int launch_design(gsa_handle* h, const double* scale, const double* lb, double* const* out, const int* voff, int nm, int d,
+                         uint64_t first, int64_t ncols) {
+    if (ncols <= 0) return GSA_OK;
+    DesignArgs a;
+    a.V = h->vtab.as<uint32_t>();
+    a.scale = scale;
+    a.lb = lb;
+    for (int m = 0; m < 8; ++m) { a.out[m] = m < nm ? out[m] : nullptr; a.voff[m] = m < nm ? voff[m] : 0; }
+    a.first = first;
+    a.ncols = ncols;
+    a.d = d;
+    a.dT = d * nm;
+    // two dimensions per thread (16-byte stores) when d is even and the outputs are 16-byte aligned
+    bool vec2 = d % 2 == 0 && !getenv("GSA_DESIGN_SCALAR");
+    for (int m = 0; m < nm; ++m) vec2 = vec2 && (reinterpret_cast<uintptr_t>(a.out[m]) % 16 == 0);
+    const int64_t units = vec2 ? a.dT / 2 : a.dT;     // work items per point
+    const int tpb = vec2 ? DESIGN_THREADS2 : DESIGN_THREADS;
+    // P*units threads ~ 2 full waves of 2048 threads per SM
+    const int64_t want = (int64_t)h->sm_count * 2048 * 2;
+    int lp = 0;
+    while (((int64_t)1 << lp) * units < want && ((int64_t)1 << lp) < ncols) ++lp;
+    a.lp = lp;
+    const int64_t threads = ((int64_t)1 << lp) * units;
+    if (vec2) sobol_design_kernel2<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, h->stream>>>(a);
+    else sobol_design_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, h->stream>>>(a);
+    h->last_launches++;
+    GSA_CUDA(cudaGetLastError());
+    return GSA_OK;
+}
+
 static int ensure_directions(gsa_handle* h, int dT) {
     if (h->vdims >= dT) return GSA_OK;
     h->vhost.resize((size_t)dT * 32);
@@ -312,7 +344,17 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
     const int64_t n = N / o->nboot;
 
     FusedPlan plan;
-    if ((rc = plan_fused(h, model, d, nout, np, second, est, &plan, gen != nullptr))) return rc;
+    // Generated design (gsa(f, ::Sobol, p_range; samples)): product-form models have a kernel that generates its points in registers;
+    // every other model / order / estimator takes its regular kernel on column CHUNKS that K1 writes into a scratch buffer just
+    // ahead of it (32 MB per matrix: the chunk is consumed out of L2) -- A and B are never materialised as a whole either way.
+    bool gen_chunked = false;
+    rc = plan_fused(h, model, d, nout, np, second, est, &plan, gen != nullptr);
+    if (rc == GSA_ERR_UNSUPPORTED && gen) {
+        plan = FusedPlan();
+        rc = plan_fused(h, model, d, nout, np, second, est, &plan, false);
+        gen_chunked = true;
+    }
+    if (rc) return rc;
     if (!gen && (plan.kind == PLAN_SMALL_ISHIGAMI || plan.kind == PLAN_SMALL_SOBOLG) && d % 2 == 0 && o->input_location == GSA_LOC_DEVICE &&
         ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15)) {
         // the register kernels read even-d rows with 16-byte vector loads; a device view that starts at an odd element takes
@@ -329,8 +371,9 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         std::vector<double> box(2 * (size_t)d);
         plan.gen_unit_box = 1;
         for (int i = 0; i < d; ++i) {
-            box[2 * i] = gen->ub[i] - gen->lb[i];
-            box[2 * i + 1] = gen->lb[i];
+            // (ub - lb, lb): interleaved pairs for the generating kernel, two vectors for K1 (chunked path)
+            box[gen_chunked ? i : 2 * i] = gen->ub[i] - gen->lb[i];
+            box[gen_chunked ? d + i : 2 * i + 1] = gen->lb[i];
             if (gen->lb[i] != 0.0 || gen->ub[i] != 1.0) plan.gen_unit_box = 0;
         }
         GSA_CUDA(cudaMemcpyAsync(h->lbub.p, box.data(), sizeof(double) * box.size(), cudaMemcpyHostToDevice, h->stream));
@@ -340,6 +383,7 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         plan.gen_first = first;
         plan.gen_nboot = o->nboot;
     }
+    const uint64_t gen_first = plan.gen_first;
 
     h->last_launches = 0;
     h->kernel_timed = false;
@@ -362,13 +406,14 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         const int nrep = rep_last - g.rep_first + 1;
         const size_t col_bytes = sizeof(double) * (size_t)d;
         bool devp = false;
-        const bool host_in = !gen && o->input_location != GSA_LOC_DEVICE;
-        const bool pinned = host_in && is_device_or_pinned(A, &devp) && is_device_or_pinned(B, &devp);
+        const bool from_host = !gen && o->input_location != GSA_LOC_DEVICE;
+        const bool host_in = from_host || gen_chunked;   // the design reaches the kernels chunk by chunk through a scratch buffer
+        const bool pinned = from_host && is_device_or_pinned(A, &devp) && is_device_or_pinned(B, &devp);
         // Host designs are streamed in column chunks (256 MB per matrix from pinned memory, 64 MB through the staging
         // buffers otherwise).  The kernel of a chunk only sees that chunk's tiles, so the tiles must be small enough that one
         // chunk holds at least a full wave of them -- with shard-sized tiles each chunk kernel ran on ONE CTA and the whole
         // pipeline sat at 25 GB/s instead of the 55 GB/s PCIe delivers (profiles/r1_notes.md).
-        const int64_t chunk_cols_target = std::max<int64_t>(plan.ts_min, (int64_t)(((pinned ? 256u : 64u) << 20) / col_bytes));
+        const int64_t chunk_cols_target = std::max<int64_t>(plan.ts_min, (int64_t)(((gen_chunked ? 32u : pinned ? 256u : 64u) << 20) / col_bytes));
         if (host_in) {
             int64_t ts = (chunk_cols_target + plan.resident - 1) / plan.resident;
             ts = (ts + plan.ts_gran - 1) / plan.ts_gran * plan.ts_gran;
@@ -465,9 +510,9 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
             // overlaps the kernel of chunk i.  Chunk boundaries are tile boundaries.
             int tiles_per_chunk = (int)std::max<int64_t>(1, chunk_cols_target / g.ts);
             const size_t buf_bytes = 2 * col_bytes * (size_t)tiles_per_chunk * g.ts;
-            for (int b = 0; b < 2; ++b)
+            for (int b = 0; b < (gen_chunked ? 1 : 2); ++b)
                 if ((rc = h->dev_in[b].reserve(buf_bytes))) return rc;
-            if (!pinned && h->pinned_cap < buf_bytes) {
+            if (from_host && !pinned && h->pinned_cap < buf_bytes) {
                 for (int b = 0; b < 2; ++b) {
                     if (h->pinned[b]) cudaFreeHost(h->pinned[b]);
                     h->pinned[b] = nullptr;
@@ -493,8 +538,23 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
                 }
                 const size_t bytes = col_bytes * (size_t)(c1 - c0);
                 if (getenv("GSA_DEBUG")) fprintf(stderr, "[gsa] chunk %d tiles [%d,%d) cols [%lld,%lld) bytes %zu buf %zu pinned %d ts %d tpr %d\n", ci, t0, t1, (long long)c0, (long long)c1, bytes, buf_bytes, (int)pinned, g.ts, g.tpr);
-                double* dA = h->dev_in[b].as<double>();
+                double* dA = h->dev_in[gen_chunked ? 0 : b].as<double>();
                 double* dB = dA + (size_t)d * (size_t)tiles_per_chunk * g.ts;
+                if (gen_chunked) {
+                    // K1 writes the chunk (same stream: the previous chunk's kernel has finished with the buffer): column c is
+                    // sample c mod samples of replicate c / samples, A from dimension block r, B from block nboot + r (:414-415)
+                    for (int64_t r = c0 / n; r * n < c1; ++r) {
+                        const int64_t s0 = std::max<int64_t>(c0, r * n), s1 = std::min<int64_t>(c1, (r + 1) * n);
+                        double* outs[2] = {dA + (size_t)d * (size_t)(s0 - c0), dB + (size_t)d * (size_t)(s0 - c0)};
+                        const int voff[2] = {(int)r * d, (o->nboot + (int)r) * d};
+                        if ((rc = launch_design(h, h->lbub.as<double>(), h->lbub.as<double>() + d, outs, voff, 2, d,
+                                                gen_first + (uint64_t)(s0 - r * n), s1 - s0))) return rc;
+                    }
+                    TileGeom gc = g;
+                    gc.buf_col0 = c0;
+                    if ((rc = plan.launch(h, dA, dB, gc, t0, t1))) return rc;
+                    continue;
+                }
                 const double* hA = A + (size_t)d * (size_t)(c0 - col0);
                 const double* hB = B + (size_t)d * (size_t)(c0 - col0);
                 // buffer b free again?  Also on the first two chunks: the previous (asynchronous) call on this handle may still be
@@ -535,26 +595,15 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
     return GSA_OK;
 }
 
-static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double* Y, int nout, int d, int64_t n, double* partials) {
-    int rc = check_opts(o);
-    if (rc) return rc;
-    if (d < 1 || nout < 1 || n < 0) return fail(GSA_ERR_INVALID, "bad shape: nout=%d d=%d n=%lld", nout, d, (long long)n);
-    if (!partials || (!Y && n > 0)) return fail(GSA_ERR_INVALID, "Y or partials is NULL");
+// the estimator kernels on a DEVICE all_y of `nboot` replicates of n samples each (block order [A | B | AB_1.. | BA_1..] per
+// replicate); the per-replicate sums are ADDED to partials[rep_first .. rep_first + nboot)
+static int y_kernels(gsa_handle* h, const gsa_sobol_opts* o, const double* Yd, int nout, int d, int64_t n, int nboot, int rep_first,
+                     double* partials) {
+    int rc;
     const bool second = o->second_order != 0;
     const int est = o->ei_estimator, step = second ? 2 * d + 2 : d + 2;
     const int nstat = stat_count(d, est, second), recsz = nstat * nout;
-    h->last_launches = 0;
-    h->kernel_timed = false;
-    const double* Yd = Y;
-    const size_t ybytes = sizeof(double) * (size_t)nout * (size_t)n * step * o->nboot;
-    if (o->input_location == GSA_LOC_HOST && ybytes) {
-        if ((rc = h->ybuf.reserve(ybytes))) return rc;
-        GSA_CUDA(cudaMemcpyAsync(h->ybuf.p, Y, ybytes, cudaMemcpyHostToDevice, h->stream));
-        Yd = h->ybuf.as<double>();
-    }
-    GSA_CUDA(cudaEventRecord(h->ev0, h->stream));
-    GSA_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (size_t)o->nboot * recsz, h->stream));
-    if (n > 0) {
+    if (n <= 0 || nboot <= 0) return GSA_OK;
         const char* force = getenv("GSA_FORCE_GENERIC");
         // register kernel: d <= 8 with second order; first order d <= 24 (Jansen: 6.4-6.5 TB/s; at d = 32 it spills and drops to 4.0 TB/s)
         // or 16 (the three-term estimators need 4d accumulators)
@@ -573,9 +622,9 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
             const int resident = h->sm_count * std::max(1, nb);
             PairsArgs a{};
             a.Y = Yd; a.n = n; a.nout = nout; a.d = d; a.nstat = nstat; a.est = est;
-            a.g.n = n; a.g.col_lo = 0; a.g.col_hi = (int64_t)o->nboot * n; a.g.buf_col0 = 0; a.g.rep_first = 0;
-            choose_tiles(n, o->nboot, std::max(1, resident / nout), 1, PM_CH * PMMA_NW, 1 << 30, PM_CH * PMMA_NW, &a.g.ts, &a.g.tpr);
-            a.g.ntiles = a.g.tpr * o->nboot;
+            a.g.n = n; a.g.col_lo = 0; a.g.col_hi = (int64_t)nboot * n; a.g.buf_col0 = 0; a.g.rep_first = 0;
+            choose_tiles(n, nboot, std::max(1, resident / nout), 1, PM_CH * PMMA_NW, 1 << 30, PM_CH * PMMA_NW, &a.g.ts, &a.g.tpr);
+            a.g.ntiles = a.g.tpr * nboot;
             tpr = a.g.tpr;
             if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)a.g.ntiles * recsz))) return rc;
             a.tile_rec = h->tile_rec.as<double>();
@@ -591,11 +640,11 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
         } else if (small) {
             // thread-per-sample register kernel: every Y value is read exactly once, straight into registers
             TileGeom g;
-            g.n = n; g.col_lo = 0; g.col_hi = (int64_t)o->nboot * n; g.buf_col0 = 0; g.rep_first = 0;
+            g.n = n; g.col_lo = 0; g.col_hi = (int64_t)nboot * n; g.buf_col0 = 0; g.rep_first = 0;
             int occ = 1;
             if ((rc = launch_small_y(h, d, second, est, Yd, n, nout, step, g, nstat, nullptr, &occ))) return rc;
-            choose_tiles(n, o->nboot, std::max(1, h->sm_count * occ / nout), 1, SMALL_THREADS, 1 << 30, SMALL_THREADS, &g.ts, &g.tpr);
-            g.ntiles = g.tpr * o->nboot;
+            choose_tiles(n, nboot, std::max(1, h->sm_count * occ / nout), 1, SMALL_THREADS, 1 << 30, SMALL_THREADS, &g.ts, &g.tpr);
+            g.ntiles = g.tpr * nboot;
             tpr = g.tpr;
             if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)g.ntiles * recsz))) return rc;
             if ((rc = launch_small_y(h, d, second, est, Yd, n, nout, step, g, nstat, h->tile_rec.as<double>()))) return rc;
@@ -609,7 +658,7 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
             if (const char* e = getenv("GSA_KY_THREADS")) threads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
             a.ts = (int)std::min<int64_t>(ts_want, (n + 31) / 32 * 32);
             a.tpr = (int)((n + a.ts - 1) / a.ts);
-            a.ntiles = a.tpr * o->nboot;
+            a.ntiles = a.tpr * nboot;
             tpr = a.tpr;
             if ((rc = h->tile_rec.reserve(sizeof(double) * (size_t)a.ntiles * recsz))) return rc;
             a.tile_rec = h->tile_rec.as<double>();
@@ -627,7 +676,84 @@ static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double*
             h->last_launches++;
             GSA_CUDA(cudaGetLastError());
         }
-        if ((rc = run_reduce(h, recsz, nstat, tpr, 0, o->nboot, partials))) return rc;
+    return run_reduce(h, recsz, nstat, tpr, rep_first, nboot, partials);
+}
+
+static int partials_y_impl(gsa_handle* h, const gsa_sobol_opts* o, const double* Y, int nout, int d, int64_t n, double* partials) {
+    int rc = check_opts(o);
+    if (rc) return rc;
+    if (d < 1 || nout < 1 || n < 0) return fail(GSA_ERR_INVALID, "bad shape: nout=%d d=%d n=%lld", nout, d, (long long)n);
+    if (!partials || (!Y && n > 0)) return fail(GSA_ERR_INVALID, "Y or partials is NULL");
+    const bool second = o->second_order != 0;
+    const int est = o->ei_estimator, step = second ? 2 * d + 2 : d + 2;
+    const int nstat = stat_count(d, est, second), recsz = nstat * nout;
+    h->last_launches = 0;
+    h->kernel_timed = false;
+    const size_t rep_bytes = sizeof(double) * (size_t)nout * (size_t)n * step;   // one replicate of all_y
+    const size_t ybytes = rep_bytes * o->nboot;
+    GSA_CUDA(cudaEventRecord(h->ev0, h->stream));
+    GSA_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (size_t)o->nboot * recsz, h->stream));
+    if (o->input_location != GSA_LOC_HOST || ybytes == 0) {
+        if ((rc = y_kernels(h, o, Y, nout, d, n, o->nboot, 0, partials))) return rc;
+        GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
+        return GSA_OK;
+    }
+    // A host all_y (the reference's `all_y = f(all_points)`, :143) is STREAMED: chunks of whole replicates, or -- when one
+    // replicate exceeds the chunk size (config 4: 189 GB in one replicate) -- of sample ranges of a replicate, each copied as
+    // `step` contiguous runs into one of two device buffers so that the copy of chunk i+1 overlaps the kernels of chunk i.  A
+    // chunk is itself a small all_y (its own n), and the sums are additive, so the same kernels serve it.
+    size_t chunk_bytes = (size_t)512 << 20;
+    if (const char* e = getenv("GSA_Y_CHUNK_MB")) chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;   // testing knob
+    bool devp = false;
+    const bool pinned = is_device_or_pinned(Y, &devp);
+    if (!pinned) chunk_bytes = std::min(chunk_bytes, (size_t)128 << 20);
+    const bool whole = rep_bytes <= chunk_bytes;
+    const int reps_per_chunk = whole ? (int)std::min<size_t>((size_t)o->nboot, chunk_bytes / rep_bytes) : 1;
+    const int64_t n_chunk = whole ? n : std::max<int64_t>(1, (int64_t)(chunk_bytes / (sizeof(double) * (size_t)nout * step)));
+    const size_t buf_bytes = whole ? rep_bytes * reps_per_chunk : sizeof(double) * (size_t)nout * step * (size_t)n_chunk;
+    for (int b = 0; b < 2; ++b)
+        if ((rc = h->y_in[b].reserve(buf_bytes))) return rc;
+    if (!pinned && h->pinned_cap < buf_bytes) {
+        for (int b = 0; b < 2; ++b) {
+            if (h->pinned[b]) cudaFreeHost(h->pinned[b]);
+            h->pinned[b] = nullptr;
+        }
+        h->pinned_cap = 0;
+        for (int b = 0; b < 2; ++b) GSA_CUDA(cudaMallocHost(&h->pinned[b], buf_bytes));
+        h->pinned_cap = buf_bytes;
+    }
+    int ci = 0;
+    auto copy_run = [&](int b, size_t dst_off, const double* src, size_t bytes) -> int {
+        char* dst = static_cast<char*>(h->y_in[b].p) + dst_off;
+        if (pinned) {
+            GSA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        } else {
+            char* st = static_cast<char*>(h->pinned[b]) + dst_off;
+            parallel_memcpy(st, src, bytes);
+            GSA_CUDA(cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        }
+        return GSA_OK;
+    };
+    for (int r0 = 0; r0 < o->nboot; r0 += reps_per_chunk) {
+        const int nr = std::min(reps_per_chunk, o->nboot - r0);
+        for (int64_t s0 = 0; s0 < n; s0 += n_chunk, ++ci) {
+            const int64_t ns = std::min(n_chunk, n - s0);
+            const int b = ci & 1;
+            GSA_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[b], 0));   // buffer b free again (also across calls)?
+            if (!pinned) GSA_CUDA(cudaEventSynchronize(h->ev_copy[b]));        // staging buffer drained?
+            if (whole) {
+                if ((rc = copy_run(b, 0, Y + (size_t)r0 * (rep_bytes / sizeof(double)), rep_bytes * nr))) return rc;
+            } else {
+                for (int blk = 0; blk < step; ++blk)
+                    if ((rc = copy_run(b, sizeof(double) * (size_t)nout * (size_t)ns * blk,
+                                       Y + (size_t)nout * ((size_t)r0 * step * n + (size_t)blk * n + s0), sizeof(double) * (size_t)nout * ns)))
+                        return rc;
+            }
+            GSA_CUDA(cudaEventRecord(h->ev_copy[b], h->copy_stream));
+            GSA_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy[b], 0));
+            if ((rc = y_kernels(h, o, h->y_in[b].as<double>(), nout, d, ns, nr, r0, partials))) return rc;
+            GSA_CUDA(cudaEventRecord(h->ev_done[b], h->stream));
+        }
     }
     GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
     return GSA_OK;
@@ -726,7 +852,7 @@ int gsa_destroy(gsa_handle* h) {
         peer_release_handle(h);
         if (h->tail_host) cudaFreeHost(h->tail_host);
         if (h->tail_flag) cudaFreeHost(h->tail_flag);
-        DevBuf* bufs[] = {&h->tile_rec, &h->partials, &h->params, &h->vtab, &h->lbub, &h->stage[0], &h->stage[1], &h->dev_in[0], &h->dev_in[1], &h->ybuf, &h->aux, &h->gram, &h->tail_counters, &h->tail_grec};
+        DevBuf* bufs[] = {&h->tile_rec, &h->partials, &h->params, &h->vtab, &h->lbub, &h->stage[0], &h->stage[1], &h->dev_in[0], &h->dev_in[1], &h->ybuf, &h->y_in[0], &h->y_in[1], &h->aux, &h->gram, &h->tail_counters, &h->tail_grec};
         for (DevBuf* b : bufs) b->release();
         for (auto& um : h->user_models)
             if (um.lib) cudaLibraryUnload(um.lib);
@@ -846,32 +972,13 @@ int gsa_sobol_design(gsa_handle* h, int64_t n, int d, int num_mats, const double
         const int64_t nc = std::min(chunk, ncols - cc);
         for (int m0 = 0; m0 < num_mats; m0 += 8) {
             const int nm = std::min(8, num_mats - m0);
-            DesignArgs a;
-            a.V = h->vtab.as<uint32_t>() + (size_t)32 * d * m0;
-            a.scale = h->lbub.as<double>();
-            a.lb = h->lbub.as<double>() + d;
-            for (int m = 0; m < 8; ++m) a.out[m] = nullptr;
-            for (int m = 0; m < nm; ++m)
-                a.out[m] = to_host ? h->stage[0].as<double>() + (size_t)(m0 + m) * d * nc : out[m0 + m] + (size_t)d * cc;
-            a.first = first + (uint64_t)cc;
-            a.ncols = nc;
-            a.d = d;
-            a.dT = d * nm;
-            // two dimensions per thread (16-byte stores) when d is even and the outputs are 16-byte aligned
-            bool vec2 = d % 2 == 0 && !getenv("GSA_DESIGN_SCALAR");
-            for (int m = 0; m < nm; ++m) vec2 = vec2 && (reinterpret_cast<uintptr_t>(a.out[m]) % 16 == 0);
-            const int64_t units = vec2 ? a.dT / 2 : a.dT;     // work items per point
-            const int tpb = vec2 ? DESIGN_THREADS2 : DESIGN_THREADS;
-            // P*units threads ~ 2 full waves of 2048 threads per SM
-            const int64_t want = (int64_t)h->sm_count * 2048 * 2;
-            int lp = 0;
-            while (((int64_t)1 << lp) * units < want && ((int64_t)1 << lp) < nc) ++lp;
-            a.lp = lp;
-            const int64_t threads = ((int64_t)1 << lp) * units;
-            if (vec2) sobol_design_kernel2<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, h->stream>>>(a);
-            else sobol_design_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, h->stream>>>(a);
-            h->last_launches++;
-            GSA_CUDA(cudaGetLastError());
+            double* outs[8];
+            int voff[8];
+            for (int m = 0; m < nm; ++m) {
+                outs[m] = to_host ? h->stage[0].as<double>() + (size_t)(m0 + m) * d * nc : out[m0 + m] + (size_t)d * cc;
+                voff[m] = (m0 + m) * d;
+            }
+            if ((rc = launch_design(h, h->lbub.as<double>(), h->lbub.as<double>() + d, outs, voff, nm, d, first + (uint64_t)cc, nc))) return rc;
         }
         if (to_host) {
             for (int m = 0; m < num_mats; ++m)
@@ -1048,32 +1155,50 @@ int gsa_sobol_all_points(gsa_handle* h, const gsa_sobol_opts* opts, const double
     const int step = opts->second_order ? 2 * d + 2 : d + 2;
     const int64_t total = (int64_t)d * n * step * opts->nboot;
     if (total == 0) return GSA_OK;
-    const double *dA = A, *dB = B;
-    const size_t in_bytes = sizeof(double) * (size_t)d * (size_t)(n * opts->nboot);
-    if (opts->input_location == GSA_LOC_HOST) {
-        for (int b = 0; b < 2; ++b)
-            if ((rc = h->dev_in[b].reserve(in_bytes))) return rc;
-        GSA_CUDA(cudaMemcpyAsync(h->dev_in[0].p, A, in_bytes, cudaMemcpyHostToDevice, h->stream));
-        GSA_CUDA(cudaMemcpyAsync(h->dev_in[1].p, B, in_bytes, cudaMemcpyHostToDevice, h->stream));
-        dA = h->dev_in[0].as<double>();
-        dB = h->dev_in[1].as<double>();
-    }
-    double* dP = P;
-    if (p_location == GSA_LOC_HOST) {
-        if ((rc = h->ybuf.reserve(sizeof(double) * (size_t)total))) return rc;
-        dP = h->ybuf.as<double>();
-    }
     h->last_launches = 0;
     GSA_CUDA(cudaEventRecord(h->ev0, h->stream));
-    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
-    all_points_kernel<<<grid, 256, 0, h->stream>>>(dA, dB, dP, d, n, step, total);
-    h->last_launches++;
-    GSA_CUDA(cudaGetLastError());
-    GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
-    if (p_location == GSA_LOC_HOST) {
-        GSA_CUDA(cudaMemcpyAsync(P, dP, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, h->stream));
-        GSA_CUDA(cudaStreamSynchronize(h->stream));
+    const bool a_host = opts->input_location == GSA_LOC_HOST, p_host = p_location == GSA_LOC_HOST;
+    if (!a_host && !p_host) {   // everything on the device: one launch
+        const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->sm_count * 16);
+        all_points_kernel<<<grid, 256, 0, h->stream>>>(A, B, P, d, n, step, total);
+        h->last_launches++;
+        GSA_CUDA(cudaGetLastError());
+        GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
+        return GSA_OK;
     }
+    // Host designs and / or a host all_points (which is `step` times the size of A and B: 5.5 TB for config 5) go through the
+    // device in chunks of a sample range of one replicate: upload the A/B columns, fuse them into a compact [step][ns] block
+    // set, and scatter the `step` blocks to their places in P -- nothing of the size of P is ever held on the device.
+    size_t chunk_bytes = (size_t)256 << 20;
+    if (const char* e = getenv("GSA_P_CHUNK_MB")) chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;   // testing knob
+    const int64_t ns_max = std::max<int64_t>(1, std::min<int64_t>(n, (int64_t)(chunk_bytes / (sizeof(double) * (size_t)d * step))));
+    if (a_host)
+        for (int b = 0; b < 2; ++b)
+            if ((rc = h->dev_in[b].reserve(sizeof(double) * (size_t)d * ns_max))) return rc;
+    if ((rc = h->ybuf.reserve(sizeof(double) * (size_t)d * ns_max * step))) return rc;
+    double* scratch = h->ybuf.as<double>();
+    for (int r = 0; r < opts->nboot; ++r)
+        for (int64_t s0 = 0; s0 < n; s0 += ns_max) {
+            const int64_t ns = std::min(ns_max, n - s0);
+            const size_t in_off = (size_t)d * (size_t)(r * n + s0), in_bytes = sizeof(double) * (size_t)d * ns;
+            const double *dA = A + in_off, *dB = B + in_off;
+            if (a_host) {
+                GSA_CUDA(cudaMemcpyAsync(h->dev_in[0].p, A + in_off, in_bytes, cudaMemcpyHostToDevice, h->stream));
+                GSA_CUDA(cudaMemcpyAsync(h->dev_in[1].p, B + in_off, in_bytes, cudaMemcpyHostToDevice, h->stream));
+                dA = h->dev_in[0].as<double>();
+                dB = h->dev_in[1].as<double>();
+            }
+            const int64_t ctotal = (int64_t)d * ns * step;
+            const int grid = (int)std::min<int64_t>((ctotal + 255) / 256, (int64_t)h->sm_count * 16);
+            all_points_kernel<<<grid, 256, 0, h->stream>>>(dA, dB, scratch, d, ns, step, ctotal);   // the chunk as a 1-replicate design
+            h->last_launches++;
+            GSA_CUDA(cudaGetLastError());
+            for (int blk = 0; blk < step; ++blk)
+                GSA_CUDA(cudaMemcpyAsync(P + (size_t)d * (((size_t)r * step + blk) * n + s0), scratch + (size_t)d * ns * blk, in_bytes,
+                                         p_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+            if (p_host || a_host) GSA_CUDA(cudaStreamSynchronize(h->stream));   // pageable host memory on either side: keep it simple and ordered
+        }
+    GSA_CUDA(cudaEventRecord(h->ev1, h->stream));
     return GSA_OK;
 }
 

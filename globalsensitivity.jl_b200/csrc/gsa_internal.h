@@ -74,7 +74,7 @@ struct gsa_handle {
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, ev_params = nullptr, ev_switch = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     std::mutex mu;
-    gsa::DevBuf tile_rec, partials, params, vtab, lbub, stage[2], dev_in[2], ybuf, aux, gram;
+    gsa::DevBuf tile_rec, partials, params, vtab, lbub, stage[2], dev_in[2], ybuf, y_in[2], aux, gram;
     void* pinned[2] = {nullptr, nullptr};
     size_t pinned_cap = 0;
     std::vector<gsa::UserModelEntry> user_models;

@@ -22,6 +22,8 @@ struct DesignArgs {
     uint64_t first;         // 0-based sequence index of local column 0
     int64_t ncols;
     int d, dT, lp;          // dT = dims handled by this launch (<= 8*d), P = 1 << lp
+    int voff[8];            // first dimension (row of V) of each matrix: m*d for a plain design; the p_range design of
+                            // gsa(f, ::Sobol, p_range) takes A from block r and B from block nboot + r (reference :414-415)
 };
 
 constexpr int DESIGN_THREADS = 256;
@@ -38,7 +40,10 @@ __global__ void __launch_bounds__(DESIGN_THREADS) sobol_design_kernel(DesignArgs
     for (int idx = threadIdx.x; idx < 32 * DESIGN_THREADS; idx += DESIGN_THREADS) {
         const int slot = idx >> 5, b = idx & 31;
         const int64_t fs = f0 + slot;
-        if (fs < total) Vs[b][slot] = __ldg(a.V + 32 * (int)(fs % a.dT) + b);
+        if (fs < total) {
+            const int jj = (int)(fs % a.dT);
+            Vs[b][slot] = __ldg(a.V + 32 * (a.voff[jj / a.d] + jj % a.d) + b);
+        }
     }
     __syncthreads();
     const int64_t f = f0 + threadIdx.x;
@@ -80,7 +85,10 @@ __global__ void __launch_bounds__(DESIGN_THREADS2) sobol_design_kernel2(DesignAr
     for (int idx = threadIdx.x; idx < 32 * 2 * DESIGN_THREADS2; idx += DESIGN_THREADS2) {
         const int slot = idx >> 5, b = idx & 31;
         const int64_t fs = f0 + (slot >> 1);
-        if (fs < total) Vs[b * ROW + slot] = __ldg(a.V + 32 * (2 * (int)(fs % dT2) + (slot & 1)) + b);
+        if (fs < total) {
+            const int jj = 2 * (int)(fs % dT2) + (slot & 1);
+            Vs[b * ROW + slot] = __ldg(a.V + 32 * (a.voff[jj / a.d] + jj % a.d) + b);
+        }
     }
     __syncthreads();
     const int64_t f = f0 + threadIdx.x;
