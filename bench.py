@@ -173,10 +173,24 @@ def peaks():
 # host memory placement: a rank's host shard lives on the NUMA node its GPU hangs off
 # ------------------------------------------------------------------------------------------------------------------
 def gpu_numa_node(idx: int):
+    """NUMA node of GPU `idx` from sysfs (None if the platform does not say: VMs often report -1)"""
+    bus = None
     try:
         import torch
         p = torch.cuda.get_device_properties(idx)
         bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+    except Exception:                                   # noqa: BLE001 - older torch: ask nvidia-smi
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(idx)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+            if out:
+                dom, rest = out.split(":", 1)
+                bus = f"{int(dom, 16):04x}:{rest.lower()}"
+        except Exception:                               # noqa: BLE001
+            bus = None
+    if not bus:
+        return None
+    try:
         with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
             n = int(f.read())
         return n if n >= 0 else None
