@@ -36,7 +36,7 @@ struct FusedPlan {
     bool pairs_tile = false;     // pairs kernel with thread-per-sample evaluation (even d <= 8)
     const void* kernel_alt = nullptr;
     size_t smem_alt = 0;
-    int lin_NB = 0;              // 8-coordinate blocks of the stacked [a; b] vector (linear Gram kernel)
+    int lin_NB = 0, lin_un = 2;  // 8-coordinate blocks of the stacked [a; b] vector (linear Gram kernel); warp steps per load group
     bool writes_partials() const { return kind == PLAN_LINEAR; }   // the plan adds its records to `out_partials` itself
     double* out_partials = nullptr;
     double* rec_base = nullptr;   // where the tile records go: h->tile_rec, or straight into `partials` when a replicate is one tile
@@ -256,11 +256,17 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
         p->kind = PLAN_LINEAR;
         p->threads = LIN_THREADS;
         const int NB = (2 * d + 7) / 8;
-        const int un = 2;
+        int un = 2;
         int st = NB <= 5 ? 6 : 4;            // groups in flight per thread (ring stages)
-        if (const char* e = getenv("GSA_LIN_ST")) st = atoi(e) == 3 ? 3 : (atoi(e) == 4 ? 4 : 6);   // tuning knob
+        if (const char* e = getenv("GSA_LIN_ST")) st = atoi(e) == 2 ? 2 : atoi(e) == 3 ? 3 : (atoi(e) == 4 ? 4 : 6);   // tuning knobs
+        if (const char* e = getenv("GSA_LIN_UN")) un = atoi(e) == 4 ? 4 : 2;
+        if (un == 4 && st > 3) st = 3;
+        if (un == 2 && st == 2) st = 3;
         const void* kern = nullptr;
-#define GSA_LIN_CASE(NBV) if (NB == NBV) kern = st == 6 ? (const void*)linear_gram_kernel<NBV, 2, 6> : st == 4 ? (const void*)linear_gram_kernel<NBV, 2, 4> : (const void*)linear_gram_kernel<NBV, 2, 3>;
+#define GSA_LIN_CASE(NBV)                                                                                                                  \
+    if (NB == NBV)                                                                                                                         \
+        kern = un == 4 ? (st == 3 ? (const void*)linear_gram_kernel<NBV, 4, 3> : (const void*)linear_gram_kernel<NBV, 4, 2>)               \
+                       : (st == 6 ? (const void*)linear_gram_kernel<NBV, 2, 6> : st == 4 ? (const void*)linear_gram_kernel<NBV, 2, 4> : (const void*)linear_gram_kernel<NBV, 2, 3>);
         GSA_LIN_CASE(1) GSA_LIN_CASE(2) GSA_LIN_CASE(3) GSA_LIN_CASE(4) GSA_LIN_CASE(5) GSA_LIN_CASE(6) GSA_LIN_CASE(7) GSA_LIN_CASE(8)
 #undef GSA_LIN_CASE
         if (!kern) return fail(GSA_ERR_UNSUPPORTED, "linear kernel: no instantiation for %d blocks", NB);
@@ -274,6 +280,7 @@ static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool se
         p->resident = h->sm_count * std::max(1, nbl);
         p->tiles_per_cta = 1;               // few, large tiles: every tile ends with a cross-warp combine and a moments write-out
         p->ts_min = p->ts_gran = 4 * un * LIN_NW;
+        p->lin_un = un;
         return GSA_OK;
     }
     {
