@@ -29,6 +29,10 @@ class SobolOpts(C.Structure):
 _dp = C.POINTER(C.c_double)
 
 
+class EfastResultC(C.Structure):
+    _fields_ = [("S1", C.POINTER(C.c_double)), ("ST", C.POINTER(C.c_double))]
+
+
 class SobolResultC(C.Structure):
     _fields_ = [("S1", _dp), ("S1_conf_int", _dp), ("S2", _dp), ("S2_conf_int", _dp), ("ST", _dp), ("ST_conf_int", _dp)]
 
@@ -71,6 +75,9 @@ SIGNATURES = {
     "gsa_multi_model_register_separable": [_vp, _vp, _sz, C.c_char_p, _i, _ip],
     "gsa_multi_sobol_run": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
     "gsa_multi_sobol_run_generated": [_vp, _op, _i, _vp, _i, _vp, _vp, _i, _i64, _rp],
+    "gsa_efast_design": [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _i],
+    "gsa_efast_run": [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i64, C.POINTER(EfastResultC)],
+    "gsa_efast_analyze_y": [_vp, _i, _vp, _i, _i, _i, _i64, C.POINTER(EfastResultC)],
     "gsa_last_timing": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), _ip],
     "gsa_peer_export": [_vp, _sz, _vp],
     "gsa_peer_connect": [_vp, _i, _i, _vp],

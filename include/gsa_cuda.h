@@ -196,6 +196,25 @@ GSA_API int gsa_sobol_analyze_y(gsa_handle* h, const gsa_sobol_opts* opts, const
 GSA_API int gsa_sobol_all_points(gsa_handle* h, const gsa_sobol_opts* opts, const double* A, const double* B, int d,
                          int64_t N, double* P, int p_location);
 
+/* ---- eFAST (reference src/eFAST_sensitivity.jl:75-213) ------------------------------------------------------ */
+/* mirrors `eFASTResult` (:70-73): S1, ST are nout x d, column-major (a 1 x d row for a scalar model); caller-allocated */
+typedef struct gsa_efast_result {
+    double* S1;
+    double* ST;
+} gsa_efast_result;
+/* The search-curve design (:98-135): P is d x (samples*d); block i (columns [i*samples, (i+1)*samples)) is the curve in which
+ * parameter i carries the frequency omega[0] = (samples-1) / (2*num_harmonics).  p_range entries are [lb_j, ub_j] (uniform; a
+ * degenerate range lb_j == ub_j gives a constant, :113).  phi[d] replaces the reference's `2 rand(rng)` per curve (:111); NULL = 0. */
+GSA_API int gsa_efast_design(gsa_handle* h, const double* lb, const double* ub, int d, int64_t samples, int num_harmonics,
+                     const double* phi, double* P, int p_location);
+/* gsa(model, eFAST(num_harmonics), p_range; samples, batch=true) (:75-166): the design is generated in registers, the device model
+ * is evaluated on it, and the spectrum is analysed (:167-213) -- nothing but lb/ub/phi goes in, S1/ST come out. */
+GSA_API int gsa_efast_run(gsa_handle* h, int num_harmonics, int model_id, const double* params, int nparams, const double* lb,
+                  const double* ub, const double* phi, int d, int64_t samples, gsa_efast_result* out);
+/* gsa_efast_all_y_analysis (:167-213) on a host or device all_y = f(design): nout x (samples*d) */
+GSA_API int gsa_efast_analyze_y(gsa_handle* h, int num_harmonics, const double* Y, int y_location, int nout, int d, int64_t samples,
+                        gsa_efast_result* out);
+
 /* Device times (ms, CUDA events on the handle's stream) of the last partials / design call: the whole call,
  * and its dominant kernel alone (the last fused / estimator launch; 0 if none); plus the number of kernels
  * the call launched.  Used by bench.py's roofline line. */
