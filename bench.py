@@ -429,7 +429,6 @@ def gpu_arm(args):
     # ---- e2e: the public call with HOST inputs; H2D of the whole shard inside the timed region --------------------------
     e2e = None
     if not args.no_e2e:
-        cudart = torch.cuda.cudart()
         nbytes = 8 * d * ncols
         hostA = np.empty((ncols, d), dtype=np.float64)
         hostB = np.empty((ncols, d), dtype=np.float64)
@@ -440,9 +439,7 @@ def gpu_arm(args):
         tB.copy_(B.t())
         torch.cuda.synchronize()
         for arr in (hostA, hostB):
-            rc = cudart.cudaHostRegister(arr.ctypes.data, nbytes, 0)
-            if int(rc) != 0:
-                raise RuntimeError(f"cudaHostRegister failed: {rc}")
+            g.pin_host(arr)                                 # gsa_host_register: what a Julia caller does with GSACuda.pin!(A)
         del A, B
         if one_call:
             del sstep
@@ -480,13 +477,27 @@ def gpu_arm(args):
                "entry": "gsa_sobol_run" if world == 1 else "gsa_sobol_run_sharded (one call per rank)",
                "max_abs_diff_vs_resident": float(max(np.abs(res_e.S1 - res.S1).max(), np.abs(res_e.ST - res.ST).max()))}
         for arr in (hostA, hostB):
-            cudart.cudaHostUnregister(arr.ctypes.data)
+            g.unpin_host(arr)
         # the same call on PAGEABLE memory (what a plain Julia Matrix{Float64} is): staged through the library's pinned buffers
         res_p, dtp, _ = timed(1, 0)
         e2e["pageable"] = {"value": w["rows"] / dtp, "unit": UNIT, "ms_per_step": 1e3 * dtp, "aggregate_h2d_gbs": 2 * 8 * d * N / dtp / 1e9,
                            "host_memory": "pageable (numpy), staged by the library",
                            "max_abs_diff_vs_resident": float(max(np.abs(res_p.S1 - res.S1).max(), np.abs(res_p.ST - res.ST).max()))}
         del hA, hB, tA, tB, hostA, hostB
+        # the platform's own ceiling: all ranks copy 2 GiB of torch-pinned memory to their GPU at the same time (no kernels, no library)
+        if world > 1:
+            src = torch.empty(1 << 28, dtype=torch.float64).pin_memory()
+            dst = torch.empty(1 << 28, dtype=torch.float64, device="cuda")
+            dst.copy_(src, non_blocking=True)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            barrier()
+            tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            e2e["platform_concurrent_h2d_gbs"] = 3 * world * src.numel() * 8 / float(tc[0]) / 1e9
+            del src, dst
 
     if rank == 0:
         peak, peak_src = peaks()

@@ -50,6 +50,8 @@ SIGNATURES = {
     "gsa_destroy": [_vp],
     "gsa_set_stream": [_vp, _vp, _i],
     "gsa_synchronize": [_vp],
+    "gsa_host_register": [_vp, _sz],
+    "gsa_host_unregister": [_vp],
     "gsa_model_lookup": [C.c_char_p, _ip],
     "gsa_model_nout": [_vp, _i, _i, _i, _ip],
     "gsa_model_register_fatbin": [_vp, _vp, _sz, C.c_char_p, _i, _ip],

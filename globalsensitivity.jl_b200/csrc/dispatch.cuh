@@ -83,16 +83,22 @@ static int plan_generic(gsa_handle* h, FusedPlan* p) {
     }
     if (!k) return fail(GSA_ERR_INVALID, "unknown model id %d", p->model);
     const size_t rec_bytes = sizeof(double) * (size_t)p->nstat * p->nout, per_warp = rec_bytes + sizeof(double) * GENERIC_TILE_DOUBLES;
-    int warps = (int)std::min<size_t>(8, ((user ? 48u : 160u) << 10) / per_warp);   // linked kernels: stay within the default 48 KB
+    // Four warps per CTA (one per SM sub-partition) whenever they fit: every warp of a CTA then runs at the same speed and the two
+    // barriers that end a tile cost nothing.  With five warps (what 48 KB allowed) an SM held 15 warps on 4 sub-partitions, the warps
+    // on the crowded one ran 4/3 slower, and 38 % of all stall samples were the others waiting for them at the tile barrier
+    // (profiles/r2_user_models_ncu.txt).
+    int warps = (int)std::min<size_t>(4, ((user ? 48u : 160u) << 10) / per_warp);   // linked kernels: stay within the default 48 KB
     if (warps < 1) return fail(GSA_ERR_UNSUPPORTED, "statistics record of %zu bytes does not fit in shared memory", rec_bytes);
+    if (warps == 3) warps = 2;
     p->kind = PLAN_GENERIC;
     p->kernel = k;
     p->threads = 32 * warps;
     p->smem = per_warp * warps;
     int nb = 2;
-    if (!user) {
-        if (p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-        GSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem));
+    if (!user && p->smem > (48u << 10)) GSA_CUDA(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem) != cudaSuccess) {   // (also answers for a linked cudaKernel_t)
+        cudaGetLastError();
+        nb = 2;
     }
     p->resident = std::max(1, nb) * h->sm_count;
     p->ts_min = 32 * warps;

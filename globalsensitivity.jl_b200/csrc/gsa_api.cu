@@ -1202,6 +1202,28 @@ int gsa_sobol_all_points(gsa_handle* h, const gsa_sobol_opts* opts, const double
     return GSA_OK;
 }
 
+int gsa_host_register(void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return fail(GSA_ERR_INVALID, "bad arguments to gsa_host_register");
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return GSA_OK;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostRegister");
+    return GSA_OK;
+}
+
+int gsa_host_unregister(void* ptr) {
+    if (!ptr) return GSA_OK;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e == cudaErrorHostMemoryNotRegistered) {
+        cudaGetLastError();
+        return GSA_OK;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostUnregister");
+    return GSA_OK;
+}
+
 int gsa_last_timing(gsa_handle* h, float* ms, float* kernel_ms, int* launches) {
     if (!h) return fail(GSA_ERR_INVALID, "handle is NULL");
     DeviceGuard guard(h->device);

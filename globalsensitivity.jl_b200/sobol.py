@@ -304,6 +304,15 @@ class GsaMulti:
         return finish()
 
 
+def pin_host(a) -> None:
+    """cudaHostRegister a NumPy array in place (gsa_host_register): host designs are then streamed at PCIe speed without staging."""
+    check(lib().gsa_host_register(a.ctypes.data, a.nbytes))
+
+
+def unpin_host(a) -> None:
+    check(lib().gsa_host_unregister(a.ctypes.data))
+
+
 _default = {}
 
 

@@ -55,6 +55,10 @@ end
 const DEFAULT = Ref{Union{Nothing, Handle}}(nothing)
 default_handle() = something(DEFAULT[], (DEFAULT[] = Handle()))
 
+# ---- pin a Julia array in place: host designs are then streamed at PCIe speed instead of staged (unpin! before it is freed) ----
+pin!(A::Array{Float64}) = (check(ccall((:gsa_host_register, libgsa), Cint, (Ptr{Cvoid}, Csize_t), A, sizeof(A))); A)
+unpin!(A::Array{Float64}) = (check(ccall((:gsa_host_unregister, libgsa), Cint, (Ptr{Cvoid},), A)); A)
+
 # ---- the device-model registry replaces the Julia closure `f` -----------------------------------------------
 struct DeviceModel
     id::Cint
@@ -261,6 +265,37 @@ function DeviceModel(m::Multi, image::Vector{UInt8}, symbol::AbstractString, par
                     m.ptr, image, length(image), symbol, nout, id))
     end
     return DeviceModel(id[], vec(Float64.(params)), Int(nout))
+end
+
+# ---- eFAST (reference src/eFAST_sensitivity.jl:75-213): design generated in registers, device model, spectral analysis -------
+struct GsaEfastResult
+    S1::Ptr{Cdouble}
+    ST::Ptr{Cdouble}
+end
+function gsa(model::DeviceModel, method::GlobalSensitivity.eFAST, p_range::AbstractVector; samples::Int, batch = true,
+             phi::Vector{Float64} = 2 .* rand(length(p_range)), handle::Handle = default_handle(), kwargs...)
+    lb = [float(p[1]) for p in p_range]; ub = [float(p[2]) for p in p_range]
+    d = length(lb); no = nout(model, d)
+    S1 = zeros(no, d); ST = zeros(no, d)
+    res = GsaEfastResult(pointer(S1), pointer(ST))
+    GC.@preserve S1 ST model lb ub phi begin
+        check(ccall((:gsa_efast_run, libgsa), Cint,
+                    (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Int64, Ref{GsaEfastResult}),
+                    handle.ptr, method.num_harmonics, model.id, model.params, length(model.params), lb, ub, phi, d, samples, Ref(res)))
+    end
+    return GlobalSensitivity.eFASTResult(S1, ST)
+end
+# the analysis alone, for any Julia closure: all_y = f(ps) as at src/eFAST_sensitivity.jl:137
+function gsa_efast_all_y_analysis(method::GlobalSensitivity.eFAST, all_y::VecOrMat{Float64}, num_params::Integer, samples::Integer;
+                                  handle::Handle = default_handle())
+    no = all_y isa AbstractMatrix ? size(all_y, 1) : 1
+    S1 = zeros(no, num_params); ST = zeros(no, num_params)
+    res = GsaEfastResult(pointer(S1), pointer(ST))
+    GC.@preserve S1 ST all_y begin
+        check(ccall((:gsa_efast_analyze_y, libgsa), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cint, Cint, Int64, Ref{GsaEfastResult}),
+                    handle.ptr, method.num_harmonics, all_y, 0, no, num_params, samples, Ref(res)))
+    end
+    return GlobalSensitivity.eFASTResult(S1, ST)
 end
 
 # QuasiMonteCarlo.sample(n, lb, ub, SobolSample()): the single-matrix design the reference's other methods draw (SURVEY 8(f) N3)

@@ -43,7 +43,7 @@ def _parity(a, b):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("samples,H", [(15000, 4), (15001, 4), (300, 4), (4099, 2), (1 << 16, 6)])
+@pytest.mark.parametrize("samples,H", [(15000, 4), (15003, 4), (301, 4), (300, 4), (4099, 2), (1 << 16, 6)])
 def test_efast_analysis_matches_oracle(samples, H):
     """gsa_efast_all_y_analysis on the GPU (pruned DFT + Parseval) against numpy's rfft restatement, on the same all_y."""
     import gsa_loader
@@ -87,6 +87,12 @@ def test_efast_design_and_device_models():
     assert _parity(res4.S1, ref4.S1) <= 1e-11 and _parity(res4.ST, ref4.ST) <= 1e-11
     with pytest.raises(g.GsaError, match="too small"):
         g.gsa_efast(g.DeviceModel("ishigami", [7.0, 0.1]), g.eFAST(), P4, samples=40, phi=phi)
+    # samples = 15001: harmonic 4 of omega = 1875 is bin 7500 = samples/2, one past the reference's buffer (a BoundsError there,
+    # an IndexError in the oracle, an error code here)
+    with pytest.raises(IndexError):
+        ef.gsa_efast(so.ishigami_batch, P4, 15001, phi=phi)
+    with pytest.raises(g.GsaError, match="BoundsError"):
+        g.gsa_efast(g.DeviceModel("ishigami", [7.0, 0.1]), g.eFAST(), P4, samples=15001, phi=phi)
     # random phases by default: results move within the reference's own tolerance
     r5 = g.gsa_efast(g.DeviceModel("ishigami", [7.0, 0.1]), g.eFAST(), P4, samples=15000)
     assert np.abs(r5.ST - np.array([[0.556244, 0.446861, 0.239259, 0.027099]])).max() < 1e-4
