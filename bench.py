@@ -252,6 +252,20 @@ def configs_block(g, h, peak, reps=5):
                      "S1_head": np.ravel(res.S1)[:3].tolist()}
         del A, B
         torch.cuda.empty_cache()
+    # eFAST: the reference's test size, and a larger one; wall time of the public call (design in registers + model +
+    # pruned-DFT analysis), spectrum kernel alone beside it
+    for name, nm, params, dd, S in (("efast_ishigami_d4_S15000", "ishigami", [7.0, 0.1], 4, 15000), ("efast_sobolg_d20_S2^17", "sobol_g", list(np.linspace(0, 9, 20)), 20, 1 << 17)):
+        rng = [[-np.pi, np.pi]] * dd if nm == "ishigami" else [[0.0, 1.0]] * dd
+        m = g.DeviceModel(nm, params)
+        ws, ks = [], []
+        for i in range(reps + 1):
+            t0 = time.perf_counter()
+            r = g.gsa_efast(m, g.eFAST(), rng, samples=S, phi=np.linspace(0.1, 1.9, dd), handle=h)
+            w = time.perf_counter() - t0
+            if i >= 1:
+                ws.append(w); ks.append(h.last_timing()[1])
+        out[name] = {"points": S * dd, "call_wall_ms": 1e3 * float(np.median(ws)), "spectrum_kernel_ms": float(np.median(ks)),
+                     "points_per_s_call": S * dd / float(np.median(ws)), "ST_head": np.ravel(r.ST)[:3].tolist()}
     # K1: first touch of fresh memory vs steady state (the second and later calls into the same buffers)
     for d, N in ((100, 1 << 22), (8, 1 << 24)):
         mats = g.generate_design_matrices(N, np.zeros(d), np.ones(d), 2, device=True, handle=h)

@@ -101,6 +101,7 @@ static int plan_generic(gsa_handle* h, FusedPlan* p) {
         nb = 2;
     }
     p->resident = std::max(1, nb) * h->sm_count;
+    p->tiles_per_cta = 1;    // every tile ends with two CTA barriers: as few, as long tiles as the wave allows
     p->ts_min = 32 * warps;
     p->ts_gran = 32 * warps;
     return GSA_OK;

@@ -193,8 +193,10 @@ __device__ __forceinline__ void fused_generic_body(const GenericArgs& a) {
 }
 
 // S: d <= 32 and d*nout <= 64;  L: d <= 128 and d*nout <= 256  (d*nout beyond that: GSA_ERR_UNSUPPORTED)
+// (CTAs are at most four warps, one per SM sub-partition: see plan_generic)
+constexpr int GENERIC_THREADS_MAX = 128;
 template <class Model, bool SECOND, bool LARGE>
-__global__ void __launch_bounds__(256) fused_generic_kernel(GenericArgs a) {
+__global__ void __launch_bounds__(GENERIC_THREADS_MAX, 5) fused_generic_kernel(GenericArgs a) {
     fused_generic_body<Model, SECOND, LARGE ? GENERIC_DMAX : 32, LARGE ? GENERIC_ACC_L : GENERIC_ACC_S>(a);
 }
 

@@ -70,7 +70,9 @@ def test_efast_design_and_device_models():
     phi = np.array([0.3, 1.1, 0.7, 1.9])
     P = g.efast_design(g.eFAST(), P4, 15000, phi=phi)
     Pr = ef.efast_design(P4, 15000, 4, phi)
-    assert P.shape == Pr.shape and np.abs(P - Pr).max() < 1e-14
+    # asin(sinpi(.)) is ill-conditioned at the turning points of a search curve (d asin / dx -> infinity at |x| = 1): an ulp of
+    # difference between CUDA's and NumPy's sinpi shows up as ~1e-13 there -- any two libms differ like this, Julia's included
+    assert P.shape == Pr.shape and np.abs(P - Pr).max() < 1e-12
     ref = ef.gsa_efast(so.ishigami_batch, P4, 15000, phi=phi)
     res = g.gsa_efast(g.DeviceModel("ishigami", [7.0, 0.1]), g.eFAST(), P4, samples=15000, phi=phi)
     assert res.S1.shape == (1, 4)
