@@ -74,6 +74,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
         subprocess.check_call(["/usr/bin/gcc", "-c", os.path.join(CSRC, "user_blob.S"), f"-DGSA_BLOB_SYM={sym}", f"-DGSA_BLOB_END={sym}_end",
                                f'-DGSA_USER_CUBIN_PATH="{ucubin}"', "-o", ublob])
         user_blobs.append(ublob)
+    # ... and the separable kernels once more as LTO-IR: when the user's image carries LTO-IR too (code=lto_100a) and uses the
+    # default symbol name, nvJitLink inlines the per-coordinate function into the kernel that is actually launched (-kernels-used)
+    lto_procs = []
+    for tag, kind in (("product", 1), ("additive", 2)):
+        ucu = os.path.join(obj_dir, f"user_{tag}.cu")
+        ltoir = os.path.join(obj_dir, f"user_{tag}.ltoir")
+        cmd = [nvcc(), "-ccbin", HOST_CXX, "-std=c++17", "-O3", "-dlto", "-ltoir", "-arch=sm_100a", "-rdc=true", "-I", CSRC,
+               f"-DGSA_USER_KIND={kind}", "-DGSA_USER_LTO_ONLY=1", "-o", ltoir, ucu]
+        lto_procs.append((ucu, ltoir, tag, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for ucu, ltoir, tag, p in lto_procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError(f"nvcc -ltoir failed on {ucu}")
+        ublob = os.path.join(obj_dir, f"user_blob_{tag}_lto.o")
+        sym = f"gsa_user_{tag}_lto_blob"
+        subprocess.check_call(["/usr/bin/gcc", "-c", os.path.join(CSRC, "user_blob.S"), f"-DGSA_BLOB_SYM={sym}", f"-DGSA_BLOB_END={sym}_end",
+                               f'-DGSA_USER_CUBIN_PATH="{ltoir}"', "-o", ublob])
+        user_blobs.append(ublob)
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode:

@@ -854,8 +854,10 @@ int gsa_destroy(gsa_handle* h) {
         if (h->tail_flag) cudaFreeHost(h->tail_flag);
         DevBuf* bufs[] = {&h->tile_rec, &h->partials, &h->params, &h->vtab, &h->lbub, &h->stage[0], &h->stage[1], &h->dev_in[0], &h->dev_in[1], &h->ybuf, &h->y_in[0], &h->y_in[1], &h->aux, &h->gram, &h->tail_counters, &h->tail_grec};
         for (DevBuf* b : bufs) b->release();
-        for (auto& um : h->user_models)
+        for (auto& um : h->user_models) {
             if (um.lib) cudaLibraryUnload(um.lib);
+            for (cudaLibrary_t l : um.lto_libs) cudaLibraryUnload(l);
+        }
         for (int b = 0; b < 2; ++b) {
             if (h->pinned[b]) cudaFreeHost(h->pinned[b]);
             if (h->ev_copy[b]) cudaEventDestroy(h->ev_copy[b]);

@@ -61,6 +61,12 @@ struct UserModelEntry {
     cudaKernel_t k_generic[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [second order][large instantiation]
     int nout = 1;
     int kind = 0;   // GSA_USER_GENERIC | GSA_USER_PRODUCT | GSA_USER_ADDITIVE
+    // separable models: the user's image is kept so that the kernel a launch needs can be LTO-linked on first use (the
+    // per-coordinate function inlined); the kernels obtained so far, by name
+    std::vector<char> image;
+    bool try_lto = false;
+    std::vector<std::pair<std::string, cudaKernel_t>> sep_kernels;
+    std::vector<cudaLibrary_t> lto_libs;
 };
 int register_user_model(gsa_handle* h, const void* image, size_t len, const char* symbol, int kind, int nout, int* model_id);
 int user_separable_kernel(gsa_handle* h, int model_id, int T, int cpl, bool jansen, const void** kernel);

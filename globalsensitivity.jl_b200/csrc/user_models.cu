@@ -20,6 +20,10 @@ extern "C" const unsigned char gsa_user_product_blob[];
 extern "C" const unsigned char gsa_user_product_blob_end[];
 extern "C" const unsigned char gsa_user_additive_blob[];
 extern "C" const unsigned char gsa_user_additive_blob_end[];
+extern "C" const unsigned char gsa_user_product_lto_blob[];
+extern "C" const unsigned char gsa_user_product_lto_blob_end[];
+extern "C" const unsigned char gsa_user_additive_lto_blob[];
+extern "C" const unsigned char gsa_user_additive_lto_blob_end[];
 
 namespace gsa {
 
@@ -27,7 +31,7 @@ namespace {
 
 // the slice of the nvJitLink API we need (nvJitLink.h), resolved at run time
 typedef void* nvJitLinkHandle;
-enum { NVJL_INPUT_CUBIN = 1, NVJL_INPUT_PTX = 2, NVJL_INPUT_ANY = 10 };
+enum { NVJL_INPUT_CUBIN = 1, NVJL_INPUT_PTX = 2, NVJL_INPUT_LTOIR = 3, NVJL_INPUT_ANY = 10 };
 struct JitLinkApi {
     void* so = nullptr;
     int (*Create)(nvJitLinkHandle*, uint32_t, const char**) = nullptr;
@@ -205,6 +209,12 @@ int register_user_model(gsa_handle* h, const void* image, size_t len, const char
         UserModelEntry um;
         um.nout = nout;
         um.kind = kind;
+        // LTO needs the default symbol name (a PTX trampoline cannot be inlined) and an image that carries LTO-IR; whether it
+        // does is found out at the first launch (user_separable_kernel)
+        const char* env = getenv("GSA_USER_LTO");
+        um.try_lto = kind != GSA_USER_GENERIC && !(env && atoi(env) == 0) &&
+                     strcmp(symbol, kind == GSA_USER_PRODUCT ? "gsa_user_factor" : "gsa_user_term") == 0;
+        if (um.try_lto) um.image.assign(static_cast<const char*>(image), static_cast<const char*>(image) + len);
         GSA_CUDA(cudaLibraryLoadData(&um.lib, cubin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
         cudaError_t ce = cudaSuccess;
         static const char* const names[2][2] = {{"gsa_user_fused_first_s", "gsa_user_fused_first_l"}, {"gsa_user_fused_second_s", "gsa_user_fused_second_l"}};
@@ -220,6 +230,42 @@ int register_user_model(gsa_handle* h, const void* image, size_t len, const char
     return GSA_OK;
 }
 
+// LTO link of ONE separable kernel against the user's image: the kernels' LTO-IR + the image (its LTO-IR member is picked under
+// -lto), everything but `kernel_name` dropped before code generation (-kernels-used).  Fails harmlessly (returns false) when the
+// image has no LTO-IR or the linker is too old: the caller then uses the call-based kernel.
+static bool link_separable_lto(const UserModelEntry& um, const char* kernel_name, std::vector<char>* cubin_out) {
+    {
+        std::lock_guard<std::mutex> lk(g_api_mu);
+        if (load_api(g_api) != GSA_OK) return false;
+    }
+    const JitLinkApi& a = g_api;
+    nvJitLinkHandle jl = nullptr;
+    const std::string used = std::string("-kernels-used=") + kernel_name;
+    const char* opts[] = {"-arch=sm_100a", "-lto", used.c_str()};
+    if (a.Create(&jl, 3, opts)) return false;
+    const bool prod = um.kind == GSA_USER_PRODUCT;
+    const unsigned char* blob = prod ? gsa_user_product_lto_blob : gsa_user_additive_lto_blob;
+    const unsigned char* blob_end = prod ? gsa_user_product_lto_blob_end : gsa_user_additive_lto_blob_end;
+    bool ok = a.AddData(jl, NVJL_INPUT_LTOIR, blob, (size_t)(blob_end - blob), "gsa_separable_ltoir") == 0 &&
+              a.AddData(jl, NVJL_INPUT_ANY, um.image.data(), um.image.size(), "user_model") == 0 && a.Complete(jl) == 0;
+    if (ok) {
+        size_t n = 0;
+        if (a.GetErrorLogSize && a.GetErrorLog && a.GetErrorLogSize(jl, &n) == 0 && n > 1) {
+            std::string log(n, '\0');
+            a.GetErrorLog(jl, &log[0]);
+            if (log.find("error") != std::string::npos) ok = false;
+        }
+    }
+    size_t cs = 0;
+    if (ok) ok = a.GetLinkedCubinSize(jl, &cs) == 0 && cs > 0;
+    if (ok) {
+        cubin_out->resize(cs);
+        ok = a.GetLinkedCubin(jl, cubin_out->data()) == 0;
+    }
+    a.Destroy(&jl);
+    return ok;
+}
+
 // the O(d) kernel of a separable user model for (lanes per sample, coordinates per lane, Jansen | other one-term estimators)
 int user_separable_kernel(gsa_handle* h, int model_id, int T, int cpl, bool jansen, const void** kernel) {
     const int idx = model_id - GSA_MODEL_USER_BASE;
@@ -228,8 +274,46 @@ int user_separable_kernel(gsa_handle* h, int model_id, int T, int cpl, bool jans
     if (um.kind == GSA_USER_GENERIC) return fail(GSA_ERR_INVALID, "user model %d is not separable", model_id);
     char name[64];
     snprintf(name, sizeof(name), "gsa_user_sep_T%d_C%d_J%d", T, cpl, jansen ? 1 : 0);
+    for (const auto& kv : um.sep_kernels)
+        if (kv.first == name) {
+            *kernel = (const void*)kv.second;
+            return GSA_OK;
+        }
     cudaKernel_t k = nullptr;
-    GSA_CUDA(cudaLibraryGetKernel(&k, um.lib, name));
+    if (um.try_lto) {
+        // linked once per (image, kernel) in the process, loaded once per handle
+        const uint64_t hash = fnv1a(um.image.data(), um.image.size());
+        const std::string key = std::string("lto:") + name;
+        const std::vector<char>* cubin = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g_linked_mu);
+            for (const LinkedCubin& c : g_linked)
+                if (c.kind == um.kind && c.hash == hash && c.len == um.image.size() && c.symbol == key) cubin = &c.cubin;
+            if (!cubin) {
+                LinkedCubin c;
+                c.kind = um.kind; c.symbol = key; c.hash = hash; c.len = um.image.size();
+                if (link_separable_lto(um, name, &c.cubin)) {
+                    g_linked.push_back(std::move(c));
+                    cubin = &g_linked.back().cubin;
+                }
+            }
+            if (cubin) {
+                cudaLibrary_t lib = nullptr;
+                if (cudaLibraryLoadData(&lib, cubin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
+                    cudaLibraryGetKernel(&k, lib, name) == cudaSuccess) {
+                    um.lto_libs.push_back(lib);
+                } else {
+                    cudaGetLastError();
+                    if (lib) cudaLibraryUnload(lib);
+                    k = nullptr;
+                }
+            }
+        }
+        if (!k) um.try_lto = false;   // no LTO-IR in the image (or an old linker): the call-based kernels from here on
+        if (getenv("GSA_DEBUG")) fprintf(stderr, "[gsa] separable kernel %s: %s\n", name, k ? "LTO (per-coordinate function inlined)" : "call-based");
+    }
+    if (!k) GSA_CUDA(cudaLibraryGetKernel(&k, um.lib, name));
+    um.sep_kernels.emplace_back(name, k);
     *kernel = (const void*)k;
     return GSA_OK;
 }

@@ -281,3 +281,25 @@ def test_offset_inputs_fp64_model_rounding_dominates():
     from conftest import parity_err
     assert parity_err(st.S1, ref.S1) < 1e-13 and parity_err(st.ST, ref.ST) < 1e-13
     assert 1e-12 < parity_err(ref.S1, ex.S1) < 1e-9 and parity_err(ref.ST, ex.ST) < 1e-13
+
+
+def test_sobol_points_at_the_far_end_of_the_table():
+    """Dimensions up to 21201: the direction-number recurrence and the embedded Joe-Kuo table against two
+    independent generators -- SciPy (its own C recurrence) and Torch (its own copy of the table, 30-bit points)."""
+    from scipy.stats import qmc
+    import torch
+    dim, n, skip = 21201, 64, 1 << 12
+    V = so.direction_numbers(dim)
+    mine = so.sobol_ints(skip, n, V).astype(np.float64) * 2.0 ** -32
+    sp = qmc.Sobol(dim, scramble=False, bits=32)
+    sp.fast_forward(skip)
+    assert np.array_equal(mine, sp.random(n).T)
+    eng = torch.quasirandom.SobolEngine(dim, scramble=False)
+    eng.fast_forward(skip)
+    tpts = eng.draw(n, dtype=torch.float64).numpy().T
+    assert np.array_equal(np.floor(mine * 2 ** 30), np.floor(tpts * 2 ** 30))
+    # the C oracle's generator on the last 200 dimensions (as matrices 105 and 106 of a 106 x 200-dimensional design)
+    Ms = gsa_ref.sobol_design(n, np.zeros(200), np.ones(200), num_mats=106)
+    first = so.sobol_first_index(n)
+    ref = so.sobol_ints(first, n, V).astype(np.float64) * 2.0 ** -32
+    assert np.array_equal(Ms[105], ref[105 * 200:106 * 200]) and np.array_equal(Ms[104], ref[104 * 200:105 * 200])

@@ -20,6 +20,11 @@ extern "C" __device__ void trig_model(const double* x, int d, const double* p, i
 }
 extern "C" __device__ double sobolg_factor(int k, double x, const double* p, int np) { return (fabs(4.0 * x - 2.0) + p[k]) / (1.0 + p[k]); }
 '''
+SRC_LTO = r'''
+extern "C" __device__ double gsa_user_factor(int k, double x, const double* p, int np) {
+    return (1.0 + p[k] * sin(3.141592653589793 * x)) / (1.0 + 0.6366197723675814 * p[k]);
+}
+'''
 only = None
 if "--only" in sys.argv:
     only = sys.argv[sys.argv.index("--only") + 1].split(",")
@@ -28,6 +33,11 @@ open(os.path.join(tmp, "um.cu"), "w").write(SRC)
 subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-ccbin", "/usr/bin/g++", "-O3", "-rdc=true", "-fatbin", "-gencode",
                        "arch=compute_100a,code=sm_100a", "-o", os.path.join(tmp, "um.fatbin"), os.path.join(tmp, "um.cu")])
 fat = open(os.path.join(tmp, "um.fatbin"), "rb").read()
+# the same factor under the default symbol name, with LTO-IR next to the SASS: nvJitLink inlines it into the kernel (no call)
+open(os.path.join(tmp, "um_lto.cu"), "w").write(SRC_LTO)
+subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-ccbin", "/usr/bin/g++", "-O3", "-rdc=true", "-fatbin", "-gencode", "arch=compute_100a,code=lto_100a",
+                       "-gencode", "arch=compute_100a,code=sm_100a", "-o", os.path.join(tmp, "um_lto.fatbin"), os.path.join(tmp, "um_lto.cu")])
+fat_lto = open(os.path.join(tmp, "um_lto.fatbin"), "rb").read()
 h = g.default_handle()
 PEAK_DFMA = 36.6e12
 for d, N in ((20, 1 << 20), (100, 1 << 18)):
@@ -35,6 +45,7 @@ for d, N in ((20, 1 << 20), (100, 1 << 18)):
     A, B = g.generate_design_matrices(N, np.zeros(d), np.ones(d), 2, device=True, handle=h)
     routes = {"generic": g.DeviceModel.from_fatbin(fat, "trig_model", params=p),
               "separable": g.DeviceModel.from_fatbin(fat, "trig_factor", params=p, kind="product"),
+              "separable_lto": g.DeviceModel.from_fatbin(fat_lto, "gsa_user_factor", params=p, kind="product"),
               "separable_sobolg": g.DeviceModel.from_fatbin(fat, "sobolg_factor", params=p, kind="product"),
               "builtin_sobolg": g.DeviceModel("sobol_g", p)}
     results = {}
@@ -49,6 +60,9 @@ for d, N in ((20, 1 << 20), (100, 1 << 18)):
         results[name] = res
         rows = N * (d + 2)
         evals = N * (d + 2) * d if name == "generic" else N * 2 * d          # per-coordinate function evaluations
+        if name == "separable_lto" and "separable" in results:
+            e = float(max(np.abs(res.S1 - results["separable"].S1).max(), np.abs(res.ST - results["separable"].ST).max()))
+            print(json.dumps({"d": d, "lto_vs_call_max_abs_diff": e}), flush=True)
         print(json.dumps({"route": name, "d": d, "N": N, "kernel_ms": k, "rows_per_s": rows / (k * 1e-3), "hbm_gbs": 16.0 * d * N / (k * 1e-3) / 1e9,
                           "factor_evals_per_s": evals / (k * 1e-3), "S1_head": np.ravel(res.S1)[:3].tolist()}), flush=True)
     if "generic" in results and "separable" in results:
