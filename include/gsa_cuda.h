@@ -124,7 +124,12 @@ GSA_API int gsa_model_register_fatbin(gsa_handle* h, const void* image, size_t l
  * (default symbols: gsa_user_factor / gsa_user_term / gsa_user_model; other names go through a PTX trampoline).  One output.
  * First/total order with Jansen1999, Sobol2007 or Homma1996 run on the separable kernel; second order and Janon2014 run on the
  * generic kernel, which evaluates the whole model through the same per-coordinate function.  Linked cubins are cached per
- * (kind, symbol, image): registering the same image on several handles / devices links once. */
+ * (kind, symbol, image): registering the same image on several handles / devices links once.
+ * An image that also carries LTO-IR (nvcc ... -gencode arch=compute_100a,code=lto_100a -gencode arch=compute_100a,code=sm_100a)
+ * and uses the default symbol name gets its function INLINED: the kernel a launch needs is LTO-linked on first use (~1.5 s once
+ * per kernel shape, cached), and runs at the speed of a built-in model instead of paying a call per coordinate.
+ * Register budget: the linked kernels run 3-4 CTAs per SM, so a user function may use at most 128 (generic) / 168 (separable)
+ * registers -- nvJitLink refuses the link otherwise and the message says so (build the model with -maxrregcount=128). */
 enum { GSA_USER_GENERIC = 0, GSA_USER_PRODUCT = 1, GSA_USER_ADDITIVE = 2 };
 GSA_API int gsa_model_register_separable(gsa_handle* h, const void* image, size_t len, const char* symbol, int kind, int* model_id);
 
@@ -134,7 +139,8 @@ GSA_API int gsa_model_register_separable(gsa_handle* h, const void* image, size_
  * (num_mats*d)-dimensional Gray-code Sobol sequence (Joe-Kuo 21201 table), first emitted 0-based index
  * 2^floor(log2 n), split by rows into num_mats matrices of d x n, scaled (ub-lb)*u + lb.
  * Writes columns [col0, col0+ncols) of every matrix: out[m] has d*ncols doubles (m < num_mats);
- * `out` is an array of num_mats pointers, all in `out_location`.  Bit-exact. */
+ * `out` is an array of num_mats pointers, all in `out_location`.  Bit-exact.  n < 2^31: the sequence index of the last point,
+ * 2^floor(log2 n) + n - 1, must fit the 32-bit Gray code the reference's generator (Sobol.jl) uses. */
 GSA_API int gsa_sobol_design(gsa_handle* h, int64_t n, int d, int num_mats, const double* lb, const double* ub,
                      int64_t col0, int64_t ncols, double* const* out, int out_location);
 

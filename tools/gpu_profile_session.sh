@@ -22,9 +22,13 @@ python tools/make_traffic_json.py $O/r2_prod.ncu-rep 24 > $O/r2_traffic.json 2>>
 reduce r2_prod; rm -f $O/r2_prod.ncu-rep
 cat $O/r2_traffic.json
 # 3. user models: generic kernel (FP64 pipe evidence) and separable kernels
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:gsa_user -c 8 -f -o $O/r2_user python tools/user_model_probe.py > $O/r2_ncu_user.log 2>&1
-reduce r2_user; rm -f $O/r2_user.ncu-rep
-cat $O/r2_user_summary.txt | head -40
+python tools/user_model_probe.py > $O/r2_user_models.jsonl 2> $O/r2_user_models.err
+for route in generic separable separable_lto; do for dd in 20 100; do
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:gsa_user --launch-skip 1 -c 1 -f -o $O/r2_u_${route}_$dd \
+      python tools/user_model_probe.py --only $route,$dd > $O/r2_ncu_user.log 2>&1
+  reduce r2_u_${route}_$dd; rm -f $O/r2_u_${route}_$dd.ncu-rep
+done; done
+cat $O/r2_u_*_summary.txt | grep -E "^##|time=" | cut -c1-260
 # 4. every other hot kernel
 timeout 600 ncu --set full --clock-control none --import-source on -f -o $O/r2_prof python tools/profile_run.py > $O/r2_ncu_prof.log 2>&1
 reduce r2_prof; rm -f $O/r2_prof.ncu-rep
