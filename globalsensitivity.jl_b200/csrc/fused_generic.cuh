@@ -20,6 +20,7 @@
 #pragma once
 #include "gsa_common.cuh"
 #include "models.cuh"
+#include "tail.cuh"
 
 namespace gsa {
 
@@ -37,6 +38,7 @@ struct GenericArgs {
     double* tile_rec;  // [ntiles][nout][nstat]
     TileGeom g;
     int d, np, nout, nstat, est, t_begin, t_end;
+    TailArgs tail;     // tail.counters != nullptr -> stage 2, exchange and host copy inside this launch (tail.cuh)
 };
 
 // shared memory: per warp a transposition tile and a record of nout*nstat doubles
@@ -189,6 +191,7 @@ __device__ __forceinline__ void fused_generic_body(const GenericArgs& a) {
             }
         }
         __syncthreads();
+        if (a.tail.counters) fused_tail_tile_done(a.tail, t);
     }
 }
 

@@ -26,6 +26,7 @@
 // Operands of future steps are in flight as cp.async copies (per-thread ring / per-warp tiles): no block-wide barrier.
 #pragma once
 #include "gsa_common.cuh"
+#include "tail.cuh"
 
 namespace gsa {
 
@@ -45,6 +46,7 @@ struct PairsArgs {
     double* tile_rec;     // [ntiles][nout][nstat]
     TileGeom g;
     int d, nstat, est, t_begin, t_end;
+    TailArgs tail;        // product sources: tail.counters != nullptr -> stage 2, exchange and host copy inside this launch (tail.cuh)
 };
 
 #ifdef __CUDACC__
@@ -102,6 +104,9 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
         double* rec = a.tile_rec + ((size_t)tile * (YSRC ? a.nout : 1) + o) * a.nstat;
         if (c1 <= c0) {
             for (int i = threadIdx.x; i < a.nstat; i += PMMA_THREADS) rec[i] = 0.0;
+            if constexpr (!YSRC) {
+                if (a.tail.counters) fused_tail_tile_done(a.tail, tile);   // an empty tile signs off too
+            }
             continue;
         }
         const int r = a.g.rep_first + tile / a.g.tpr;
@@ -474,6 +479,9 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
                 rec[0] = S.hi; rec[1] = S.lo; rec[2] = Q.hi; rec[3] = Q.lo;
                 rec[4] = SA.hi; rec[5] = SA.lo; rec[6] = QA.hi; rec[7] = QA.lo;
             }
+        }
+        if constexpr (!YSRC) {
+            if (a.tail.counters) fused_tail_tile_done(a.tail, tile);   // (fences and barriers inside: the record is complete)
         }
     }
 }

@@ -11,6 +11,7 @@
 // (shared-memory transpose, 16 accumulators per pass).  No atomics, bitwise reproducible.
 #pragma once
 #include "gsa_common.cuh"
+#include "tail.cuh"
 #include "models.cuh"
 
 namespace gsa {
@@ -211,6 +212,7 @@ struct SmallArgs {
     double* tile_rec;   // [ntiles][nout][nstat]
     TileGeom g;         // fused sources: global columns; Y source: col_lo = 0, col_hi = nboot*n, rep_first = 0
     int nout, nstat, est, t_begin, t_end;
+    TailArgs tail;      // fused sources: tail.counters != nullptr -> stage 2, exchange and host copy inside this launch (tail.cuh)
 };
 
 // dynamic shared memory: the staging ring, re-used by the tile flush ([SMALL_CH][SMALL_THREADS+1] doubles), + 8 dd slots per warp
@@ -347,6 +349,9 @@ __global__ void __launch_bounds__(SMALL_THREADS) small_kernel(SmallArgs<Src> a) 
             rec[2 * tid + 1] = s.lo;
         }
         __syncthreads();
+        if constexpr (!Src::kIsY) {
+            if (a.tail.counters) fused_tail_tile_done(a.tail, tile);
+        }
     }
 }
 

@@ -318,7 +318,11 @@ static int wait_tail(gsa_handle* h, const TailRequest& tr) {
             }
             _mm_pause();
         }
-        if (*f < want) GSA_CUDA(cudaStreamSynchronize(h->stream));
+        if (*f < want) {
+            GSA_CUDA(cudaStreamSynchronize(h->stream));
+            if (*f < want && !(tr.exchange && h->peer && h->peer->status_host && *h->peer->status_host))
+                return fail(GSA_ERR_CUDA, "the fused kernel finished without raising its result flag (internal error: tile sign-off incomplete)");
+        }
     } else {
         GSA_CUDA(cudaStreamSynchronize(h->stream));
     }

@@ -5,7 +5,7 @@ namespace gsa {
 
 template <int D, bool SECOND>
 static int go(gsa_handle* h, int est, const double* Y, int64_t n, int nout, int step, const TileGeom& g, int nstat, double* tile_rec, int* occ) {
-    SmallArgs<YSource<D, SECOND>> a;
+    SmallArgs<YSource<D, SECOND>> a{};
     a.src.Y = Y; a.src.n = n; a.src.nout = nout; a.src.step = step;
     a.tile_rec = tile_rec; a.g = g; a.nout = nout; a.nstat = nstat; a.est = est; a.t_begin = 0; a.t_end = g.ntiles;
     if (est == GSA_EI_JANSEN1999) return launch_small<YSource<D, SECOND>, D, SECOND, true>(h, a, occ);
