@@ -41,7 +41,8 @@ struct FusedPlan {
     double* out_partials = nullptr;
     double* rec_base = nullptr;   // where the tile records go: h->tile_rec, or straight into `partials` when a replicate is one tile
     TailArgs tail{};              // tail.counters != nullptr: stage 2 + exchange + host copy happen inside the launch (tail.cuh)
-    bool supports_tail() const { return kind != PLAN_LINEAR; }   // (the linear path has its own moment reduction)
+    // (the linear path has its own moment reduction; the thread-per-sample register kernels cannot spare the registers)
+    bool supports_tail() const { return kind == PLAN_PRODUCT || kind == PLAN_PAIRS_MMA || kind == PLAN_GENERIC; }
 
     int prepare(gsa_handle* h, const double* params, int np);
     int launch(gsa_handle* h, const double* A, const double* B, const TileGeom& g, int t0, int t1);
@@ -191,6 +192,7 @@ static int plan_product(gsa_handle* h, FusedPlan* p) {
         }
     }
     p->resident = std::max(1, nb) * h->sm_count;
+    if (const char* e = getenv("GSA_TILES_PER_CTA")) p->tiles_per_cta = std::max(1, atoi(e));   // tuning knob
     p->ts_min = p->ts_gran = PROD_THREADS / p->prod_T;
     return GSA_OK;
 }

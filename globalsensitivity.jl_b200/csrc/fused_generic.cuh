@@ -199,7 +199,7 @@ __device__ __forceinline__ void fused_generic_body(const GenericArgs& a) {
 // (CTAs are at most four warps, one per SM sub-partition: see plan_generic)
 constexpr int GENERIC_THREADS_MAX = 128;
 template <class Model, bool SECOND, bool LARGE>
-__global__ void __launch_bounds__(GENERIC_THREADS_MAX, 5) fused_generic_kernel(GenericArgs a) {
+__global__ void __launch_bounds__(GENERIC_THREADS_MAX, 5) fused_generic_kernel(const __grid_constant__ GenericArgs a) {
     fused_generic_body<Model, SECOND, LARGE ? GENERIC_DMAX : 32, LARGE ? GENERIC_ACC_L : GENERIC_ACC_S>(a);
 }
 

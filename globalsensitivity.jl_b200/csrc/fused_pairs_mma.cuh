@@ -73,7 +73,7 @@ inline size_t pm_smem_bytes(size_t ring_doubles, int NB) { return sizeof(double)
 // NB = 8-coordinate blocks (d <= 8*NB); UN = warp steps per load group (PRODUCT) or d itself (PRODUCT_TILE); ST = stages in flight
 enum { PM_SRC_PRODUCT = 0, PM_SRC_Y = 1, PM_SRC_PRODUCT_TILE = 2 };
 template <int SRC, int NB, int UN, int ST, bool JANSEN = true>
-__global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
+__global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(const __grid_constant__ PairsArgs a) {
     constexpr bool YSRC = SRC == PM_SRC_Y, TSRC = SRC == PM_SRC_PRODUCT_TILE;
     static_assert(!TSRC || NB == 1, "thread-per-sample evaluation: one 8-coordinate block (UN carries d)");
     constexpr int DU = 8 * NB, NP = NB * (NB + 1) / 2;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
         if (c1 <= c0) {
             for (int i = threadIdx.x; i < a.nstat; i += PMMA_THREADS) rec[i] = 0.0;
             if constexpr (!YSRC) {
-                if (a.tail.counters) fused_tail_tile_done(a.tail, tile);   // an empty tile signs off too
+                if (a.tail.counters) fused_tail_tile_done_call(a.tail, tile);   // an empty tile signs off too
             }
             continue;
         }
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
             }
         }
         if constexpr (!YSRC) {
-            if (a.tail.counters) fused_tail_tile_done(a.tail, tile);   // (fences and barriers inside: the record is complete)
+            if (a.tail.counters) fused_tail_tile_done_call(a.tail, tile);   // (fences and barriers inside: the record is complete)
         }
     }
 }

@@ -338,12 +338,12 @@ __device__ __forceinline__ void fused_product_body(const ProductArgs& a) {
 }
 
 template <int T, int CPL, bool GEN, bool JANSEN = true>
-__global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fused_product_kernel(ProductArgs a) {
+__global__ void __launch_bounds__(PROD_THREADS, GEN ? PROD_GEN_MINBLOCKS : 3) fused_product_kernel(const __grid_constant__ ProductArgs a) {
     fused_product_body<T, CPL, GEN, JANSEN, SobolGFactor, false>(a);
 }
 // pair-load variant (even d, aligned rows)
 template <int T, int CPL, bool JANSEN = true>
-__global__ void __launch_bounds__(PROD_THREADS, 3) fused_product_kernel_v2(ProductArgs a) {
+__global__ void __launch_bounds__(PROD_THREADS, 3) fused_product_kernel_v2(const __grid_constant__ ProductArgs a) {
     fused_product_body<T, CPL, false, JANSEN, SobolGFactor, false, 2>(a);
 }
 

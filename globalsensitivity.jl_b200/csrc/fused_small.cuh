@@ -223,7 +223,7 @@ constexpr size_t small_smem_bytes() {
 }
 
 template <class Src, int D, bool SECOND, bool JANSEN>
-__global__ void __launch_bounds__(SMALL_THREADS) small_kernel(SmallArgs<Src> a) {
+__global__ void __launch_bounds__(SMALL_THREADS) small_kernel(const __grid_constant__ SmallArgs<Src> a) {
     using Sh = SmallShape<D, SECOND>;
     constexpr int NE = JANSEN ? 1 : 3;
     constexpr int NACC = D + NE * D + Sh::NPAIR;
@@ -349,9 +349,8 @@ __global__ void __launch_bounds__(SMALL_THREADS) small_kernel(SmallArgs<Src> a) 
             rec[2 * tid + 1] = s.lo;
         }
         __syncthreads();
-        if constexpr (!Src::kIsY) {
-            if (a.tail.counters) fused_tail_tile_done(a.tail, tile);
-        }
+        // (no fused tail here: these kernels live on their register budget -- 80 registers, three CTAs per SM -- and are
+        //  launch-latency-sized anyway; stage 2 and the exchange follow as launches of their own)
     }
 }
 

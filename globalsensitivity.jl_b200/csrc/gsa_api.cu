@@ -468,7 +468,15 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         const int t_lo = (int)((col0 - (int64_t)g.rep_first * n) / g.ts);
         const int t_hi = (rep_last - g.rep_first) * g.tpr + (int)((valid_hi - 1 - (int64_t)rep_last * n) / g.ts) + 1;
         // one launch per step: stage 2, the exchange and the host copy run in the kernel's last CTA (tail.cuh)
-        const bool fuse = want_tail && plan.supports_tail() && !host_in && t_hi > t_lo && !getenv("GSA_NO_TAIL");
+        // (a replicate of more than TAIL_G groups = 1024 tiles, or an exchange of more than 4096 doubles -- the fused exchange is
+        // the work of ONE CTA -- take the classic launches)
+        // Measured (tools/tail_probe.py, profiles/r2_tail_probe.txt): the in-kernel tree costs ~20-30 us for one replicate of
+        // 444-888 tiles -- about what reduce_tiles + the copy cost as launches of their own, minus their launch gaps and the
+        // host's stream synchronisation -- but 2-3x more than the classic sequence for many replicates of few tiles (every
+        // replicate's finisher pays its own fences and host write).  So: few replicates only.
+        const bool fuse = want_tail && plan.supports_tail() && !host_in && t_hi > t_lo && !getenv("GSA_NO_TAIL") &&
+                          tail_groups_per_replicate(g.tpr) <= TAIL_G && (!tr->exchange || count <= 4096) &&
+                          (nrep <= 4 || getenv("GSA_FORCE_TAIL"));
         if (fuse) {
             TailArgs& t = plan.tail;
             const size_t cbytes = sizeof(unsigned int) * tail_counter_count(nrep, g.tpr);
@@ -487,6 +495,7 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
             t.reduce = direct ? 0 : 1;
             t.recsz = recsz; t.nstat = nstat; t.tpr = g.tpr; t.rep_first = g.rep_first; t.nrep = nrep; t.nboot = o->nboot;
             t.t_lo = t_lo; t.t_hi = t_hi;
+            t.dbg = getenv("GSA_TAIL_DBG") ? atoi(getenv("GSA_TAIL_DBG")) : 0;
             t.exchange = 0;
             t.host_out = nullptr;
             if (tr->exchange) {
