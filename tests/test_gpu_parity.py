@@ -809,7 +809,9 @@ def test_one_call_step_with_fused_tail(monkeypatch):
         fused = step.run()
         fused2 = step.run()                                 # the counters and the flag are monotonic over launches
         launches = h.last_timing()[2]
-        assert launches == 1, launches
+        # one launch for a few long replicates; many short replicates go through the classic launches (kernel + stage 2), which
+        # are cheaper there (profiles/r2_tail_probe.txt)
+        assert launches == (1 if nboot <= 4 else 2), (nboot, launches)
         h.set_stream(None)
         monkeypatch.setenv("GSA_NO_TAIL", "1")
         classic = g.gsa(model, method, A, B, batch=True, Ei_estimator=est)
