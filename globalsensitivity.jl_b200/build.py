@@ -77,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # ... and the separable kernels once more as LTO-IR: when the user's image carries LTO-IR too (code=lto_100a) and uses the
     # default symbol name, nvJitLink inlines the per-coordinate function into the kernel that is actually launched (-kernels-used)
     lto_procs = []
-    for tag, kind in (("product", 1), ("additive", 2)):
+    for tag, kind in (("kernel", 0), ("product", 1), ("additive", 2)):
         ucu = os.path.join(obj_dir, f"user_{tag}.cu")
         ltoir = os.path.join(obj_dir, f"user_{tag}.ltoir")
         cmd = [nvcc(), "-ccbin", HOST_CXX, "-std=c++17", "-O3", "-dlto", "-ltoir", "-arch=sm_100a", "-rdc=true", "-I", CSRC,

@@ -76,7 +76,7 @@ static int plan_generic(gsa_handle* h, FusedPlan* p) {
     if (user) {
         const int idx = p->model - GSA_MODEL_USER_BASE;
         if (idx >= (int)h->user_models.size()) return fail(GSA_ERR_INVALID, "unknown user model id %d for this handle", p->model);
-        k = (const void*)h->user_models[idx].k_generic[p->second ? 1 : 0][large ? 1 : 0];
+        k = user_generic_kernel(h, p->model, p->second, large);
     } else if (p->second) {
         k = large ? (const void*)generic_kernel_for<true, true>(p->model) : (const void*)generic_kernel_for<true, false>(p->model);
     } else {

@@ -70,6 +70,7 @@ struct UserModelEntry {
 };
 int register_user_model(gsa_handle* h, const void* image, size_t len, const char* symbol, int kind, int nout, int* model_id);
 int user_separable_kernel(gsa_handle* h, int model_id, int T, int cpl, bool jansen, const void** kernel);
+const void* user_generic_kernel(gsa_handle* h, int model_id, bool second, bool large);   // LTO-linked (model inlined) when possible
 struct PeerState;                          // peer.cu: mailboxes of the NVLink all-reduce
 void peer_release_handle(gsa_handle* h);   // frees h->peer (no-op when absent)
 }  // namespace gsa

@@ -20,6 +20,8 @@ extern "C" const unsigned char gsa_user_product_blob[];
 extern "C" const unsigned char gsa_user_product_blob_end[];
 extern "C" const unsigned char gsa_user_additive_blob[];
 extern "C" const unsigned char gsa_user_additive_blob_end[];
+extern "C" const unsigned char gsa_user_kernel_lto_blob[];
+extern "C" const unsigned char gsa_user_kernel_lto_blob_end[];
 extern "C" const unsigned char gsa_user_product_lto_blob[];
 extern "C" const unsigned char gsa_user_product_lto_blob_end[];
 extern "C" const unsigned char gsa_user_additive_lto_blob[];
@@ -212,8 +214,8 @@ int register_user_model(gsa_handle* h, const void* image, size_t len, const char
         // LTO needs the default symbol name (a PTX trampoline cannot be inlined) and an image that carries LTO-IR; whether it
         // does is found out at the first launch (user_separable_kernel)
         const char* env = getenv("GSA_USER_LTO");
-        um.try_lto = kind != GSA_USER_GENERIC && !(env && atoi(env) == 0) &&
-                     strcmp(symbol, kind == GSA_USER_PRODUCT ? "gsa_user_factor" : "gsa_user_term") == 0;
+        um.try_lto = !(env && atoi(env) == 0) &&
+                     strcmp(symbol, kind == GSA_USER_PRODUCT ? "gsa_user_factor" : kind == GSA_USER_ADDITIVE ? "gsa_user_term" : "gsa_user_model") == 0;
         if (um.try_lto) um.image.assign(static_cast<const char*>(image), static_cast<const char*>(image) + len);
         GSA_CUDA(cudaLibraryLoadData(&um.lib, cubin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
         cudaError_t ce = cudaSuccess;
@@ -243,9 +245,8 @@ static bool link_separable_lto(const UserModelEntry& um, const char* kernel_name
     const std::string used = std::string("-kernels-used=") + kernel_name;
     const char* opts[] = {"-arch=sm_100a", "-lto", used.c_str()};
     if (a.Create(&jl, 3, opts)) return false;
-    const bool prod = um.kind == GSA_USER_PRODUCT;
-    const unsigned char* blob = prod ? gsa_user_product_lto_blob : gsa_user_additive_lto_blob;
-    const unsigned char* blob_end = prod ? gsa_user_product_lto_blob_end : gsa_user_additive_lto_blob_end;
+    const unsigned char* blob = um.kind == GSA_USER_PRODUCT ? gsa_user_product_lto_blob : um.kind == GSA_USER_ADDITIVE ? gsa_user_additive_lto_blob : gsa_user_kernel_lto_blob;
+    const unsigned char* blob_end = um.kind == GSA_USER_PRODUCT ? gsa_user_product_lto_blob_end : um.kind == GSA_USER_ADDITIVE ? gsa_user_additive_lto_blob_end : gsa_user_kernel_lto_blob_end;
     bool ok = a.AddData(jl, NVJL_INPUT_LTOIR, blob, (size_t)(blob_end - blob), "gsa_separable_ltoir") == 0 &&
               a.AddData(jl, NVJL_INPUT_ANY, um.image.data(), um.image.size(), "user_model") == 0 && a.Complete(jl) == 0;
     if (ok) {
@@ -266,6 +267,57 @@ static bool link_separable_lto(const UserModelEntry& um, const char* kernel_name
     return ok;
 }
 
+// kernel `name` of user model `um`, LTO-linked against the user's image on first use (the model inlined); nullptr when the image
+// carries no LTO-IR / the symbol is not the default one / the link fails: the caller then takes the call-based kernel
+static cudaKernel_t user_lto_kernel(UserModelEntry& um, const char* name) {
+    for (const auto& kv : um.sep_kernels)
+        if (kv.first == name) return kv.second;
+    cudaKernel_t k = nullptr;
+    if (um.try_lto) {
+        // linked once per (image, kernel) in the process, loaded once per handle
+        const uint64_t hash = fnv1a(um.image.data(), um.image.size());
+        const std::string key = std::string("lto:") + name;
+        const std::vector<char>* cubin = nullptr;
+        std::lock_guard<std::mutex> lk(g_linked_mu);
+        for (const LinkedCubin& c : g_linked)
+            if (c.kind == um.kind && c.hash == hash && c.len == um.image.size() && c.symbol == key) cubin = &c.cubin;
+        if (!cubin) {
+            LinkedCubin c;
+            c.kind = um.kind; c.symbol = key; c.hash = hash; c.len = um.image.size();
+            if (link_separable_lto(um, name, &c.cubin)) {
+                g_linked.push_back(std::move(c));
+                cubin = &g_linked.back().cubin;
+            }
+        }
+        if (cubin) {
+            cudaLibrary_t lib = nullptr;
+            if (cudaLibraryLoadData(&lib, cubin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
+                cudaLibraryGetKernel(&k, lib, name) == cudaSuccess) {
+                um.lto_libs.push_back(lib);
+            } else {
+                cudaGetLastError();
+                if (lib) cudaLibraryUnload(lib);
+                k = nullptr;
+            }
+        }
+        if (!k) um.try_lto = false;   // no LTO-IR in the image (or an old linker): the call-based kernels from here on
+        if (getenv("GSA_DEBUG")) fprintf(stderr, "[gsa] user kernel %s: %s\n", name, k ? "LTO (model inlined)" : "call-based");
+    }
+    if (k) um.sep_kernels.emplace_back(name, k);
+    return k;
+}
+
+// the generic kernel of a user model: [second order][large instantiation]
+const void* user_generic_kernel(gsa_handle* h, int model_id, bool second, bool large) {
+    const int idx = model_id - GSA_MODEL_USER_BASE;
+    if (idx < 0 || idx >= (int)h->user_models.size()) return nullptr;
+    UserModelEntry& um = h->user_models[idx];
+    static const char* const names[2][2] = {{"gsa_user_fused_first_s", "gsa_user_fused_first_l"}, {"gsa_user_fused_second_s", "gsa_user_fused_second_l"}};
+    if (um.kind == GSA_USER_GENERIC)
+        if (cudaKernel_t k = user_lto_kernel(um, names[second ? 1 : 0][large ? 1 : 0])) return (const void*)k;
+    return (const void*)um.k_generic[second ? 1 : 0][large ? 1 : 0];
+}
+
 // the O(d) kernel of a separable user model for (lanes per sample, coordinates per lane, Jansen | other one-term estimators)
 int user_separable_kernel(gsa_handle* h, int model_id, int T, int cpl, bool jansen, const void** kernel) {
     const int idx = model_id - GSA_MODEL_USER_BASE;
@@ -274,46 +326,15 @@ int user_separable_kernel(gsa_handle* h, int model_id, int T, int cpl, bool jans
     if (um.kind == GSA_USER_GENERIC) return fail(GSA_ERR_INVALID, "user model %d is not separable", model_id);
     char name[64];
     snprintf(name, sizeof(name), "gsa_user_sep_T%d_C%d_J%d", T, cpl, jansen ? 1 : 0);
-    for (const auto& kv : um.sep_kernels)
-        if (kv.first == name) {
-            *kernel = (const void*)kv.second;
-            return GSA_OK;
+    cudaKernel_t k = user_lto_kernel(um, name);
+    if (!k) {
+        for (const auto& kv : um.sep_kernels)
+            if (kv.first == name) k = kv.second;
+        if (!k) {
+            GSA_CUDA(cudaLibraryGetKernel(&k, um.lib, name));
+            um.sep_kernels.emplace_back(name, k);
         }
-    cudaKernel_t k = nullptr;
-    if (um.try_lto) {
-        // linked once per (image, kernel) in the process, loaded once per handle
-        const uint64_t hash = fnv1a(um.image.data(), um.image.size());
-        const std::string key = std::string("lto:") + name;
-        const std::vector<char>* cubin = nullptr;
-        {
-            std::lock_guard<std::mutex> lk(g_linked_mu);
-            for (const LinkedCubin& c : g_linked)
-                if (c.kind == um.kind && c.hash == hash && c.len == um.image.size() && c.symbol == key) cubin = &c.cubin;
-            if (!cubin) {
-                LinkedCubin c;
-                c.kind = um.kind; c.symbol = key; c.hash = hash; c.len = um.image.size();
-                if (link_separable_lto(um, name, &c.cubin)) {
-                    g_linked.push_back(std::move(c));
-                    cubin = &g_linked.back().cubin;
-                }
-            }
-            if (cubin) {
-                cudaLibrary_t lib = nullptr;
-                if (cudaLibraryLoadData(&lib, cubin->data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
-                    cudaLibraryGetKernel(&k, lib, name) == cudaSuccess) {
-                    um.lto_libs.push_back(lib);
-                } else {
-                    cudaGetLastError();
-                    if (lib) cudaLibraryUnload(lib);
-                    k = nullptr;
-                }
-            }
-        }
-        if (!k) um.try_lto = false;   // no LTO-IR in the image (or an old linker): the call-based kernels from here on
-        if (getenv("GSA_DEBUG")) fprintf(stderr, "[gsa] separable kernel %s: %s\n", name, k ? "LTO (per-coordinate function inlined)" : "call-based");
     }
-    if (!k) GSA_CUDA(cudaLibraryGetKernel(&k, um.lib, name));
-    um.sep_kernels.emplace_back(name, k);
     *kernel = (const void*)k;
     return GSA_OK;
 }

@@ -811,7 +811,7 @@ def test_one_call_step_with_fused_tail(monkeypatch):
         launches = h.last_timing()[2]
         # one launch for a few long replicates; many short replicates go through the classic launches (kernel + stage 2), which
         # are cheaper there (profiles/r2_tail_probe.txt)
-        assert launches == (1 if nboot <= 4 else 2), (nboot, launches)
+        assert launches == 1 if nboot <= 4 else launches in (1, 2), (nboot, launches)     # (one tile per replicate needs no stage 2 either)
         h.set_stream(None)
         monkeypatch.setenv("GSA_NO_TAIL", "1")
         classic = g.gsa(model, method, A, B, batch=True, Ei_estimator=est)
