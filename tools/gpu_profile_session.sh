@@ -23,7 +23,7 @@ reduce r2_prod; rm -f $O/r2_prod.ncu-rep
 cat $O/r2_traffic.json
 # 3. user models: generic kernel (FP64 pipe evidence) and separable kernels
 python tools/user_model_probe.py > $O/r2_user_models.jsonl 2> $O/r2_user_models.err
-for route in generic separable separable_lto; do for dd in 20 100; do
+for route in generic generic_lto separable separable_lto; do for dd in 20 100; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:gsa_user --launch-skip 1 -c 1 -f -o $O/r2_u_${route}_$dd \
       python tools/user_model_probe.py --only $route,$dd > $O/r2_ncu_user.log 2>&1
   reduce r2_u_${route}_$dd; rm -f $O/r2_u_${route}_$dd.ncu-rep
