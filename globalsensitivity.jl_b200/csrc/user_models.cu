@@ -160,6 +160,23 @@ static int link_user_image(const void* image, size_t len, const char* symbol, in
     const char* target = "gsa_user_model";
     if (kind == GSA_USER_PRODUCT) { blob = gsa_user_product_blob; blob_end = gsa_user_product_blob_end; target = "gsa_user_factor"; }
     if (kind == GSA_USER_ADDITIVE) { blob = gsa_user_additive_blob; blob_end = gsa_user_additive_blob_end; target = "gsa_user_term"; }
+    if (strcmp(symbol, target) != 0) {
+        // A trampoline maps `symbol` to the name the kernels call.  If the image defines that name ITSELF the link would see it
+        // twice -- and nvJitLink 12.9 segfaults on that "Multiple definition" error when an -lto link has run earlier in the
+        // process (reproduced with the plain API, no GPU involved).  So look first: kernels + image alone link cleanly exactly when
+        // the image already provides the name.
+        nvJitLinkHandle probe = nullptr;
+        if (a.Create(&probe, 1, opts) == 0) {
+            const bool defines = a.AddData(probe, NVJL_INPUT_CUBIN, blob, (size_t)(blob_end - blob), "gsa_user_kernel") == 0 &&
+                                 a.AddData(probe, NVJL_INPUT_ANY, image, len, "user_model") == 0 && a.Complete(probe) == 0;
+            a.Destroy(&probe);
+            if (defines) {
+                a.Destroy(&jl);
+                return fail(GSA_ERR_INVALID, "nvJitLink: the image already defines '%s'; registering it as '%s' would define that name twice "
+                                             "(register it under '%s', or rename the function)", target, symbol, target);
+            }
+        }
+    }
     if ((e = a.AddData(jl, NVJL_INPUT_CUBIN, blob, (size_t)(blob_end - blob), "gsa_user_kernel"))) return log_and_fail("nvJitLinkAddData(kernel)", e);
     if ((e = a.AddData(jl, NVJL_INPUT_ANY, image, len, "user_model"))) return log_and_fail("nvJitLinkAddData(user image)", e);
     std::string ptx;
