@@ -41,8 +41,9 @@ struct FusedPlan {
     double* out_partials = nullptr;
     double* rec_base = nullptr;   // where the tile records go: h->tile_rec, or straight into `partials` when a replicate is one tile
     TailArgs tail{};              // tail.counters != nullptr: stage 2 + exchange + host copy happen inside the launch (tail.cuh)
-    // (the linear path has its own moment reduction; the thread-per-sample register kernels cannot spare the registers)
-    bool supports_tail() const { return kind == PLAN_PRODUCT || kind == PLAN_PAIRS_MMA || kind == PLAN_GENERIC; }
+    // (the linear path has its own moment reduction; the thread-per-sample register kernels cannot spare the registers; the pair
+    //  kernels lost 8 % of their main loop to it)
+    bool supports_tail() const { return kind == PLAN_PRODUCT || kind == PLAN_GENERIC; }
 
     int prepare(gsa_handle* h, const double* params, int np);
     int launch(gsa_handle* h, const double* A, const double* B, const TileGeom& g, int t0, int t1);
@@ -352,9 +353,9 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         GSA_CUDA(cudaLaunchKernel(kernel, dim3(grid), dim3(threads), kargs, smem, h->stream));   // also takes cudaKernel_t handles
     }
     else if (kind == PLAN_SMALL_ISHIGAMI)
-        return launch_small_ishigami(h, d, second, est, A, B, pa, pb, g, t0, t1, nstat, recs, nullptr, &tail);
+        return launch_small_ishigami(h, d, second, est, A, B, pa, pb, g, t0, t1, nstat, recs, nullptr);
     else if (kind == PLAN_SMALL_SOBOLG)
-        return launch_small_sobolg(h, d, second, est, A, B, h->aux.as<double2>(), g, t0, t1, nstat, recs, nullptr, &tail);
+        return launch_small_sobolg(h, d, second, est, A, B, h->aux.as<double2>(), g, t0, t1, nstat, recs, nullptr);
     else if (kind == PLAN_LINEAR) {
         // moments per tile -> moments per replicate of this launch -> records added to `partials` (no tile records, no stage 2)
         const int gs = lin_gram_size(lin_NB);
@@ -381,7 +382,6 @@ inline int FusedPlan::launch(gsa_handle* h, const double* A, const double* B, co
         PairsArgs a{};
         a.A = A; a.B = B; a.coef = h->aux.as<double2>(); a.tile_rec = recs; a.nout = 1;
         a.g = g; a.d = d; a.nstat = nstat; a.est = est; a.t_begin = t0; a.t_end = t1;
-        a.tail = tail;
         void* kargs[] = {&a};
         const bool aligned = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
         if (pairs_tile && !aligned) GSA_CUDA(cudaLaunchKernel(kernel_alt, dim3(grid), dim3(threads), kargs, smem_alt, h->stream));

@@ -26,7 +26,6 @@
 // Operands of future steps are in flight as cp.async copies (per-thread ring / per-warp tiles): no block-wide barrier.
 #pragma once
 #include "gsa_common.cuh"
-#include "tail.cuh"
 
 namespace gsa {
 
@@ -46,7 +45,6 @@ struct PairsArgs {
     double* tile_rec;     // [ntiles][nout][nstat]
     TileGeom g;
     int d, nstat, est, t_begin, t_end;
-    TailArgs tail;        // product sources: tail.counters != nullptr -> stage 2, exchange and host copy inside this launch (tail.cuh)
 };
 
 #ifdef __CUDACC__
@@ -73,7 +71,7 @@ inline size_t pm_smem_bytes(size_t ring_doubles, int NB) { return sizeof(double)
 // NB = 8-coordinate blocks (d <= 8*NB); UN = warp steps per load group (PRODUCT) or d itself (PRODUCT_TILE); ST = stages in flight
 enum { PM_SRC_PRODUCT = 0, PM_SRC_Y = 1, PM_SRC_PRODUCT_TILE = 2 };
 template <int SRC, int NB, int UN, int ST, bool JANSEN = true>
-__global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(const __grid_constant__ PairsArgs a) {
+__global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
     constexpr bool YSRC = SRC == PM_SRC_Y, TSRC = SRC == PM_SRC_PRODUCT_TILE;
     static_assert(!TSRC || NB == 1, "thread-per-sample evaluation: one 8-coordinate block (UN carries d)");
     constexpr int DU = 8 * NB, NP = NB * (NB + 1) / 2;
@@ -104,9 +102,6 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(const __grid_co
         double* rec = a.tile_rec + ((size_t)tile * (YSRC ? a.nout : 1) + o) * a.nstat;
         if (c1 <= c0) {
             for (int i = threadIdx.x; i < a.nstat; i += PMMA_THREADS) rec[i] = 0.0;
-            if constexpr (!YSRC) {
-                if (a.tail.counters) fused_tail_tile_done_call(a.tail, tile);   // an empty tile signs off too
-            }
             continue;
         }
         const int r = a.g.rep_first + tile / a.g.tpr;
@@ -480,9 +475,8 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(const __grid_co
                 rec[4] = SA.hi; rec[5] = SA.lo; rec[6] = QA.hi; rec[7] = QA.lo;
             }
         }
-        if constexpr (!YSRC) {
-            if (a.tail.counters) fused_tail_tile_done_call(a.tail, tile);   // (fences and barriers inside: the record is complete)
-        }
+        // (no fused tail here: carrying it cost the main loop 8 % on config 3 -- 98 -> 107 us -- for a ~10 us saving on the host;
+        //  stage 2 and the exchange follow as launches of their own)
     }
 }
 #endif  // __CUDACC__

@@ -11,7 +11,6 @@
 // (shared-memory transpose, 16 accumulators per pass).  No atomics, bitwise reproducible.
 #pragma once
 #include "gsa_common.cuh"
-#include "tail.cuh"
 #include "models.cuh"
 
 namespace gsa {
@@ -212,7 +211,6 @@ struct SmallArgs {
     double* tile_rec;   // [ntiles][nout][nstat]
     TileGeom g;         // fused sources: global columns; Y source: col_lo = 0, col_hi = nboot*n, rep_first = 0
     int nout, nstat, est, t_begin, t_end;
-    TailArgs tail;      // fused sources: tail.counters != nullptr -> stage 2, exchange and host copy inside this launch (tail.cuh)
 };
 
 // dynamic shared memory: the staging ring, re-used by the tile flush ([SMALL_CH][SMALL_THREADS+1] doubles), + 8 dd slots per warp
@@ -223,7 +221,7 @@ constexpr size_t small_smem_bytes() {
 }
 
 template <class Src, int D, bool SECOND, bool JANSEN>
-__global__ void __launch_bounds__(SMALL_THREADS) small_kernel(const __grid_constant__ SmallArgs<Src> a) {
+__global__ void __launch_bounds__(SMALL_THREADS) small_kernel(SmallArgs<Src> a) {
     using Sh = SmallShape<D, SECOND>;
     constexpr int NE = JANSEN ? 1 : 3;
     constexpr int NACC = D + NE * D + Sh::NPAIR;

@@ -44,10 +44,8 @@ int launch_small(gsa_handle* h, SmallArgs<Src>& a, int* occupancy_only = nullptr
 int launch_small_y(gsa_handle* h, int d, bool second, int est, const double* Y, int64_t n, int nout, int step, const TileGeom& g,
                    int nstat, double* tile_rec, int* occupancy_only = nullptr);
 int launch_small_ishigami(gsa_handle* h, int d, bool second, int est, const double* A, const double* B, double pa, double pb,
-                          const TileGeom& g, int t0, int t1, int nstat, double* tile_rec, int* occupancy_only = nullptr,
-                          const TailArgs* tail = nullptr);
+                          const TileGeom& g, int t0, int t1, int nstat, double* tile_rec, int* occupancy_only = nullptr);
 int launch_small_sobolg(gsa_handle* h, int d, bool second, int est, const double* A, const double* B, const double2* coef,
-                        const TileGeom& g, int t0, int t1, int nstat, double* tile_rec, int* occupancy_only = nullptr,
-                        const TailArgs* tail = nullptr);
+                        const TileGeom& g, int t0, int t1, int nstat, double* tile_rec, int* occupancy_only = nullptr);
 
 }  // namespace gsa

@@ -164,10 +164,6 @@ __device__ __forceinline__ void fused_tail_tile_done(const TailArgs& t, int tile
         if (tid == 0) st_release_sys(t.host_flag, t.flag_value);
     }
 }
-// out-of-line form for kernels whose main loop is register-sensitive (thread-per-sample register kernels, the pair kernels): the
-// tail's load batches then cost them no registers.  (Not for the relocatable user kernels: a separately compiled callee cannot be
-// fitted under their register cap.)
-static __device__ __noinline__ void fused_tail_tile_done_call(const TailArgs& t, int tile) { fused_tail_tile_done(t, tile); }
 #endif
 
 }  // namespace gsa
