@@ -228,6 +228,8 @@ def configs_block(g, h, peak, reps=5):
         "c2_ishigami_d3_N2^20_order2_nboot1000": dict(model=("ishigami", [7.0, 0.1]), d=3, N=1 << 20, order=[0, 1, 2], nboot=1000, lb=-np.pi, ub=np.pi),
         "c3_sobolg_d8_N2^22_order2": dict(model=("sobol_g", [0, 1, 4.5, 9, 99, 99, 99, 99]), d=8, N=1 << 22, order=[0, 1, 2], nboot=1, lb=0.0, ub=1.0),
         "c4_linear_d20_256out_N2^22": dict(model=("linear", W_c4()), d=20, N=1 << 22, order=[0, 1], nboot=1, lb=0.0, ub=1.0),
+        # not a BASELINE config: the second-order path beyond d = 8 (lane-per-coordinate source of the pair kernel)
+        "x_sobolg_d20_N2^21_order2": dict(model=("sobol_g", list(np.linspace(0, 9, 20))), d=20, N=1 << 21, order=[0, 1, 2], nboot=1, lb=0.0, ub=1.0),
     }
     for name, c in cfgs.items():
         d, N = c["d"], c["N"]

@@ -199,8 +199,7 @@ static int plan_product(gsa_handle* h, FusedPlan* p) {
 }
 
 // ---- second-order pair sums on the FP64 tensor-core path (fused_pairs_mma.cuh) ----------------------
-constexpr int PMMA_UN = 2, PMMA_ST = 4;
-inline int pmma_y_stages(int NB) { return NB == 1 ? 3 : 2; }   // warp tiles of (2+2d) * 36 doubles per stage: two CTAs per SM beat deeper rings
+constexpr int PMMA_UN = 2, PMMA_ST = 3;   // (ring depth 3 beat 4 and 6 in both sweeps, profiles/r2_pairs_sweep3.txt)
 template <bool J>
 static const void* pairs_mma_kernel_product_j(int NB, size_t* smem) {
     switch (NB) {
@@ -211,6 +210,14 @@ static const void* pairs_mma_kernel_product_j(int NB, size_t* smem) {
     }
 }
 static const void* pairs_mma_kernel_product(int NB, size_t* smem, bool jansen = true) {
+    if (const char* e = getenv("GSA_PAIRS_VARIANT")) {   // tuning experiment (NB = 3, Jansen): "UN,ST"
+        int un = 0, st = 0;
+        if (NB == 3 && jansen && sscanf(e, "%d,%d", &un, &st) == 2) {
+#define GSA_PMV(UNV, STV) if (un == UNV && st == STV) { *smem = pm_smem_bytes(pm_ring_doubles_product<3, UNV, STV>(), 3); return (const void*)pairs_mma_kernel<PM_SRC_PRODUCT, 3, UNV, STV, true>; }
+            GSA_PMV(4, 2) GSA_PMV(1, 6) GSA_PMV(2, 4) GSA_PMV(1, 8)
+#undef GSA_PMV
+        }
+    }
     return jansen ? pairs_mma_kernel_product_j<true>(NB, smem) : pairs_mma_kernel_product_j<false>(NB, smem);
 }
 constexpr int PMMA_TILE_ST = 3;
@@ -228,21 +235,29 @@ static const void* pairs_mma_kernel_tile_j(int d, size_t* smem) {
 static const void* pairs_mma_kernel_tile(int d, size_t* smem, bool jansen = true) {
     return jansen ? pairs_mma_kernel_tile_j<true>(d, smem) : pairs_mma_kernel_tile_j<false>(d, smem);
 }
+// Y source: (samples per chunk, stages) of the warp tiles.  One 8-coordinate block keeps the round-1 shape (32, 3); wider rows
+// take small chunks and deep rings (fused_pairs_mma.cuh).  GSA_PAIRS_YCH / GSA_PAIRS_YST: tuning knobs.
 template <bool J>
-static const void* pairs_mma_kernel_y_j(int NB, int st) {
-#define GSA_PMY(NBV, STV) if (NB == NBV && st == STV) return (const void*)pairs_mma_kernel<PM_SRC_Y, NBV, 1, STV, J>;
-    GSA_PMY(1, 2) GSA_PMY(1, 3) GSA_PMY(1, 4) GSA_PMY(2, 2) GSA_PMY(2, 3) GSA_PMY(2, 4) GSA_PMY(3, 2) GSA_PMY(3, 3) GSA_PMY(4, 2)
+static const void* pairs_mma_kernel_y_j(int NB, int ch, int st) {
+#define GSA_PMY(NBV, CHV, STV) if (NB == NBV && ch == CHV && st == STV) return (const void*)pairs_mma_kernel<PM_SRC_Y, NBV, CHV, STV, J>;
+#define GSA_PMY_NB(NBV) GSA_PMY(NBV, 32, 2) GSA_PMY(NBV, 32, 3) GSA_PMY(NBV, 16, 3) GSA_PMY(NBV, 16, 4) GSA_PMY(NBV, 16, 6)
+    GSA_PMY_NB(1) GSA_PMY_NB(2) GSA_PMY_NB(3) GSA_PMY_NB(4)
+#undef GSA_PMY_NB
 #undef GSA_PMY
     return nullptr;
 }
 static const void* pairs_mma_kernel_y(int d, size_t* smem, bool jansen = true) {
     const int NB = (d + 7) / 8;
-    int st = pmma_y_stages(NB);
-    if (const char* e = getenv("GSA_PAIRS_YST")) st = std::max(2, std::min(4, atoi(e)));   // tuning knob: stages of the warp tiles
-    if (NB >= 3 && st > 3) st = 3;
-    if (NB == 4) st = 2;
-    *smem = pm_smem_bytes(pm_ring_doubles_y(d, st), NB);
-    return jansen ? pairs_mma_kernel_y_j<true>(NB, st) : pairs_mma_kernel_y_j<false>(NB, st);
+    // measured at d = 20 (profiles/r2_pairs_sweep2.txt): (16, 4) 85 %, (32, 2) 81 %, (16, 3) 79 %, (32, 3) 65 %, (16, 6) 59 % of the HBM
+    // peak -- the deepest ring that still leaves two CTAs per SM
+    int ch = NB == 1 ? 32 : 16, st = NB == 1 ? 3 : 4;
+    if (NB > 1 && pm_smem_bytes(pm_ring_doubles_y(d, 4, 16), NB) > (112u << 10)) st = 3;
+    if (const char* e = getenv("GSA_PAIRS_YCH")) ch = atoi(e) == 32 ? 32 : 16;
+    if (const char* e = getenv("GSA_PAIRS_YST")) st = atoi(e);
+    if (ch == 32) st = st <= 2 ? 2 : 3;
+    else st = st <= 3 ? 3 : st <= 4 ? 4 : 6;
+    *smem = pm_smem_bytes(pm_ring_doubles_y(d, st, ch), NB);
+    return jansen ? pairs_mma_kernel_y_j<true>(NB, ch, st) : pairs_mma_kernel_y_j<false>(NB, ch, st);
 }
 
 static int plan_fused(gsa_handle* h, int model, int d, int nout, int np, bool second, int est, FusedPlan* p, bool gen = false) {

@@ -8,11 +8,15 @@
 // yAB value the B fragment (k = t, column g) of the block pairs rb <= cb.  One DMMA replaces 64 (diagonal blocks: 28 useful)
 // multiply-adds AND the shuffles that a lane-per-coordinate layout would need to bring yBA_k to the lane of yAB_j.
 //
-// Values enter the products shifted by c = yA of the tile's first sample (p = yBA - c, q = yAB - c), so the sums stay of the
-// order of the output's spread, not its mean:
-//     sum (yBA_k yAB_j - yA yB) = [P'_kj - sum fa' fb'] + c [(sum p_k + sum q_j) - (sum fa' + sum fb')],   fa' = yA - c, fb' = yB - c.
+// The products are taken of DIFFERENCES, u_k = yBA_k - yB and w_j = yAB_j - yA (w_j is the difference the first-order term
+// needs anyway, :192), so the sums stay of the order of the output's spread, not its mean, and no separate shift is carried:
+//     sum (yBA_k yAB_j - yA yB) = sum yB w_j + sum yA u_k + sum u_k w_j = V_j + U_k + P_kj
+// with V_j the first-order numerator itself, U_k one more running sum per coordinate and P = sum u w^T the mma product.
+// (Round 1 shifted both operands by a constant c and carried four correction sums; this form needs 7 fewer FP64 instructions per
+// warp step, and the FP64 pipe -- which DMMA shares with DFMA, profiles/r2_dmma_peak.jsonl -- is what bounds these kernels.)
 // The first- and total-order terms are formed per sample exactly as the reference forms them (difference first, :192, :213;
 // Sobol2007 :211 and Homma1996 :207 are one-accumulator estimators too and share the kernel; Janon2014 needs three terms).
+// sum y and sum y^2 (the variance) are accumulated shifted by c = yA of the tile's first sample and un-shifted in double-double.
 //
 // Three sources feed the same engine (template parameter SRC):
 //   * PRODUCT -- product-form models (Sobol G), 8 < d <= 32: lane (g, t) loads coordinate 8*blk+g of rows A_s, B_s (the 8 lanes
@@ -21,10 +25,12 @@
 //   * PRODUCT_TILE -- the same models for even d <= 8 (BASELINE config 3): with a single block the butterfly would dominate, so
 //     lane L evaluates ALL 2d+2 values of sample L of a 32-sample chunk from prefix/suffix products (no shuffles), writes them
 //     to a warp-private tile, and the mma fragments are read back from the tile;
-//   * Y -- a precomputed Y = f(all_points) (estimator-only entry): every warp streams chunks of 32 samples of all 2d+2 blocks
-//     into such a tile (lane = sample: 256 contiguous bytes per block and copy) and reads the fragments from there.
+//   * Y -- a precomputed Y = f(all_points) (estimator-only entry): every warp streams chunks of CH = 16 or 32 samples of all 2d+2
+//     blocks into such a tile (128 / 256 contiguous bytes per block; 16-byte copies that bypass L1 when the blocks are 16-byte
+//     aligned) and reads the fragments from there.
 // Operands of future steps are in flight as cp.async copies (per-thread ring / per-warp tiles): no block-wide barrier.
 #pragma once
+#include <type_traits>
 #include "gsa_common.cuh"
 
 namespace gsa {
@@ -56,34 +62,43 @@ __device__ __forceinline__ void pm_dmma(double& c0, double& c1, double a, double
 }
 
 // Staging.  Product source: every thread keeps ST groups of UN steps of ITS OWN operands (xa, xb per block) in flight as
-// cp.async copies into a private ring (no barrier).  Y source: every WARP keeps ST chunks of 32 samples in flight -- lane L
-// copies sample L of every block (256 contiguous bytes per block and instruction, the access pattern of a streaming read) into
-// a warp-private tile [block][36]; the fragments are then read back conflict-free (pitch 36: lanes (g, t) hit 16 distinct
-// 8-byte bank pairs per half-warp); only __syncwarp() separates the copies from the reads.
+// cp.async copies into a private ring (no barrier).  Y source: every WARP keeps ST chunks of CH samples in flight in a
+// warp-private tile [block][CH] whose 4-sample groups are xor-swizzled with the block number (pm_yidx), so that the copies (a
+// half-warp writes a permutation of one row) and the fragment reads (lanes (g, t) of a half-warp hit 16 distinct 8-byte bank
+// pairs) are both conflict-free without padding; only __syncwarp() separates the copies from the reads.  Small chunks and many
+// stages: the data a warp waits for was requested (ST-1) chunks earlier, and 8-9 warps per SM fit (the round-1 tile -- 32
+// samples, pitch 36, two stages -- spent most of its time waiting for the chunk requested one step earlier: top stall long
+// scoreboard at the wait_group, profiles/r2_prof_stalls.txt).
 constexpr int PM_CH = 32, PM_PITCH = 36;
 template <int NB, int UN, int ST>
 __host__ __device__ constexpr size_t pm_ring_doubles_product() { return (size_t)ST * UN * 2 * NB * PMMA_THREADS; }
-inline size_t pm_ring_doubles_y(int d, int ST) { return (size_t)PMMA_NW * ST * (2 + 2 * d) * PM_PITCH; }
+inline size_t pm_ring_doubles_y(int d, int ST, int CH) { return (size_t)PMMA_NW * ST * (2 + 2 * d) * CH; }
+__host__ __device__ __forceinline__ int pm_yidx(int row, int sl, int CH) { return row * CH + (sl ^ ((row & 3) << 2)); }
 // thread-per-sample product source (d <= 8, even): per warp ST stages of the chunk's raw A and B rows + one tile of model values
 __host__ __device__ inline size_t pm_ring_doubles_tile(int d, int ST) { return (size_t)PMMA_NW * ((size_t)ST * 2 * PM_CH * d + (2 + 2 * d) * PM_PITCH); }
 inline size_t pm_smem_bytes(size_t ring_doubles, int NB) { return sizeof(double) * (ring_doubles + 64 * NB * NB + 4 * 8 * NB + 8); }
 
-// NB = 8-coordinate blocks (d <= 8*NB); UN = warp steps per load group (PRODUCT) or d itself (PRODUCT_TILE); ST = stages in flight
+// NB = 8-coordinate blocks (d <= 8*NB); UN = warp steps per load group (PRODUCT), d itself (PRODUCT_TILE) or the samples per
+// chunk (Y: 16 or 32); ST = stages in flight
 enum { PM_SRC_PRODUCT = 0, PM_SRC_Y = 1, PM_SRC_PRODUCT_TILE = 2 };
+// CTAs per SM the register allocation aims at: what the shared memory of each source leaves room for
+constexpr int pm_min_ctas(int SRC, int NB) { return SRC == PM_SRC_PRODUCT ? (NB <= 3 ? 4 : 1) : (SRC == PM_SRC_PRODUCT_TILE || NB == 1) ? 3 : 2; }
 template <int SRC, int NB, int UN, int ST, bool JANSEN = true>
-__global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
+__global__ void __launch_bounds__(PMMA_THREADS, pm_min_ctas(SRC, NB)) pairs_mma_kernel(PairsArgs a) {
     constexpr bool YSRC = SRC == PM_SRC_Y, TSRC = SRC == PM_SRC_PRODUCT_TILE;
     static_assert(!TSRC || NB == 1, "thread-per-sample evaluation: one 8-coordinate block (UN carries d)");
     constexpr int DU = 8 * NB, NP = NB * (NB + 1) / 2;
     extern __shared__ __align__(16) double pm_sm[];
     const int d = a.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g8 = lane >> 2, t4 = lane & 3;
     const int nblk = 2 + 2 * d;                                   // Y blocks per sample: yA, yB, yAB_1..d, yBA_1..d
-    const size_t ring_doubles = YSRC ? (size_t)PMMA_NW * ST * nblk * PM_PITCH
+    constexpr int YCH = YSRC ? UN : PM_CH;                        // Y source: samples per chunk
+    static_assert(!YSRC || YCH == 16 || YCH == 32, "Y source: chunks of 16 or 32 samples");
+    const size_t ring_doubles = YSRC ? (size_t)PMMA_NW * ST * nblk * YCH
                               : TSRC ? pm_ring_doubles_tile(d, ST) : pm_ring_doubles_product<NB, UN, ST>();
     double* ring = pm_sm + threadIdx.x;                          // product: [ST][UN][2 NB][THREADS]
-    double* wtile = pm_sm + (size_t)warp * ST * nblk * PM_PITCH; // Y: [ST][nblk][PM_PITCH] per warp
+    double* wtile = pm_sm + (size_t)warp * ST * nblk * YCH;      // Y: [ST][nblk][YCH] per warp, swizzled (pm_yidx)
     double* Csm = pm_sm + ring_doubles;                          // [DU][DU]
-    double* Vsm = Csm + DU * DU;                                 // V[DU], E[DU], SP[DU], SQ[DU], sums[8]
+    double* Vsm = Csm + DU * DU;                                 // V[DU], E[DU], U[DU], (unused [DU]), sums[8]
     bool ok[NB];
     double2 cf[NB];
 #pragma unroll
@@ -129,34 +144,37 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
             c = la;
         }
 
-        double V[NB], E[NB], SP[NB], SQ[NB], acc[NP][2];
+        double V[NB], E[NB], U[NB], acc[NP][2];
 #pragma unroll
-        for (int k = 0; k < NB; ++k) V[k] = E[k] = SP[k] = SQ[k] = 0.0;
+        for (int k = 0; k < NB; ++k) V[k] = E[k] = U[k] = 0.0;
 #pragma unroll
         for (int p = 0; p < NP; ++p) acc[p][0] = acc[p][1] = 0.0;
-        double sfa = 0.0, sfb = 0.0, qfa = 0.0, qfb = 0.0, sab = 0.0;   // sums of fa', fb', fa'^2, fb'^2, fa' fb' (this lane's samples)
+        double sfa = 0.0, sfb = 0.0, qfa = 0.0, qfb = 0.0;   // sums of fa' = yA - c, fb' = yB - c, fa'^2, fb'^2 (this lane's samples)
 
         // one warp step: this lane's sample contributes yA, yB and, per block, yAB_i / yBA_i of coordinate i = 8k + g
         auto sample_sums = [&](bool valid, double yA, double yB) {
             const double fa = valid ? yA - c : 0.0, fb = valid ? yB - c : 0.0;
             sfa += fa; sfb += fb;
-            qfa = fma(fa, fa, qfa); qfb = fma(fb, fb, qfb); sab = fma(fa, fb, sab);
+            qfa = fma(fa, fa, qfa); qfb = fma(fb, fb, qfb);
         };
-        auto step = [&](bool valid, double yA, double yB, const double (&yab)[NB], const double (&yba)[NB]) {
-            if constexpr (!TSRC) sample_sums(valid, yA, yB);   // (tile source: added once per sample by the lane that evaluated it)
+        // full_c = std::true_type: every sample of the step is inside the tile -- no validity selects at all.  The lanes of padded
+        // coordinates then carry finite junk (their operands are valid rows or the constant 0.5 with factor 1) into sums and
+        // accumulator rows / columns that are never read (i >= d).
+        auto step = [&](auto full_c, bool valid, double yA, double yB, const double (&yab)[NB], const double (&yba)[NB]) {
+            constexpr bool FULL = decltype(full_c)::value;
+            if constexpr (!TSRC) sample_sums(FULL || valid, yA, yB);   // (tile source: added once per sample by the lane that evaluated it)
             double pv[NB], qv[NB];
 #pragma unroll
             for (int k = 0; k < NB; ++k) {
-                const bool lv = valid && ok[k];
+                const bool lv = FULL || (valid && ok[k]);
                 const double df = lv ? yab[k] - yA : 0.0;
                 V[k] = fma(yB, df, V[k]);            // :192
                 // total-order term: (yA - yAB)^2 (Jansen1999, :213), yA (yA - yAB) (Sobol2007, :211) or yA yAB (Homma1996, :207)
                 if constexpr (JANSEN) E[k] = fma(df, df, E[k]);
                 else E[k] = fma(lv ? yA : 0.0, sobol2007 ? -df : yab[k], E[k]);
-                pv[k] = lv ? yba[k] - c : 0.0;
-                qv[k] = lv ? yab[k] - c : 0.0;
-                SP[k] += pv[k];
-                SQ[k] += qv[k];
+                pv[k] = lv ? yba[k] - yB : 0.0;
+                qv[k] = df;
+                U[k] = fma(yA, pv[k], U[k]);
             }
             int p = 0;
 #pragma unroll
@@ -166,15 +184,41 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
         };
 
         if constexpr (YSRC) {
-            // ---- Y source: warp-private tiles of 32 samples, the warps take chunks round-robin ----
-            const int64_t nchunks = (cnt + PM_CH - 1) / PM_CH;
+            // ---- Y source: warp-private tiles of YCH samples, the warps take chunks round-robin ----
+            const int64_t nchunks = (cnt + YCH - 1) / YCH;
+            int rab[NB], rba[NB];   // tile rows of this lane's yAB / yBA values
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                rab[k] = ok[k] ? 2 + 8 * k + g8 : 0;
+                rba[k] = ok[k] ? 2 + d + 8 * k + g8 : 0;
+            }
+            // 16-byte copies (two samples of a block, around L1) when every block of this tile starts 16-byte aligned
+            const bool wide = a.nout == 1 && (a.n & 1) == 0 && (reinterpret_cast<uintptr_t>(ybase) & 15) == 0;
             auto issue = [&](int64_t ch, int st) {
-                const int64_t s = ch * PM_CH + lane;
-                if (ch < nchunks && s < cnt) {
-                    const double* yp = ybase + (size_t)a.nout * s;
-                    double* dst = wtile + (size_t)st * nblk * PM_PITCH + lane;
+                if (ch < nchunks) {
+                    double* dst = wtile + (size_t)st * nblk * YCH;
+                    if (wide) {
+                        constexpr int LPR = YCH / 2, RPI = 32 / LPR;          // lanes per row, rows per instruction
+                        const int sl = 2 * (lane % LPR);
+                        const int64_t s = ch * YCH + sl;
+                        const double* yp = ybase + s;
+                        if (s + 1 < cnt) {
+#pragma unroll 4
+                            for (int b = lane / LPR; b < nblk; b += RPI)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + pm_yidx(b, sl, YCH))), "l"(yp + ybs * b) : "memory");
+                        } else if (s < cnt) {
+                            for (int b = lane / LPR; b < nblk; b += RPI) pm_cp_async8(dst + pm_yidx(b, sl, YCH), yp + ybs * b);
+                        }
+                    } else {
+                        constexpr int RPI = 32 / YCH;
+                        const int sl = lane % YCH;
+                        const int64_t s = ch * YCH + sl;
+                        if (s < cnt) {
+                            const double* yp = ybase + (size_t)a.nout * s;
 #pragma unroll 6
-                    for (int b = 0; b < nblk; ++b) pm_cp_async8(dst + b * PM_PITCH, yp + ybs * b);
+                            for (int b = lane / YCH; b < nblk; b += RPI) pm_cp_async8(dst + pm_yidx(b, sl, YCH), yp + ybs * b);
+                        }
+                    }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
@@ -186,20 +230,34 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
                 issue(ch + (int64_t)(ST - 1) * PMMA_NW, st == 0 ? ST - 1 : st - 1);
                 asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
                 __syncwarp();   // the other lanes' copies of this chunk are visible
-                const double* tl = wtile + (size_t)st * nblk * PM_PITCH;
+                const double* tl = wtile + (size_t)st * nblk * YCH;
+                if ((ch + 1) * YCH <= cnt) {   // a full chunk: no selects (padded coordinates read row 0)
 #pragma unroll 2
-                for (int q = 0; q < PM_CH / 4; ++q) {
-                    const int sl = 4 * q + t4;
-                    const bool valid = ch * PM_CH + sl < cnt;
-                    double yab[NB], yba[NB];
-                    const double yA = valid ? tl[sl] : c, yB = valid ? tl[PM_PITCH + sl] : c;
+                    for (int q = 0; q < YCH / 4; ++q) {
+                        const int sl = 4 * q + t4;
+                        double yab[NB], yba[NB];
 #pragma unroll
-                    for (int k = 0; k < NB; ++k) {
-                        const bool lv = valid && ok[k];
-                        yab[k] = lv ? tl[(2 + 8 * k + g8) * PM_PITCH + sl] : yA;
-                        yba[k] = lv ? tl[(2 + d + 8 * k + g8) * PM_PITCH + sl] : c;
+                        for (int k = 0; k < NB; ++k) {
+                            yab[k] = tl[pm_yidx(rab[k], sl, YCH)];
+                            yba[k] = tl[pm_yidx(rba[k], sl, YCH)];
+                        }
+                        step(std::true_type{}, true, tl[pm_yidx(0, sl, YCH)], tl[pm_yidx(1, sl, YCH)], yab, yba);
                     }
-                    step(valid, yA, yB, yab, yba);
+                } else {
+#pragma unroll 2
+                    for (int q = 0; q < YCH / 4; ++q) {
+                        const int sl = 4 * q + t4;
+                        const bool valid = ch * YCH + sl < cnt;
+                        double yab[NB], yba[NB];
+                        const double yA = valid ? tl[pm_yidx(0, sl, YCH)] : c, yB = valid ? tl[pm_yidx(1, sl, YCH)] : c;
+#pragma unroll
+                        for (int k = 0; k < NB; ++k) {
+                            const bool lv = valid && ok[k];
+                            yab[k] = lv ? tl[pm_yidx(rab[k], sl, YCH)] : yA;
+                            yba[k] = lv ? tl[pm_yidx(rba[k], sl, YCH)] : c;
+                        }
+                        step(std::false_type{}, valid, yA, yB, yab, yba);
+                    }
                 }
                 st = st + 1 == ST ? 0 : st + 1;
             }
@@ -286,7 +344,7 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
                         double yab[1], yba[1];
                         yab[0] = ytile[(2 + gi) * PM_PITCH + sl];
                         yba[0] = ytile[(2 + TD + gi) * PM_PITCH + sl];
-                        step(true, ytile[sl], ytile[PM_PITCH + sl], yab, yba);
+                        step(std::true_type{}, true, ytile[sl], ytile[PM_PITCH + sl], yab, yba);
                     }
                 } else {
                     phase_a(st, ch * PM_CH + lane < cnt);   // (lanes beyond the tile read stale rows: finite or not, they are masked)
@@ -300,7 +358,7 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
                         double yab[1], yba[1];
                         yab[0] = lv ? ytile[(2 + gi) * PM_PITCH + sl] : yA;
                         yba[0] = lv ? ytile[(2 + TD + gi) * PM_PITCH + sl] : c;
-                        step(valid, yA, yB, yab, yba);
+                        step(std::false_type{}, valid, yA, yB, yab, yba);
                     }
                 }
                 st = st + 1 == ST ? 0 : st + 1;
@@ -329,14 +387,20 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
-            auto consume = [&](int64_t G, int st) {
+            // (the slots of padded coordinates are never copied into: they hold 0.5, and the factor there is the constant 1)
+#pragma unroll
+            for (int k = 0; k < NB; ++k)
+                if (!ok[k])
+                    for (int q = 0; q < ST * UN; ++q) { *slot_of(0, q, 2 * k) = 0.5; *slot_of(0, q, 2 * k + 1) = 0.5; }
+            auto consume = [&](auto full_c, int64_t G, int st) {
+                constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
                 for (int j = 0; j < UN; ++j) {
-                    const bool valid = G * (4 * UN) + t4 + 4 * j < cnt;
+                    const bool valid = FULL || G * (4 * UN) + t4 + 4 * j < cnt;
                     double ga[NB], gb[NB];
 #pragma unroll
                     for (int k = 0; k < NB; ++k) {
-                        const bool lv = valid && ok[k];
+                        const bool lv = FULL || (valid && ok[k]);
                         const double xa = lv ? *slot_of(st, j, 2 * k) : 0.5, xb = lv ? *slot_of(st, j, 2 * k + 1) : 0.5;
                         ga[k] = fma(fabs(xa - 0.5), cf[k].x, cf[k].y);
                         gb[k] = fma(fabs(xb - 0.5), cf[k].x, cf[k].y);
@@ -362,7 +426,7 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
                         yab[k] = gb[k] * (ea[k] * oa);   // A with coordinate i from B (:96-99)
                         yba[k] = ga[k] * (eb[k] * ob);   // B with coordinate i from A (:100-104)
                     }
-                    step(valid, pa, pb, yab, yba);
+                    step(full_c, valid, pa, pb, yab, yba);
                 }
             };
 #pragma unroll
@@ -371,7 +435,8 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
             for (int64_t G = warp; G < ngroups; G += PMMA_NW) {
                 issue(G + (int64_t)(ST - 1) * PMMA_NW, st == 0 ? ST - 1 : st - 1);
                 asm volatile("cp.async.wait_group %0;" ::"n"(ST - 1) : "memory");
-                consume(G, st);
+                if ((G + 1) * (4 * UN) <= cnt) consume(std::true_type{}, G, st);
+                else consume(std::false_type{}, G, st);
                 st = st + 1 == ST ? 0 : st + 1;
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -384,19 +449,16 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
             for (int k = 0; k < NB; ++k) {
                 V[k] += __shfl_xor_sync(0xffffffffu, V[k], x);
                 E[k] += __shfl_xor_sync(0xffffffffu, E[k], x);
-                SP[k] += __shfl_xor_sync(0xffffffffu, SP[k], x);
-                SQ[k] += __shfl_xor_sync(0xffffffffu, SQ[k], x);
+                U[k] += __shfl_xor_sync(0xffffffffu, U[k], x);
             }
             sfa += __shfl_xor_sync(0xffffffffu, sfa, x); sfb += __shfl_xor_sync(0xffffffffu, sfb, x);
             qfa += __shfl_xor_sync(0xffffffffu, qfa, x); qfb += __shfl_xor_sync(0xffffffffu, qfb, x);
-            sab += __shfl_xor_sync(0xffffffffu, sab, x);
         }
         if constexpr (TSRC) {   // every lane added its own samples: finish the reduction over the 8 lane groups
 #pragma unroll
             for (int x = 4; x < 32; x <<= 1) {
                 sfa += __shfl_xor_sync(0xffffffffu, sfa, x); sfb += __shfl_xor_sync(0xffffffffu, sfb, x);
                 qfa += __shfl_xor_sync(0xffffffffu, qfa, x); qfb += __shfl_xor_sync(0xffffffffu, qfb, x);
-                sab += __shfl_xor_sync(0xffffffffu, sab, x);
             }
         }
         __syncthreads();   // nobody still reads the shared arrays of the previous tile
@@ -417,19 +479,18 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
 #pragma unroll
                     for (int k = 0; k < NB; ++k) {
                         const int i = 8 * k + g8;
-                        Vsm[i] += V[k]; Vsm[DU + i] += E[k]; Vsm[2 * DU + i] += SP[k]; Vsm[3 * DU + i] += SQ[k];
+                        Vsm[i] += V[k]; Vsm[DU + i] += E[k]; Vsm[2 * DU + i] += U[k];
                     }
                 }
                 if (lane == 0) {
                     double* q = Vsm + 4 * DU;
-                    q[0] += sfa; q[1] += sfb; q[2] += qfa; q[3] += qfb; q[4] += sab;
+                    q[0] += sfa; q[1] += sfb; q[2] += qfa; q[3] += qfb;
                 }
             }
             __syncthreads();
         }
         {
             const double* q = Vsm + 4 * DU;
-            const double s_ab = q[0] + q[1];
             const int pbase = stat_pair_base(d, a.est);
             for (int i = threadIdx.x; i < d; i += PMMA_THREADS) {
                 rec[stat_v(i)] = Vsm[i];
@@ -437,7 +498,7 @@ __global__ void __launch_bounds__(PMMA_THREADS) pairs_mma_kernel(PairsArgs a) {
             }
             for (int e = threadIdx.x; e < d * d; e += PMMA_THREADS) {
                 const int k = e / d, j = e - k * d;
-                if (k < j) rec[pbase + pair_index(d, k, j)] = (Csm[k * DU + j] - q[4]) + c * ((Vsm[2 * DU + k] + Vsm[3 * DU + j]) - s_ab);
+                if (k < j) rec[pbase + pair_index(d, k, j)] = Csm[k * DU + j] + (Vsm[j] + Vsm[2 * DU + k]);   // P_kj + V_j + U_k
             }
             if (threadIdx.x == 0) {
                 // un-shift exactly (double-double): sum y = s' + m c ; sum y^2 = q' + 2 c s' + m c^2

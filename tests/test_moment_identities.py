@@ -1,6 +1,6 @@
 """CPU checks of the algebra behind the FP64-mma kernels (pure NumPy, no GPU, no oracle): the moment forms of
 csrc/fused_linear.cuh (every estimator term of a linear model from the Gram matrix of the stacked, shifted rows) and the
-shifted-product identity of csrc/fused_pairs_mma.cuh, against direct per-sample evaluation of the reference's formulas
+difference-product identity of csrc/fused_pairs_mma.cuh, against direct per-sample evaluation of the reference's formulas
 (src/sobol_sensitivity.jl:192, :197, :207-224)."""
 import numpy as np
 
@@ -47,18 +47,18 @@ def test_linear_moment_forms_reproduce_every_estimator_term():
                 assert abs(got - want) <= 1e-13 * scale, (o, k, j)
 
 
-def test_shifted_pair_sums_identity():
-    """sum (yBA_k yAB_j - yA yB) = [sum p_k q_j - sum fa' fb'] + c [(sum p_k + sum q_j) - (sum fa' + sum fb')] with
-    p = yBA - c, q = yAB - c, fa' = yA - c, fb' = yB - c  (the decomposition the pair kernels accumulate)."""
+def test_difference_pair_sums_identity():
+    """sum (yBA_k yAB_j - yA yB) = V_j + U_k + P_kj with u_k = yBA_k - yB, w_j = yAB_j - yA, V_j = sum yB w_j (the first-order
+    numerator, :192), U_k = sum yA u_k and P = sum u w^T (the decomposition the pair kernels accumulate; P is the mma product)."""
     rng = np.random.default_rng(4)
     n, d = 300, 5
     yA, yB = 1.0 + 1e-2 * rng.normal(size=n), 1.0 + 1e-2 * rng.normal(size=n)          # mean >> spread
     yAB, yBA = 1.0 + 1e-2 * rng.normal(size=(n, d)), 1.0 + 1e-2 * rng.normal(size=(n, d))
-    c = yA[0]
-    p, q, fa, fb = yBA - c, yAB - c, yA - c, yB - c
-    P = p.T @ q                                                                         # what the DMMAs accumulate
+    u, w = yBA - yB[:, None], yAB - yA[:, None]
+    P = u.T @ w                                                                         # what the DMMAs accumulate
+    V, U = (yB[:, None] * w).sum(0), (yA[:, None] * u).sum(0)
     for k in range(d):
         for j in range(k + 1, d):
             want = (yBA[:, k] * yAB[:, j] - yA * yB).sum()
-            got = (P[k, j] - (fa * fb).sum()) + c * ((p[:, k].sum() + q[:, j].sum()) - (fa.sum() + fb.sum()))
+            got = P[k, j] + (V[j] + U[k])
             assert abs(got - want) <= 1e-15 * n, (k, j, got, want)
