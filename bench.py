@@ -218,6 +218,12 @@ def W_c4(nout=256, d=20):
     return 1.0 + ((o * 31 + i * 17) % 13) / 13.0
 
 
+# measured on a B200 at 1965 MHz (tools/dmma_peak.cu -> profiles/r2_dmma_peak.jsonl): ns per warp instruction per SM sub-partition
+DMMA_NS, DFMA_NS = 8.2, 1.125
+# (DMMA, other FP64 instructions) per warp step in the main loop of the config's kernel
+FP64_PIPE_WORK = {"c4_linear_d20_256out_N2^22": (15, 10), "x_sobolg_d20_N2^21_order2": (6, 57)}
+
+
 def configs_block(g, h, peak, reps=5):
     """BASELINE configs 1-4 (fused path), K1 in steady state, the estimator-only kernel: device-resident inputs, kernel time from
     CUDA events around the dominant kernel (gsa_last_timing), the public call's wall time beside it."""
@@ -252,6 +258,15 @@ def configs_block(g, h, peak, reps=5):
         out[name] = {"rows": rows, "kernel_ms": k, "device_ms": t, "call_wall_ms": 1e3 * w, "launches": nl, "algorithmic_bytes": alg,
                      "achieved_gbs": alg / (k * 1e-3) / 1e9, "frac": alg / (k * 1e-3) / 1e9 / peak, "rows_per_s_call": rows / w,
                      "S1_head": np.ravel(res.S1)[:3].tolist()}
+        if name in FP64_PIPE_WORK:
+            # the kernels whose sums run as mma.sync.m8n8k4.f64: DMMA shares the FP64 pipe with DFMA/DADD/DMUL (measured: the times
+            # add, profiles/r2_dmma_peak.jsonl), so their second roofline is that pipe: per warp step (4 samples) and SM sub-partition,
+            # DMMA_NS per DMMA + DFMA_NS per other FP64 instruction (counts from the SASS main loop, profiles/r2_sass_summary.txt)
+            nd, nf = FP64_PIPE_WORK[name]
+            sms = torch.cuda.get_device_properties(0).multi_processor_count
+            floor_ms = (c["nboot"] * n / 4.0) / (4 * sms) * (nd * DMMA_NS + nf * DFMA_NS) * 1e-6
+            out[name]["fp64_pipe"] = {"dmma_per_warp_step": nd, "other_fp64_per_warp_step": nf, "floor_ms": floor_ms, "frac": floor_ms / k,
+                                      "ceilings": "36.9 TFLOP/s DMMA, 33.7 TFLOP/s DFMA, one shared pipe (profiles/r2_dmma_peak.jsonl)"}
         del A, B
         torch.cuda.empty_cache()
     # eFAST: the reference's test size, and a larger one; wall time of the public call (design in registers + model +

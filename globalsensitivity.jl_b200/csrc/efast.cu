@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "efast.cuh"
+#include "efast_fft.cuh"
 #include "gsa_internal.h"
 
 namespace gsa {
@@ -85,18 +86,47 @@ static int efast_analyze_device(gsa_handle* h, const double* Yd, int nout, int d
     a.g.nlow = (int)(omega[0] / 2);
     a.g.nbins = a.g.nlow + H + (int)(S & 1);
     const int nser = d * nout;
-    // scratch: centred series, moments, powers, results -- one allocation
-    const size_t nC = (size_t)nser * S, nM = 4 * (size_t)nser, nP = (size_t)nser * a.g.nbins, nR = 2 * (size_t)nser;
-    if ((rc = h->ybuf.reserve(sizeof(double) * (nC + nM + nP + nR)))) return rc;
+    // the spectrum: a Stockham FFT when the size factors into 2, 3, 5 (efast_fft.cuh), else the pruned DFT (any size).
+    // GSA_EFAST_DFT=1 forces the DFT (tests compare the two).
+    const int64_t M = (S & 1) ? S : S / 2;
+    std::vector<int> radices;
+    const char* force_dft = getenv("GSA_EFAST_DFT");
+    const bool fft = efast_fft_plan(M, &radices) && !(force_dft && atoi(force_dft) != 0);
+    // scratch: centred series, moments, powers, results, two complex work arrays -- one allocation
+    const size_t nC = ((size_t)nser * S + 1) & ~(size_t)1, nM = 4 * (size_t)nser, nP = ((size_t)nser * a.g.nbins + 1) & ~(size_t)1, nR = 2 * (size_t)nser;
+    const size_t nW = fft ? 2 * (size_t)nser * M : 0;
+    if ((rc = h->ybuf.reserve(sizeof(double) * (nC + nM + nP + nR + 2 * nW)))) return rc;
     a.Y = Yd;
     a.C = h->ybuf.as<double>();
     a.mom = a.C + nC;
     a.power = a.mom + nM;
     a.S1 = a.power + nP;
     a.ST = a.S1 + nser;
+    double* work[2] = {a.ST + nser, a.ST + nser + nW};
     efast_center_kernel<<<nser, 256, 0, h->stream>>>(a);
     GSA_CUDA(cudaEventRecord(h->evk0, h->stream));
-    efast_spectrum_kernel<<<dim3((a.g.nbins + EF_THREADS - 1) / EF_THREADS, nser), EF_THREADS, 0, h->stream>>>(a);
+    if (fft) {
+        EfastFftArgs f{a.C, work[0], M, 1};
+        bool first = true;
+        int w = 0;
+        for (int R : radices) {
+            const dim3 grid((unsigned)((M / R + 255) / 256), nser);
+            const bool real_in = first && (S & 1);
+#define GSA_EF_PASS(RV) case RV: if (real_in) efast_fft_pass_kernel<RV, true><<<grid, 256, 0, h->stream>>>(f); else efast_fft_pass_kernel<RV, false><<<grid, 256, 0, h->stream>>>(f); break;
+            switch (R) { GSA_EF_PASS(2) GSA_EF_PASS(3) GSA_EF_PASS(4) GSA_EF_PASS(5) }
+#undef GSA_EF_PASS
+            f.in = work[w];
+            w ^= 1;
+            f.out = work[w];
+            f.Ls *= R;
+            first = false;
+            h->last_launches++;
+        }
+        EfastPowerArgs pa{f.in, a.power, a.g, M};
+        efast_fft_power_kernel<<<dim3((a.g.nbins + 255) / 256, nser), 256, 0, h->stream>>>(pa);
+    } else {
+        efast_spectrum_kernel<<<dim3((a.g.nbins + EF_THREADS - 1) / EF_THREADS, nser), EF_THREADS, 0, h->stream>>>(a);
+    }
     GSA_CUDA(cudaEventRecord(h->evk1, h->stream));
     h->kernel_timed = true;
     efast_indices_kernel<<<nser, 256, 0, h->stream>>>(a);

@@ -10,11 +10,12 @@
 //                        S1 = sum_{h <= H} |F_{h omega0}|^2 / z,   ST = 1 - sum_{j <= omega0/2} |F_j|^2 / z,   z = sum_j |F_j|^2.
 //
 // The analysis needs omega0/2 + H of the samples/2 bins (samples/16 for H = 4) and the TOTAL power.  The total comes from
-// Parseval's identity on the centred series -- exact, one pass -- so no full transform is needed; the wanted bins are a PRUNED DFT:
-// one thread per bin, the series staged through shared memory and broadcast, the twiddle advanced by a rotation that is re-seeded
-// from the exact integer phase (j*s mod samples -> sincospi) every EF_RESEED samples, so its error stays below 1e-14.  For the
-// reference's sizes (samples = 15000: 941 bins x 15000 samples per series) this is ~0.1 ms of FP64 work per call and embarrassingly
-// parallel over (series, bin); a radix FFT only wins beyond samples ~ 2^20, where it would still be dwarfed by the model.
+// Parseval's identity on the centred series -- exact, one pass.  The wanted bins come from a hand-written mixed-radix Stockham
+// FFT (efast_fft.cuh) when the size factors into 2, 3 and 5 -- 15000 samples x 4 series: 0.03 ms -- and otherwise (primes such
+// as 4099, 15003 = 3^2 * 1667) from the PRUNED DFT below, exact for any size: one thread per bin, the series staged through
+// shared memory and broadcast, the twiddle advanced by a rotation that is re-seeded from the exact integer phase
+// (j*s mod samples -> sincospi) every EF_RESEED samples, so its error stays below 1e-14; O(samples^2 / 16) per series
+// (0.3 ms at 15000 samples, 12 ms at 2^17 x 20 series, where the FFT takes 0.07 ms: profiles/r2_efast_probe.jsonl).
 #pragma once
 #include "gsa_common.cuh"
 #include "models.cuh"

@@ -43,9 +43,12 @@ def _parity(a, b):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("samples,H", [(15000, 4), (15003, 4), (301, 4), (300, 4), (4099, 2), (1 << 16, 6)])
+@pytest.mark.parametrize("samples,H", [(15000, 4), (15003, 4), (301, 4), (300, 4), (4099, 2), (1 << 16, 6), (3000, 4), (1 << 14, 4), (16875, 4), (405, 4),
+                                       (2 * 3 ** 9, 4)])
 def test_efast_analysis_matches_oracle(samples, H):
-    """gsa_efast_all_y_analysis on the GPU (pruned DFT + Parseval) against numpy's rfft restatement, on the same all_y."""
+    """gsa_efast_all_y_analysis on the GPU against numpy's rfft restatement, on the same all_y.  Sizes whose half (even) or whole
+    (odd) factors into 2, 3, 5 take the Stockham FFT (every radix and the real-input first pass are covered here); 15003, 301 and
+    4099 take the pruned DFT."""
     import gsa_loader
     g = gsa_loader.load()
     phi = [0.3, 1.1, 0.7, 1.9]
@@ -60,6 +63,22 @@ def test_efast_analysis_matches_oracle(samples, H):
     ref = ef.efast_analysis(Y - Y.mean(), 4, samples, H)
     res = g.gsa_efast_all_y_analysis(g.eFAST(H), Y, 4, samples)
     assert _parity(res.S1, ref.S1) <= 1e-9 and _parity(res.ST, ref.ST) <= 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("samples", [15000, 16875, 1 << 13, 600])
+def test_efast_fft_and_pruned_dft_agree(samples, monkeypatch):
+    """the two spectrum routes (efast_fft.cuh / efast.cuh) on the same series: 1e-13"""
+    import gsa_loader
+    g = gsa_loader.load()
+    rng = np.random.default_rng(samples)
+    Y = rng.normal(size=(2, samples * 5)) + 3.0
+    fft = g.gsa_efast_all_y_analysis(g.eFAST(4), Y, 5, samples)
+    assert g.default_handle().last_timing()[2] > 3                     # one launch per radix + centre, power, indices
+    monkeypatch.setenv("GSA_EFAST_DFT", "1")
+    dft = g.gsa_efast_all_y_analysis(g.eFAST(4), Y, 5, samples)
+    assert g.default_handle().last_timing()[2] == 3
+    assert _parity(fft.S1, dft.S1) <= 1e-13 and _parity(fft.ST, dft.ST) <= 1e-13, (_parity(fft.S1, dft.S1), _parity(fft.ST, dft.ST))
 
 
 @pytest.mark.gpu

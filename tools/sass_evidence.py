@@ -8,8 +8,8 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 SO = os.path.join(ROOT, "globalsensitivity.jl_b200", "libgsa_cuda.so")
 WANT = [("fused_product_kernel<8, 13, false, true>", "config 5 (8-byte loads)"), ("fused_product_kernel_v2<8, 14, true>", "config 5 (16-byte pair loads)"),
         ("fused_product_kernel<8, 13, true, true>", "config 5, generated design"), ("pairs_mma_kernel<2, 1, 8, 3, true>", "config 3 (tile source)"),
-        ("pairs_mma_kernel<0, 3, 2, 4, true>", "Sobol G d=20 order 2"), ("pairs_mma_kernel<1, 3, 1, 2, true>", "estimator on Y, d=20 order 2"),
-        ("linear_gram_kernel<5, 2, 6>", "config 4"), ("small_kernel<gsa::IshigamiSource<3, true>, 3, true, true>", "config 2"),
+        ("pairs_mma_kernel<0, 3, 2, 3, true>", "Sobol G d=20 order 2"), ("pairs_mma_kernel<1, 3, 16, 4, true>", "estimator on Y, d=20 order 2"),
+        ("linear_gram_kernel<5, 2, 3>", "config 4"), ("small_kernel<gsa::IshigamiSource<3, true>, 3, true, true>", "config 2"),
         ("small_kernel<gsa::IshigamiSource<3, false>, 3, false, true>", "config 1"), ("sobol_design_kernel2", "K1"),
         ("estimator_y_kernel<false>", "estimator on Y, d=100"),
         ("fused_generic_kernel<gsa::SobolGModel, false, true>", "generic kernel (large instantiation)"), ("peer_allreduce_kernel", "K5 stand-alone"),
@@ -55,3 +55,23 @@ for pat, what in WANT:
         mid = idx[len(idx) // 2]
         for l in ins[max(0, mid - 4):mid + 8]:
             print("      " + re.sub(r"\s+/\* 0x[0-9a-f]+ \*/", "", l)[:150])
+    # loops that carry DMMA: instruction mix per trip (the FP64-pipe work per warp step quoted in DESIGN.md / bench.py comes from here)
+    if cnt["DMMA"]:
+        addr = []
+        for l in ins:
+            m = re.search(r"/\*([0-9a-f]{4,6})\*/\s+(.*?);", l)
+            if m:
+                addr.append((int(m.group(1), 16), m.group(2)))
+        for a, t in addr:
+            m2 = re.search(r"BRA\S*\s.*0x([0-9a-f]+)", t)
+            if not m2 or int(m2.group(1), 16) >= a:
+                continue
+            lo = int(m2.group(1), 16)
+            mix = collections.Counter()
+            for b, u in addr:
+                if lo <= b <= a:
+                    w = u.split()
+                    op = (w[1] if w[0].startswith("@") and len(w) > 1 else w[0]).split(".")[0]
+                    mix[op] += 1
+            if mix["DMMA"] and sum(mix.values()) < 700:
+                print(f"   loop {lo:#x}..{a:#x}: {sum(mix.values())} instructions  " + "  ".join(f"{k}={v}" for k, v in mix.most_common(12)))
