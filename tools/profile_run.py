@@ -51,4 +51,7 @@ o, i = np.meshgrid(np.arange(1, 257), np.arange(1, 21), indexing="ij")
 W = 1.0 + ((o * 31 + i * 17) % 13) / 13.0
 A, B = g.generate_design_matrices(1 << 22, np.zeros(20), np.ones(20), 2, device=True, handle=h)
 run(lambda: g.sobol_partials(g.DeviceModel("linear", W), method, A, B, 1 << 22, 0, handle=h))
+del A, B
+# eFAST: design in registers + model, centring, Stockham FFT passes (efast_fft.cuh), power, indices
+run(lambda: g.gsa_efast(g.DeviceModel("sobol_g", list(np.linspace(0, 9, 20))), g.eFAST(), [[0.0, 1.0]] * 20, samples=1 << 17, phi=np.linspace(0.1, 1.9, 20), handle=h))
 print("profile_run done")
