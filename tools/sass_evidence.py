@@ -9,7 +9,7 @@ SO = os.path.join(ROOT, "globalsensitivity.jl_b200", "libgsa_cuda.so")
 WANT = [("fused_product_kernel<8, 13, false, true>", "config 5 (8-byte loads)"), ("fused_product_kernel_v2<8, 14, true>", "config 5 (16-byte pair loads)"),
         ("fused_product_kernel<8, 13, true, true>", "config 5, generated design"), ("pairs_mma_kernel<2, 1, 8, 3, true>", "config 3 (tile source)"),
         ("pairs_mma_kernel<0, 3, 2, 3, true>", "Sobol G d=20 order 2"), ("pairs_mma_kernel<1, 3, 16, 4, true>", "estimator on Y, d=20 order 2"),
-        ("linear_gram_kernel<5, 2, 3>", "config 4"), ("small_kernel<gsa::IshigamiSource<3, true>, 3, true, true>", "config 2"),
+        ("linear_gram_kernel<5, 2, 6>", "config 4"), ("small_kernel<gsa::IshigamiSource<3, true>, 3, true, true>", "config 2"),
         ("small_kernel<gsa::IshigamiSource<3, false>, 3, false, true>", "config 1"), ("sobol_design_kernel2", "K1"),
         ("estimator_y_kernel<false>", "estimator on Y, d=100"),
         ("fused_generic_kernel<gsa::SobolGModel, false, true>", "generic kernel (large instantiation)"), ("peer_allreduce_kernel", "K5 stand-alone"),
