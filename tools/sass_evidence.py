@@ -73,5 +73,5 @@ for pat, what in WANT:
                     w = u.split()
                     op = (w[1] if w[0].startswith("@") and len(w) > 1 else w[0]).split(".")[0]
                     mix[op] += 1
-            if mix["DMMA"] and sum(mix.values()) < 700:
+            if mix["DMMA"] and sum(mix.values()) < 1300:
                 print(f"   loop {lo:#x}..{a:#x}: {sum(mix.values())} instructions  " + "  ".join(f"{k}={v}" for k, v in mix.most_common(12)))
