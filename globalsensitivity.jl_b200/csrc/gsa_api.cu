@@ -468,14 +468,16 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
         const int t_lo = (int)((col0 - (int64_t)g.rep_first * n) / g.ts);
         const int t_hi = (rep_last - g.rep_first) * g.tpr + (int)((valid_hi - 1 - (int64_t)rep_last * n) / g.ts) + 1;
         // one launch per step: stage 2, the exchange and the host copy run in the kernel's last CTA (tail.cuh)
-        // (a replicate of more than TAIL_G groups = 1024 tiles, or an exchange of more than 4096 doubles -- the fused exchange is
-        // the work of ONE CTA -- take the classic launches)
+        // (a shard with more than TAIL_G groups = 1024 launched tiles in a replicate, or an exchange of more than 4096 doubles --
+        // the fused exchange is the work of ONE CTA -- take the classic launches)
         // Measured (tools/tail_probe.py, profiles/r2_tail_probe.txt): the in-kernel tree costs ~20-30 us for one replicate of
         // 444-888 tiles -- about what reduce_tiles + the copy cost as launches of their own, minus their launch gaps and the
         // host's stream synchronisation -- but 2-3x more than the classic sequence for many replicates of few tiles (every
         // replicate's finisher pays its own fences and host write).  So: few replicates only.
+        // (groups with launched tiles per replicate: a shard is a slice of the replicate's tiles)
+        const int launched_groups = std::min(tail_groups_per_replicate(g.tpr), (t_hi - t_lo + TAIL_G - 1) / TAIL_G + 1);
         const bool fuse = want_tail && plan.supports_tail() && !host_in && t_hi > t_lo && !getenv("GSA_NO_TAIL") &&
-                          tail_groups_per_replicate(g.tpr) <= TAIL_G && (!tr->exchange || count <= 4096) &&
+                          launched_groups <= TAIL_G && (!tr->exchange || count <= 4096) &&
                           (nrep <= 4 || getenv("GSA_FORCE_TAIL"));
         if (fuse) {
             TailArgs& t = plan.tail;
@@ -512,9 +514,18 @@ static int partials_impl(gsa_handle* h, const gsa_sobol_opts* o, int model, cons
             GSA_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * count, h->stream));
             zeroed = true;
         }
-        if (!direct && t_lo > 0) GSA_CUDA(cudaMemsetAsync(h->tile_rec.p, 0, sizeof(double) * (size_t)t_lo * recsz, h->stream));
-        if (!direct && t_hi < g.ntiles)
-            GSA_CUDA(cudaMemsetAsync(h->tile_rec.as<double>() + (size_t)t_hi * recsz, 0, sizeof(double) * (size_t)(g.ntiles - t_hi) * recsz, h->stream));
+        // tile records outside the launched range are zero records: all of them for the classic stage 2, under the fused tail
+        // only those that share a group with a launched tile (the tail sums whole groups; the others are never read)
+        int z_lo = 0, z_hi = g.ntiles;
+        if (fuse) {
+            const int r0 = t_lo / g.tpr * g.tpr, r1 = (t_hi - 1) / g.tpr * g.tpr;
+            z_lo = r0 + (t_lo - r0) / TAIL_G * TAIL_G;
+            z_hi = std::min(r1 + g.tpr, r1 + ((t_hi - 1 - r1) / TAIL_G + 1) * TAIL_G);
+        }
+        if (!direct && t_lo > z_lo)
+            GSA_CUDA(cudaMemsetAsync(h->tile_rec.as<double>() + (size_t)z_lo * recsz, 0, sizeof(double) * (size_t)(t_lo - z_lo) * recsz, h->stream));
+        if (!direct && t_hi < z_hi)
+            GSA_CUDA(cudaMemsetAsync(h->tile_rec.as<double>() + (size_t)t_hi * recsz, 0, sizeof(double) * (size_t)(z_hi - t_hi) * recsz, h->stream));
 
         if (!host_in) {
             if ((rc = plan.launch(h, A, B, g, t_lo, t_hi))) return rc;

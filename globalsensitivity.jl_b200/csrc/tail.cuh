@@ -131,7 +131,7 @@ __device__ __forceinline__ void fused_tail_tile_done(const TailArgs& t, int tile
             if (!tail_arrive(t.counters + (size_t)t.nrep * t.ngr + rl, (unsigned)(gl - gf + 1), &s_flag)) return;
             const double* gbase = t.grec + ((size_t)rl * t.ngr + gf) * t.recsz;
             const int ng = gl - gf + 1;
-            if (sums) tail_sum_records<TAIL_G>(gbase, ng, t.recsz, t.recsz, t.nstat, prec, hrec);   // (the host only fuses when ngr <= TAIL_G)
+            if (sums) tail_sum_records<TAIL_G>(gbase, ng, t.recsz, t.recsz, t.nstat, prec, hrec);   // (the host only fuses when at most TAIL_G groups of a replicate have launched tiles)
         }
         if (!tail_arrive(t.counters + (size_t)t.nrep * t.ngr + t.nrep, (unsigned)t.nrep, &s_flag, hrec != nullptr && !(t.dbg & 4))) return;
         // replicates this shard does not touch

@@ -836,6 +836,25 @@ def test_one_call_step_with_fused_tail(monkeypatch):
         assert np.array_equal(np.isnan(getattr(sl, f)), np.isnan(getattr(want, f)))
 
 
+def test_one_call_step_on_a_slice_of_a_long_replicate():
+    """A shard that is one eighth of a long replicate (what each rank of an 8-GPU run holds): the replicate has ~7000 tiles, the
+    shard ~900 of them, starting in the middle of a group -- still ONE launch (the tail counts the groups with launched tiles)."""
+    import torch
+    d, N = 100, 1 << 20
+    a = np.array([0.0, 1.0, 4.5, 9.0] + [99.0] * 96)
+    model, method = g.DeviceModel("sobol_g", a), g.Sobol()
+    h = g.default_handle()
+    for col0, ncols in ((5 * N // 8 + 24, N // 8), (0, N // 8 - 8), (7 * N // 8, N // 8)):
+        A, B = g.generate_design_matrices(N, np.zeros(d), np.ones(d), 2, device=True, col0=col0, ncols=ncols)
+        fused = g.ShardedStep(model, method, A, B, N, col0).run()
+        assert h.last_timing()[2] == 1, h.last_timing()
+        h.set_stream(None)
+        p = g.sobol_partials(model, method, A, B, N, col0)                 # classic launches: kernel, stage 2
+        torch.cuda.synchronize()
+        want = g.sobol_finalize(method, p, d, N)
+        assert_parity(fused, want, what=("slice", col0, ncols))
+
+
 def test_streamed_host_inputs_large():
     """Host designs larger than one streaming chunk (pinned: 256 MB per matrix; pageable: 64 MB): many chunk kernels."""
     import torch
