@@ -224,6 +224,18 @@ DMMA_NS, DFMA_NS = 8.2, 1.125
 FP64_PIPE_WORK = {"c4_linear_d20_256out_N2^22": (15, 10), "x_sobolg_d20_N2^21_order2": (6, 57)}
 
 
+def kernel_sass_hash(lib, mangled):
+    """sha256[:16] of the SASS of one kernel of `lib` (cuobjdump), or None: identifies the kernel code independently of the rest of
+    the library (profiles/r2_traffic.json names the kernel its DRAM traffic was captured from)."""
+    import hashlib, re, subprocess
+    try:
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", mangled, lib], capture_output=True, text=True, timeout=120).stdout
+    except (OSError, subprocess.SubprocessError):
+        return None
+    lines = [l.strip() for l in out.splitlines() if re.search(r"/\*[0-9a-f]{4,5}\*/", l)]
+    return hashlib.sha256("\n".join(lines).encode()).hexdigest()[:16] if lines else None
+
+
 def configs_block(g, h, peak, reps=5):
     """BASELINE configs 1-4 (fused path), K1 in steady state, the estimator-only kernel: device-resident inputs, kernel time from
     CUDA events around the dominant kernel (gsa_last_timing), the public call's wall time beside it."""
@@ -541,7 +553,10 @@ def gpu_arm(args):
             import hashlib
             with open(g.LIB_PATH, "rb") as f:
                 sha = hashlib.sha256(f.read()).hexdigest()[:16]
-            if tr.get("lib_sha256_16") in (None, sha):
+            same = tr.get("lib_sha256_16") in (None, sha)
+            if not same and tr.get("kernel_sass_sha256_16"):     # a rebuilt library: the same kernel code? (compare its SASS)
+                same = kernel_sass_hash(g.LIB_PATH, tr.get("kernel_mangled", "")) == tr["kernel_sass_sha256_16"]
+            if same:
                 traffic, traffic_src = tr["dram_bytes_per_algorithmic_byte"] * alg_bytes, tr["source"]
             else:
                 traffic_src = "profiles/r2_traffic.json was captured from another build of libgsa_cuda.so: not reported"

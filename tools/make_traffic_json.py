@@ -20,7 +20,21 @@ alg = 16.0 * 100 * (1 << log2n)
 with open(os.path.join(ROOT, "globalsensitivity.jl_b200", "libgsa_cuda.so"), "rb") as f:
     sha = hashlib.sha256(f.read()).hexdigest()[:16]
 name, rd, wr = best
+# the kernel's own identity: its mangled name and a hash of its SASS (bench.py falls back to this when the library was rebuilt)
+sys.path.insert(0, ROOT)
+from bench import kernel_sass_hash
+LIB = os.path.join(ROOT, "globalsensitivity.jl_b200", "libgsa_cuda.so")
+syms = subprocess.run(["cuobjdump", "-elf", LIB], capture_output=True, text=True).stdout
+import re
+def norm(n):   # ncu prints "void f<8, 14, 1>(ProductArgs)", c++filt "void gsa::f<8, 14, true>(gsa::ProductArgs)"
+    return n.replace("gsa::", "").replace("true", "1").replace("false", "0").replace(" ", "")
+mangled = ""
+for m in sorted(set(re.findall(r"_ZN3gsa\d+fused_product_kernel\w+", syms))):
+    if norm(subprocess.run(["c++filt", m], capture_output=True, text=True).stdout.strip()) == norm(name):
+        mangled = m
+        break
 print(json.dumps({"fused_product_kernel": {
-    "dram_bytes_per_algorithmic_byte": (rd + wr) / alg, "lib_sha256_16": sha, "kernel": name, "log2n": log2n,
+    "dram_bytes_per_algorithmic_byte": (rd + wr) / alg, "lib_sha256_16": sha, "kernel": name, "kernel_mangled": mangled,
+    "kernel_sass_sha256_16": kernel_sass_hash(LIB, mangled) if mangled else None, "log2n": log2n,
     "source": f"ncu --set full --clock-control none, bench.py --log2n {log2n} (one launch of {name[:60]}): dram__bytes_read.sum "
               f"{rd / 1e9:.6f} GB + dram__bytes_write.sum {wr / 1e9:.6f} GB for {alg / 1e9:.6f} GB algorithmic; {os.path.basename(rep)}"}}, indent=1))
