@@ -113,6 +113,15 @@ function gsa(model::DeviceModel, method::Sobol, A::Matrix{Float64}, B::Matrix{Fl
     return finish()
 end
 
+# Float32 / Float16 designs (reference test/interface_tests.jl:21-31): computed in Float64 on the device, results returned in the
+# element type of the design, as the reference's generic code would.  BigFloat and every other element type have no method here
+# and stay on the reference's own code (they need arithmetic the device does not have).
+function gsa(model::DeviceModel, method::Sobol, A::AbstractMatrix{T}, B::AbstractMatrix{T}; kwargs...) where {T <: Union{Float16, Float32}}
+    r = gsa(model, method, Matrix{Float64}(A), Matrix{Float64}(B); kwargs...)
+    c(x) = x === nothing ? nothing : T.(x)
+    return SobolResult(c(r.S1), c(r.S1_Conf_Int), c(r.S2), c(r.S2_Conf_Int), c(r.ST), c(r.ST_Conf_Int))
+end
+
 # ---- gsa(model, Sobol(...), p_range; samples): design generated on the GPU (reference :407-417) ---------------
 function generate_design_matrices(n::Integer, lb::Vector{Float64}, ub::Vector{Float64}, num_mats::Integer = 2;
                                   handle::Handle = default_handle())
