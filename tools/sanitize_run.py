@@ -47,5 +47,10 @@ g.gsa_sobol_all_y_analysis(g.Sobol(), Y, 100, 4000, handle=h)
 # host (streamed) inputs through the new kernels
 A, B = design(20011, 8)
 g.gsa(sg(8), g.Sobol(order=[0, 1, 2]), A.cpu().numpy(), B.cpu().numpy(), batch=True, handle=h)
+# eFAST: FFT route (even packed size with every radix, odd size with the real-input first pass) and the pruned DFT (a prime size)
+for S in (3000, 405, 1024, 4099):
+    Y = torch.rand((2, S * 5), dtype=torch.float64, device="cuda")
+    g.gsa_efast_all_y_analysis(g.eFAST(4), Y, 5, S, handle=h)
+g.gsa_efast(g.DeviceModel("ishigami", [7.0, 0.1]), g.eFAST(), [[-np.pi, np.pi]] * 4, samples=3000, phi=np.linspace(0.1, 1.9, 4), handle=h)
 torch.cuda.synchronize()
 print("sanitize_run done")
